@@ -1,0 +1,385 @@
+// C ABI (include/slb200.h): argument checks, device gate, error strings, and the host-buffer
+// pipeline (pinned-memory friendly H2D -> kernels -> D2H on a small ring of CUDA streams).
+// Nothing here computes on the CPU: every entry point either launches the sm_100a kernels
+// or fails.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+#include "sl_common.cuh"
+#include "sl_kernels.h"
+
+namespace sl {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return kErrCuda;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct DevInfo { int checked = 0; int ok = 0; int sms = 0; };
+static DevInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+// returns the SM count of the current device, or a negative error
+static int device_gate(int* sms) {
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return kErrDevice; }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevInfo& d = g_dev[dev];
+  if (!d.checked) {
+    int major = 0, minor = 0, n = 0;
+    SL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    SL_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    SL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    d.checked = 1; d.ok = (major == 10 && minor == 0); d.sms = n;
+    if (!d.ok) { d.sms = -(major * 10 + minor); }
+  }
+  if (!d.ok) {
+    set_error("slb200 is built for sm_100a only; device %d is sm_%d (no fallback path exists)", dev, -d.sms);
+    return kErrDevice;
+  }
+  *sms = d.sms;
+  return kOk;
+}
+
+static int check_decode_shape(int B, int F, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive (got %d, %d, %d)", B, H, W); return kErrBadArg; }
+  if (F < 14 || (F - 2) % 4) { set_error("F must be 4n+2 with n >= 3 (got %d)", F); return kErrBadArg; }
+  if ((F - 2) / 4 > 15) { set_error("n = %d bits exceeds the int16 index range (max 15)", (F - 2) / 4); return kErrBadArg; }
+  return kOk;
+}
+
+}  // namespace sl
+
+using namespace sl;
+
+extern "C" {
+
+const char* sl_last_error(void) { return g_err; }
+int sl_version(void) { return 100; }
+int64_t sl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sl_device_check(int device) {
+  if (device >= 0) SL_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  return device_gate(&sms);
+}
+
+int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
+                 size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
+                 int8_t* v_codes, void* stream) {
+  int rc = check_decode_shape(B, F, H, W);
+  if (rc) return rc;
+  if (!frames || !h_idx || !v_idx) { set_error("frames, h_idx, v_idx must be non-null"); return kErrBadArg; }
+  if ((h_codes == nullptr) != (v_codes == nullptr)) { set_error("h_codes and v_codes must be given together"); return kErrBadArg; }
+  const long long npix = (long long)H * W;
+  if (frame_pitch < (size_t)npix) { set_error("frame_pitch smaller than H*W"); return kErrBadArg; }
+  if (B > 1 && scan_pitch < frame_pitch * (size_t)F) { set_error("scan_pitch smaller than F*frame_pitch"); return kErrBadArg; }
+  if (!(eps == eps)) { set_error("eps is NaN"); return kErrBadArg; }
+  int sms = 0;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, h_codes, v_codes,
+                       sms, (cudaStream_t)stream);
+}
+
+int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
+                       double* L_g, void* stream) {
+  int rc = check_decode_shape(1, F, H, W);
+  if (rc) return rc;
+  if (!frames || !L_d || !L_g) { set_error("null buffer"); return kErrBadArg; }
+  if (frame_pitch < (size_t)H * W) { set_error("frame_pitch smaller than H*W"); return kErrBadArg; }
+  int sms = 0;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_decode_parts(frames, F, (long long)H * W, frame_pitch, 0.0, nullptr, nullptr, L_d, L_g, nullptr,
+                             nullptr, sms, (cudaStream_t)stream);
+}
+
+int sl_is_lit(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, const double* L_d,
+              const double* L_g, double eps, int8_t* h_codes, int8_t* v_codes, void* stream) {
+  int rc = check_decode_shape(1, F, H, W);
+  if (rc) return rc;
+  if (!frames || !L_d || !L_g || !h_codes || !v_codes) { set_error("null buffer"); return kErrBadArg; }
+  if (frame_pitch < (size_t)H * W) { set_error("frame_pitch smaller than H*W"); return kErrBadArg; }
+  if (!(eps == eps)) { set_error("eps is NaN"); return kErrBadArg; }
+  int sms = 0;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_decode_parts(frames, F, (long long)H * W, frame_pitch, eps, L_d, L_g, nullptr, nullptr, h_codes,
+                             v_codes, sms, (cudaStream_t)stream);
+}
+
+int sl_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int n, int64_t npix,
+                       size_t run_pitch, int16_t* h_idx, int16_t* v_idx, void* stream) {
+  if (!h_codes || !v_codes || !h_idx || !v_idx) { set_error("null buffer"); return kErrBadArg; }
+  if (R < 1 || n < 1 || n > 15 || npix < 0) { set_error("bad R/n/npix (%d, %d, %lld)", R, n, (long long)npix); return kErrBadArg; }
+  if (R > 1 && run_pitch < (size_t)n * (size_t)npix) { set_error("run_pitch smaller than n*npix"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  if (npix == 0) return kOk;
+  return launch_codes_to_pixels(h_codes, v_codes, R, n, npix, run_pitch, h_idx, v_idx, sms, (cudaStream_t)stream);
+}
+
+size_t sl_cloud_workspace_bytes(int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) return 0;
+  return cloud_workspace_bytes(B, H, W);
+}
+
+int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H, int W,
+                       void* workspace, int64_t* counts, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_compact_offsets(h_idx, v_idx, B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
+}
+
+int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, int B,
+                  int H, int W, int proj_w, int proj_h, const void* workspace, float* cam_pts,
+                  float* proj_pts, uint8_t* rgb, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !cam_pts || !proj_pts) { set_error("null buffer"); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1 || proj_w < 1 || proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_emit_pairs(h_idx, v_idx, white_rgb, B, H, W, proj_w, proj_h, workspace, cam_pts, proj_pts, rgb,
+                           (cudaStream_t)stream);
+}
+
+int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                  const SlCalib* calib, int precision, int B, int H, int W, const void* workspace,
+                  float* xyz, uint8_t* rgb, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !xyz || !calib) { set_error("null buffer"); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
+  if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_emit_cloud(h_idx, v_idx, white_rgb, *calib, precision, B, H, W, workspace, xyz, rgb,
+                           (cudaStream_t)stream);
+}
+
+int sl_triangulate_points(const float* cam_pts, const float* proj_pts, int64_t N,
+                          const SlCalib* calib, int precision, double* out, void* stream) {
+  if (N < 0 || !calib) { set_error("bad argument"); return kErrBadArg; }
+  if (N > 0 && (!cam_pts || !proj_pts || !out)) { set_error("null buffer"); return kErrBadArg; }
+  if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_triangulate_points(cam_pts, proj_pts, N, *calib, precision, out, (cudaStream_t)stream);
+}
+
+size_t sl_filter_workspace_bytes(int64_t N) { return N < 0 ? 0 : filter_workspace_bytes(N); }
+
+int sl_filter_box(const double* pts, const double* colors, int64_t N, double threshold,
+                  double* out_pts, double* out_colors, int64_t* out_count, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  if (N < 0 || !out_count || !workspace) { set_error("bad argument"); return kErrBadArg; }
+  if (N > 0 && (!pts || !out_pts)) { set_error("null buffer"); return kErrBadArg; }
+  if ((colors == nullptr) != (out_colors == nullptr)) { set_error("colors and out_colors must be given together"); return kErrBadArg; }
+  if (workspace_bytes < filter_workspace_bytes(N)) { set_error("workspace too small"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_filter_box(pts, colors, N, threshold, out_pts, out_colors, (long long*)out_count, workspace,
+                           (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-buffer pipeline
+struct SlPipeline {
+  int device = 0, max_batch = 0, F = 0, H = 0, W = 0, sms = 0;
+  static constexpr int kSlots = 3;
+  struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t counted = nullptr;
+    uint8_t* frames = nullptr;   // [F][H][W]
+    uint8_t* white = nullptr;    // [H][W][3]
+    int16_t* h = nullptr;
+    int16_t* v = nullptr;
+    void* ws = nullptr;
+    long long* counts = nullptr;       // device [2]
+    long long* counts_pinned = nullptr; // host pinned [2]
+    float* xyz = nullptr;
+    uint8_t* rgb = nullptr;
+  } slot[kSlots];
+  int8_t* h_codes = nullptr;   // lazily allocated for sl_decode_host with codes
+  int8_t* v_codes = nullptr;
+};
+
+static void pipeline_free(SlPipeline* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (auto& s : p->slot) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFree(s.frames); cudaFree(s.white); cudaFree(s.h); cudaFree(s.v); cudaFree(s.ws);
+    cudaFree(s.counts); cudaFreeHost(s.counts_pinned); cudaFree(s.xyz); cudaFree(s.rgb);
+    if (s.counted) cudaEventDestroy(s.counted);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  cudaFree(p->h_codes); cudaFree(p->v_codes);
+  delete p;
+}
+
+int sl_pipeline_create(SlPipeline** out, int device, int max_batch, int F, int H, int W) {
+  if (!out) { set_error("out is null"); return kErrBadArg; }
+  *out = nullptr;
+  int rc = check_decode_shape(max_batch < 1 ? 0 : 1, F, H, W);
+  if (rc) return rc;
+  if (max_batch < 1) { set_error("max_batch must be >= 1"); return kErrBadArg; }
+  if (device >= 0) SL_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  if ((rc = device_gate(&sms))) return rc;
+  SlPipeline* p = new (std::nothrow) SlPipeline();
+  if (!p) { set_error("out of host memory"); return kErrAlloc; }
+  cudaGetDevice(&p->device);
+  p->max_batch = max_batch; p->F = F; p->H = H; p->W = W; p->sms = sms;
+  const size_t npix = (size_t)H * W;
+  cudaError_t e = cudaSuccess;
+  for (auto& s : p->slot) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.counted, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&s.frames, (size_t)F * npix);
+    if (e == cudaSuccess) e = cudaMalloc(&s.white, npix * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&s.h, npix * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&s.v, npix * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&s.ws, cloud_workspace_bytes(1, H, W));
+    if (e == cudaSuccess) e = cudaMalloc(&s.counts, 2 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&s.counts_pinned, 2 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&s.xyz, npix * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&s.rgb, npix * 3);
+  }
+  if (e != cudaSuccess) {
+    pipeline_free(p);
+    set_error("pipeline allocation failed: %s", cudaGetErrorString(e));
+    return kErrAlloc;
+  }
+  *out = p;
+  return kOk;
+}
+
+void sl_pipeline_destroy(SlPipeline* p) { pipeline_free(p); }
+
+// Scan i goes through slot i % kSlots: H2D -> decode -> offsets -> emit -> D2H(count).  The cloud
+// D2H needs the count (packed host output), so it is issued one step later, after the slot's
+// `counted` event, while the next scans' copies and kernels are already queued on other streams.
+int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host,
+                          int B, const SlCalib* calib, int precision, double eps,
+                          int16_t* h_idx_host, int16_t* v_idx_host, float* xyz_host,
+                          uint8_t* rgb_host, int64_t cap_points, int64_t* counts_host) {
+  if (!p || !frames_host || !calib || !xyz_host || !counts_host) { set_error("null argument"); return kErrBadArg; }
+  if (B < 1 || B > p->max_batch) { set_error("B=%d outside 1..max_batch=%d", B, p->max_batch); return kErrBadArg; }
+  if ((h_idx_host == nullptr) != (v_idx_host == nullptr)) { set_error("h_idx_host and v_idx_host go together"); return kErrBadArg; }
+  if (rgb_host && !white_rgb_host) { set_error("rgb_host needs white_rgb_host"); return kErrBadArg; }
+  if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  SL_CUDA(cudaSetDevice(p->device));
+  const size_t npix = (size_t)p->H * p->W;
+  const size_t stack = (size_t)p->F * npix;
+  const int S = SlPipeline::kSlots;
+  long long total = 0;
+  bool overflow = false;
+  int rc = kOk;
+
+  auto drain = [&](int i) -> int {   // finish scan i: wait for its count, copy its cloud out
+    auto& s = p->slot[i % S];
+    SL_CUDA(cudaEventSynchronize(s.counted));
+    const long long n = s.counts_pinned[0];
+    counts_host[i] = n;
+    if (total + n > cap_points) overflow = true;
+    if (!overflow && n > 0) {
+      SL_CUDA(cudaMemcpyAsync(xyz_host + (size_t)total * 3, s.xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+      if (rgb_host)
+        SL_CUDA(cudaMemcpyAsync(rgb_host + (size_t)total * 3, s.rgb, (size_t)n * 3, cudaMemcpyDeviceToHost, s.stream));
+    }
+    total += n;
+    return kOk;
+  };
+
+  for (int i = 0; i < B && rc == kOk; ++i) {
+    if (i >= S) {                 // the slot is reused: scan i-S must be on its way out first.
+      // drain() queues that scan's D2H on the slot's stream, so stream order protects the
+      // slot's buffers from the copies queued next.
+      if ((rc = drain(i - S)) != kOk) break;
+    }
+    auto& s = p->slot[i % S];
+    SL_CUDA(cudaMemcpyAsync(s.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, s.stream));
+    if (white_rgb_host)
+      SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host + (size_t)i * npix * 3, npix * 3, cudaMemcpyHostToDevice, s.stream));
+    rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, p->sms, s.stream);
+    if (rc) break;
+    if (h_idx_host) {
+      SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, s.h, npix * 2, cudaMemcpyDeviceToHost, s.stream));
+      SL_CUDA(cudaMemcpyAsync(v_idx_host + (size_t)i * npix, s.v, npix * 2, cudaMemcpyDeviceToHost, s.stream));
+    }
+    rc = launch_compact_offsets(s.h, s.v, 1, p->H, p->W, s.ws, s.counts, s.stream);
+    if (rc) break;
+    SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
+    rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, 1, p->H, p->W, s.ws,
+                           s.xyz, (white_rgb_host && rgb_host) ? s.rgb : nullptr, s.stream);
+    if (rc) break;
+    SL_CUDA(cudaEventRecord(s.counted, s.stream));
+  }
+  if (rc == kOk) {
+    for (int i = (B > S ? B - S : 0); i < B; ++i)
+      if ((rc = drain(i)) != kOk) break;
+  }
+  for (auto& s : p->slot) {
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess && rc == kOk) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (rc != kOk) return rc;
+  counts_host[B] = total;
+  if (overflow) { set_error("cloud of %lld points exceeds cap_points=%lld", total, (long long)cap_points); return kErrBadArg; }
+  return kOk;
+}
+
+int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
+                   int16_t* h_idx_host, int16_t* v_idx_host, int8_t* h_codes_host,
+                   int8_t* v_codes_host) {
+  if (!p || !frames_host || !h_idx_host || !v_idx_host) { set_error("null argument"); return kErrBadArg; }
+  if (B < 1 || B > p->max_batch) { set_error("B=%d outside 1..max_batch=%d", B, p->max_batch); return kErrBadArg; }
+  if ((h_codes_host == nullptr) != (v_codes_host == nullptr)) { set_error("codes buffers go together"); return kErrBadArg; }
+  SL_CUDA(cudaSetDevice(p->device));
+  const size_t npix = (size_t)p->H * p->W;
+  const size_t stack = (size_t)p->F * npix;
+  const int n = (p->F - 2) / 4;
+  if (h_codes_host && !p->h_codes) {
+    SL_CUDA(cudaMalloc(&p->h_codes, (size_t)n * npix));
+    SL_CUDA(cudaMalloc(&p->v_codes, (size_t)n * npix));
+  }
+  const int S = SlPipeline::kSlots;
+  int rc = kOk;
+  for (int i = 0; i < B; ++i) {
+    auto& s = p->slot[i % S];
+    cudaStream_t st = s.stream;
+    if (h_codes_host) {   // the code planes are single-buffered: serialise on them
+      st = p->slot[0].stream;
+    }
+    auto& u = h_codes_host ? p->slot[0] : s;
+    SL_CUDA(cudaMemcpyAsync(u.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, st));
+    rc = launch_decode(u.frames, 1, p->F, (long long)npix, npix, stack, eps, u.h, u.v,
+                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, p->sms, st);
+    if (rc) break;
+    SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, u.h, npix * 2, cudaMemcpyDeviceToHost, st));
+    SL_CUDA(cudaMemcpyAsync(v_idx_host + (size_t)i * npix, u.v, npix * 2, cudaMemcpyDeviceToHost, st));
+    if (h_codes_host) {
+      SL_CUDA(cudaMemcpyAsync(h_codes_host + (size_t)i * n * npix, p->h_codes, (size_t)n * npix, cudaMemcpyDeviceToHost, st));
+      SL_CUDA(cudaMemcpyAsync(v_codes_host + (size_t)i * n * npix, p->v_codes, (size_t)n * npix, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  for (auto& s : p->slot) {
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess && rc == kOk) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  return rc;
+}
+
+}  // extern "C"

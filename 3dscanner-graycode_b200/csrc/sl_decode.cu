@@ -1,0 +1,329 @@
+// Stage 1: fused Gray-code decode kernels (sm_100a).
+//
+// K1  decode_tma_kernel     persistent, one CTA per SM.  A producer warp streams row tiles of
+//                           all F frames into a ring of shared-memory stages with TMA bulk copies
+//                           (cp.async.bulk + mbarrier complete_tx); consumer warps read them as
+//                           conflict-free 32-bit words (4 pixels / thread), keep every per-pixel
+//                           decision in registers as byte-SWAR flags and write two int16 indices.
+//                           Bound: HBM.  Algorithmic bytes / pixel = F + 4.
+// K1g decode_generic_kernel any alignment / any eps: direct loads, fp64 compares exactly as
+//                           scanner/grayCode/decode_codes.py:172-182 writes them.
+// K1m codes_to_pixels_kernel run merge (src/3-capture_decode.py:95-96) + Gray->decimal (:99-100).
+#include "sl_common.cuh"
+#include "sl_decode_quad.cuh"
+#include "sl_kernels.h"
+
+namespace sl {
+
+// ------------------------------------------------------------------ K1 configuration
+constexpr int kTilePx = 1024;                 // pixels per stage row (bytes per frame per stage)
+constexpr int kGroups = 2;                    // consumer groups, alternate tiles
+constexpr int kWarpsPerGroup = kTilePx / 4 / 32;   // 8 warps * 32 lanes * 4 px = 1024 px
+constexpr int kConsumerWarps = kGroups * kWarpsPerGroup;
+constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;   // + 1 producer warp
+constexpr int kMaxStages = 4;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct DecodeArgs {
+  const uint8_t* frames;
+  size_t frame_pitch, scan_pitch;
+  int16_t* h_idx;
+  int16_t* v_idx;
+  int8_t* h_codes;
+  int8_t* v_codes;
+  long long npix;        // pixels per scan
+  long long npix16;      // npix rounded down to a multiple of 16 (TMA part)
+  long long total_tiles; // B * tiles_per_scan
+  int tiles_per_scan;
+  int n, F, e, stages;
+};
+
+template <int NB, bool CODES>
+__global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const DecodeArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int n = NB ? NB : a.n;
+  const int F = 4 * n + 2;
+  const int stages = a.stages;
+  const uint32_t stage_bytes = (uint32_t)F * kTilePx;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  // bars[0..stages) = full, bars[stages..2*stages) = empty
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[stages + s]), kWarpsPerGroup);
+    }
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------ producer (one lane)
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
+        const long long b = t / a.tiles_per_scan;
+        const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
+        const long long rem = a.npix16 - px0;
+        const uint32_t bytes = (uint32_t)(rem < kTilePx ? rem : kTilePx);
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_arrive_expect_tx(full, bytes * (uint32_t)F);
+        const uint8_t* src = a.frames + (size_t)b * a.scan_pitch + (size_t)px0;
+        const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+        for (int f = 0; f < F; ++f)
+          bulk_g2s(dst + (uint32_t)f * kTilePx, src + (size_t)f * a.frame_pitch, bytes, full, pol);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  const int group = warp / kWarpsPerGroup;
+  const int off = ((warp - group * kWarpsPerGroup) * 32 + lane) * 4;   // pixel offset in tile
+  long long it = group;
+  for (long long t = (long long)blockIdx.x + (long long)group * gridDim.x; t < a.total_tiles;
+       t += (long long)kGroups * gridDim.x, it += kGroups) {
+    const int s = (int)(it % stages);
+    const uint32_t ph = (uint32_t)((it / stages) & 1);
+    mbar_wait(smem_u32(&bars[s]), ph);
+
+    const long long b = t / a.tiles_per_scan;
+    const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
+    const long long rem = a.npix16 - px0;
+    const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
+    if (off < cnt) {
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + (off >> 2);
+      auto ld = [&](int f) { return base[f * (kTilePx / 4)]; };
+      const long long px = px0 + off;
+      int8_t* hc = CODES ? a.h_codes + (size_t)b * n * a.npix + px : nullptr;
+      int8_t* vc = CODES ? a.v_codes + (size_t)b * n * a.npix + px : nullptr;
+      auto st = [&](int axis, int bit, uint32_t tri) {
+        int8_t* dst = (axis ? vc : hc) + (size_t)bit * a.npix;
+        *reinterpret_cast<uint32_t*>(dst) = tri;
+      };
+      const QuadOut o = decode_quad<NB, CODES>(ld, st, n, a.e);
+      st_global_v2(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23);
+      st_global_v2(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));
+  }
+}
+
+// ------------------------------------------------------------------ K1g generic
+struct GenericArgs {
+  const uint8_t* frames;
+  size_t frame_pitch, scan_pitch;
+  int16_t* h_idx;
+  int16_t* v_idx;
+  int8_t* h_codes;
+  int8_t* v_codes;
+  long long npix, px_begin, px_end;   // per-scan pixel range [px_begin, px_end)
+  int n, B;
+  double eps;
+  const double* ld_in;    // nullable: caller-supplied L_d / L_g (get_is_lit, decode_codes.py:125)
+  const double* lg_in;
+  double* ld_out;         // nullable: get_direct_indirect outputs (decode_codes.py:90-122)
+  double* lg_out;
+};
+
+__device__ __forceinline__ int classify_fp64(double p, double q, double ld, double lge, bool a, double eps) {
+  // decode_codes.py:172-182, later rule wins.  Every sum is a single rounded fp64 add.
+  const double pe = dadd(p, eps), qe = dadd(q, eps);
+  int r = -1;
+  if (a && p > qe) r = 1;
+  if (a && pe < q) r = 0;
+  if (pe < ld && q > lge) r = 0;
+  if (p > lge && qe < ld) r = 1;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) decode_generic_kernel(const GenericArgs a) {
+  const long long span = a.px_end - a.px_begin;
+  const long long total = span * a.B;
+  const int n = a.n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / span;
+    const long long px = a.px_begin + (i - b * span);
+    const uint8_t* f0 = a.frames + (size_t)b * a.scan_pitch + (size_t)px;
+    auto ld = [&](int f) { return (double)__ldg(f0 + (size_t)f * a.frame_pitch); };
+    const double black = ld(0), white = ld(1);
+    double lmax = ld(2 + 2 * (n - 1)), lmin = ld(3);
+    lmax = fmax(lmax, ld(2 + 2 * (n - 2)));  lmax = fmax(lmax, ld(2 + 2 * (n - 3)));
+    lmax = fmax(lmax, ld(2 + 2 * n + 2 * (n - 1)));
+    lmax = fmax(lmax, ld(2 + 2 * n + 2 * (n - 2)));
+    lmax = fmax(lmax, ld(2 + 2 * n + 2 * (n - 3)));
+    lmin = fmin(lmin, ld(5));  lmin = fmin(lmin, ld(7));
+    lmin = fmin(lmin, ld(3 + 2 * n));  lmin = fmin(lmin, ld(5 + 2 * n));  lmin = fmin(lmin, ld(7 + 2 * n));
+    const double b_inv = ddiv(white, dadd(white, black));               // decode_codes.py:113
+    double l_d = dmul(dsub(lmax, lmin), b_inv);                          // :119
+    double l_g = dmul(dmul(2.0, dsub(lmax, l_d)), b_inv);                // :120
+    if (a.ld_out) {
+      a.ld_out[(size_t)b * a.npix + px] = l_d;
+      a.lg_out[(size_t)b * a.npix + px] = l_g;
+      if (!a.h_idx) continue;
+    }
+    if (a.ld_in) {
+      l_d = a.ld_in[(size_t)b * a.npix + px];
+      l_g = a.lg_in[(size_t)b * a.npix + px];
+    }
+    const double lge = dadd(l_g, a.eps);
+    const bool big = l_d > lge;
+
+    uint32_t gh = 0, gv = 0;
+    bool okh = true, okv = true;
+    for (int j = 0; j < n; ++j) {        // column bits, MSB first
+      const int r = classify_fp64(ld(2 + 2 * j), ld(2 + 2 * n + 2 * j), l_d, lge, big, a.eps);
+      okh &= (r >= 0);
+      gh = (gh << 1) | (uint32_t)(r > 0);
+      if (a.h_codes) a.h_codes[((size_t)b * n + j) * a.npix + px] = (int8_t)r;
+    }
+    for (int k = n - 1; k >= 0; --k) {   // row bits are stored LSB first
+      const int r = classify_fp64(ld(3 + 2 * k), ld(3 + 2 * n + 2 * k), l_d, lge, big, a.eps);
+      okv &= (r >= 0);
+      gv = (gv << 1) | (uint32_t)(r > 0);
+      if (a.v_codes) a.v_codes[((size_t)b * n + k) * a.npix + px] = (int8_t)r;
+    }
+    if (a.h_idx) {
+      a.h_idx[(size_t)b * a.npix + px] = okh ? (int16_t)gray_to_binary16(gh) : (int16_t)-1;
+      a.v_idx[(size_t)b * a.npix + px] = okv ? (int16_t)gray_to_binary16(gv) : (int16_t)-1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K1m merge + convert
+__global__ void __launch_bounds__(256) codes_to_pixels_kernel(const int8_t* __restrict__ h_codes,
+                                                               const int8_t* __restrict__ v_codes,
+                                                               int R, int n, long long npix,
+                                                               size_t run_pitch,
+                                                               int16_t* __restrict__ h_idx,
+                                                               int16_t* __restrict__ v_idx) {
+  for (long long px = blockIdx.x * (long long)blockDim.x + threadIdx.x; px < npix;
+       px += (long long)gridDim.x * blockDim.x) {
+    uint32_t gh = 0, gv = 0;
+    bool okh = true, okv = true;
+    for (int j = 0; j < n; ++j) {
+      int mh = -1, mv = -1;
+      for (int r = 0; r < R; ++r) {     // np.max over runs: 1 > 0 > -1
+        mh = max(mh, (int)h_codes[(size_t)r * run_pitch + (size_t)j * npix + px]);
+        mv = max(mv, (int)v_codes[(size_t)r * run_pitch + (size_t)(n - 1 - j) * npix + px]);
+      }
+      okh &= (mh >= 0);  okv &= (mv >= 0);
+      gh = (gh << 1) | (uint32_t)(mh > 0);
+      gv = (gv << 1) | (uint32_t)(mv > 0);
+    }
+    h_idx[px] = okh ? (int16_t)gray_to_binary16(gh) : (int16_t)-1;
+    v_idx[px] = okv ? (int16_t)gray_to_binary16(gv) : (int16_t)-1;
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+template <int NB, bool CODES>
+static int launch_tma(const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+  auto k = decode_tma_kernel<NB, CODES>;
+  SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, kDecodeThreads, smem, st>>>(a);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+template <bool CODES>
+static int dispatch_tma(const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+  switch (a.n) {
+    case 8:  return launch_tma<8, CODES>(a, grid, smem, st);
+    case 9:  return launch_tma<9, CODES>(a, grid, smem, st);
+    case 10: return launch_tma<10, CODES>(a, grid, smem, st);
+    case 11: return launch_tma<11, CODES>(a, grid, smem, st);
+    case 12: return launch_tma<12, CODES>(a, grid, smem, st);
+    default: return launch_tma<0, CODES>(a, grid, smem, st);
+  }
+}
+
+int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
+                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
+                  int8_t* v_codes, int num_sms, cudaStream_t st) {
+  const int n = (F - 2) / 4;
+  const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
+  const bool aligned = ((uintptr_t)frames % 16 == 0) && (frame_pitch % 16 == 0) &&
+                       (scan_pitch % 16 == 0) && ((uintptr_t)h_idx % 8 == 0) &&
+                       ((uintptr_t)v_idx % 8 == 0) && (npix % 4 == 0 || B == 1) &&
+                       (!h_codes || (((uintptr_t)h_codes % 4 == 0) && ((uintptr_t)v_codes % 4 == 0) &&
+                                     npix % 4 == 0));
+  long long tma_px = (int_eps && aligned) ? (npix & ~15LL) : 0;
+
+  if (tma_px > 0) {
+    DecodeArgs a;
+    a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
+    a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
+    a.npix = npix; a.npix16 = tma_px;
+    a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
+    a.total_tiles = (long long)a.tiles_per_scan * B;
+    a.n = n; a.F = F; a.e = (int)eps;
+    const size_t stage_bytes = (size_t)F * kTilePx;
+    int stages = (int)((kSmemBudget - 256) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    stages -= stages % kGroups;
+    if (stages < kGroups) { tma_px = 0; }
+    else {
+      a.stages = stages;
+      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+      const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
+      const int rc = h_codes ? dispatch_tma<true>(a, grid, smem, st) : dispatch_tma<false>(a, grid, smem, st);
+      if (rc != kOk) return rc;
+    }
+  }
+  if (tma_px < npix) {
+    GenericArgs g;
+    g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = scan_pitch;
+    g.h_idx = h_idx; g.v_idx = v_idx; g.h_codes = h_codes; g.v_codes = v_codes;
+    g.npix = npix; g.px_begin = tma_px; g.px_end = npix; g.n = n; g.B = B; g.eps = eps;
+    g.ld_in = g.lg_in = nullptr; g.ld_out = g.lg_out = nullptr;
+    const long long total = (npix - tma_px) * B;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+    decode_generic_kernel<<<(int)blocks, 256, 0, st>>>(g);
+    count_launch();
+    SL_CUDA(cudaGetLastError());
+  }
+  return kOk;
+}
+
+// get_direct_indirect (ld_out/lg_out) and get_is_lit with caller-supplied L_d/L_g (ld_in/lg_in):
+// the reference API lets the two halves of get_codes be called separately.
+int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t frame_pitch, double eps,
+                        const double* ld_in, const double* lg_in, double* ld_out, double* lg_out,
+                        int8_t* h_codes, int8_t* v_codes, int num_sms, cudaStream_t st) {
+  GenericArgs g;
+  g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = 0;
+  g.h_idx = nullptr; g.v_idx = nullptr; g.h_codes = h_codes; g.v_codes = v_codes;
+  g.npix = npix; g.px_begin = 0; g.px_end = npix; g.n = (F - 2) / 4; g.B = 1; g.eps = eps;
+  g.ld_in = ld_in; g.lg_in = lg_in; g.ld_out = ld_out; g.lg_out = lg_out;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  if (blocks < 1) return kOk;
+  decode_generic_kernel<<<(int)blocks, 256, 0, st>>>(g);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int n,
+                           long long npix, size_t run_pitch, int16_t* h_idx, int16_t* v_idx,
+                           int num_sms, cudaStream_t st) {
+  long long blocks = (npix + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  codes_to_pixels_kernel<<<(int)blocks, 256, 0, st>>>(h_codes, v_codes, R, n, npix, run_pitch, h_idx, v_idx);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace sl

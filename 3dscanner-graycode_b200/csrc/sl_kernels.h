@@ -1,0 +1,48 @@
+// Internal launcher interface between the kernel translation units and the C ABI (sl_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/slb200.h"
+
+namespace sl {
+
+void count_launch();   // bumps the process-wide kernel launch counter
+
+// ---- stage 1 (sl_decode.cu)
+int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
+                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
+                  int8_t* v_codes, int num_sms, cudaStream_t st);
+int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t frame_pitch, double eps,
+                        const double* ld_in, const double* lg_in, double* ld_out, double* lg_out,
+                        int8_t* h_codes, int8_t* v_codes, int num_sms, cudaStream_t st);
+int launch_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int n,
+                           long long npix, size_t run_pitch, int16_t* h_idx, int16_t* v_idx,
+                           int num_sms, cudaStream_t st);
+
+// ---- stage 2 (sl_cloud.cu)
+struct CloudWorkspace {      // views into the caller's workspace buffer
+  uint32_t* band_cnt;        // [B][bands][W]  count, then exclusive prefix down the column
+  uint32_t* col_tot;         // [B][W]
+  long long* col_base;       // [B][W] packed offset of the first point of column x of scan b
+  int bands;
+};
+size_t cloud_workspace_bytes(int B, int H, int W);
+CloudWorkspace carve_workspace(void* ws, int B, int H, int W);
+
+int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int W, void* ws,
+                           long long* counts, cudaStream_t st);
+int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
+                      int proj_w, int proj_h, const void* ws, float* cam_pts, float* proj_pts,
+                      uint8_t* rgb, cudaStream_t st);
+int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
+                      int precision, int B, int H, int W, const void* ws, float* xyz, uint8_t* rgb,
+                      cudaStream_t st);
+int launch_triangulate_points(const float* cam_pts, const float* proj_pts, long long N,
+                              const SlCalib& calib, int precision, double* out, cudaStream_t st);
+size_t filter_workspace_bytes(long long N);
+int launch_filter_box(const double* pts, const double* colors, long long N, double threshold,
+                      double* out_pts, double* out_colors, long long* out_count, void* ws,
+                      cudaStream_t st);
+
+}  // namespace sl

@@ -1,0 +1,477 @@
+"""Torch-tensor front end of the C ABI.
+
+PyTorch is used for device memory, streams and dtype plumbing only; every function
+here ends in a call into ``libslb200.so``.  Reference citations are relative to the
+reference repository (guillaume-charron/3DScanner-GrayCode).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import SL_PREC_FP32, SL_PREC_FP64, SlCalib, check, lib
+
+_PREC = {"fp32": SL_PREC_FP32, "fp64": SL_PREC_FP64, SL_PREC_FP32: SL_PREC_FP32, SL_PREC_FP64: SL_PREC_FP64}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("slb200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def launch_count() -> int:
+    """Kernels launched by the extension in this process."""
+    return int(lib().sl_launch_count())
+
+
+# --------------------------------------------------------------------------- calibration
+@dataclass
+class Calibration:
+    """Calibration in the form the kernels take.  ``proj_mtx`` is ALREADY scaled to the
+    panel size (scanner/triangulation/triangulate.py:28-33)."""
+    cam_mtx: np.ndarray
+    cam_dist: np.ndarray
+    proj_mtx: np.ndarray
+    proj_dist: np.ndarray
+    proj_R: np.ndarray
+    proj_T: np.ndarray
+    proj_size: Tuple[int, int]
+
+    @classmethod
+    def from_reference(cls, cam_mtx, cam_dist, proj_mtx, proj_dist, proj_R, proj_T,
+                       proj_size=(1920, 1080), proj_calib_size=(1920, 1080)) -> "Calibration":
+        pm = np.array(proj_mtx, dtype=np.float64, copy=True)
+        pm[0, :] = pm[0, :] * (proj_size[0] / proj_calib_size[0])     # triangulate.py:30-33
+        pm[1, :] = pm[1, :] * (proj_size[1] / proj_calib_size[1])
+        return cls(np.asarray(cam_mtx, np.float64), np.asarray(cam_dist, np.float64), pm,
+                   np.asarray(proj_dist, np.float64), np.asarray(proj_R, np.float64),
+                   np.asarray(proj_T, np.float64), (int(proj_size[0]), int(proj_size[1])))
+
+    def struct(self) -> SlCalib:
+        s = SlCalib()
+
+        def fill(dst, src, n, what):
+            a = np.asarray(src, dtype=np.float64).ravel()
+            if a.size > n:
+                raise ValueError(f"{what}: at most {n} values supported, got {a.size}")
+            for i in range(n):
+                dst[i] = float(a[i]) if i < a.size else 0.0
+
+        def mat(dst, src, what):
+            a = np.asarray(src, dtype=np.float64)
+            if a.shape != (3, 3):
+                raise ValueError(f"{what} must be 3x3")
+            for i in range(9):
+                dst[i] = float(a.flat[i])
+
+        mat(s.cam_K, self.cam_mtx, "cam_mtx")
+        mat(s.proj_K, self.proj_mtx, "proj_mtx")
+        mat(s.R, self.proj_R, "proj_R")
+        fill(s.cam_dist, self.cam_dist, 8, "cam_dist")
+        fill(s.proj_dist, self.proj_dist, 8, "proj_dist")
+        t = np.asarray(self.proj_T, dtype=np.float64).reshape(-1)
+        if t.size != 3:
+            raise ValueError("proj_T must hold 3 values")
+        for i in range(3):
+            s.T[i] = float(t[i])
+        s.proj_w, s.proj_h = int(self.proj_size[0]), int(self.proj_size[1])
+        return s
+
+
+# --------------------------------------------------------------------------- inputs
+def as_u8_stack(images, device=None) -> torch.Tensor:
+    """Frame stack -> contiguous uint8 CUDA tensor.
+
+    The reference feeds float64 frames holding integer grey levels
+    (src/3-capture_decode.py:66-70).  Float input is accepted only if every value is an
+    integer in 0..255 -- anything else would silently diverge from the reference's fp64
+    arithmetic, so it raises instead.
+    """
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if isinstance(images, torch.Tensor):
+        t = images
+    else:
+        a = np.asarray(images)
+        if a.dtype == object:
+            raise TypeError("frame stack must be numeric")
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype == torch.uint8:
+        return t.to(dev).contiguous()
+    if t.dtype == torch.bool:
+        raise TypeError("boolean frame stack")
+    t = t.to(dev)
+    u = t.to(torch.uint8) if not t.dtype.is_floating_point else t.clamp(0, 255).to(torch.uint8)
+    if not bool((u.to(t.dtype) == t).all()):
+        raise ValueError("frame stack must hold integer grey levels in 0..255 "
+                         "(the B200 path computes on uint8 samples)")
+    return u.contiguous()
+
+
+def _stack_dims(frames: torch.Tensor):
+    if frames.dim() == 3:
+        f, h, w = frames.shape
+        return 1, f, h, w, False
+    if frames.dim() == 4:
+        b, f, h, w = frames.shape
+        return b, f, h, w, True
+    raise ValueError("frames must be (F,H,W) or (B,F,H,W)")
+
+
+def _check_stack(frames: torch.Tensor):
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8):
+        raise TypeError("frames must be a CUDA uint8 tensor (use as_u8_stack)")
+    if not frames.is_contiguous():
+        raise ValueError("frames must be contiguous")
+
+
+# --------------------------------------------------------------------------- stage 1
+def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """Fused decode: ``(F,H,W)`` / ``(B,F,H,W)`` uint8 -> ``h_pixels, v_pixels`` int16, -1 invalid.
+
+    Replaces get_codes + the per-pixel gray_to_decimal loops
+    (scanner/grayCode/decode_codes.py:231-248, src/3-capture_decode.py:99-100).
+    """
+    _check_stack(frames)
+    b, f, h, w, batched = _stack_dims(frames)
+    shape = (b, h, w) if batched else (h, w)
+    if out is None:
+        h_idx = torch.empty(shape, dtype=torch.int16, device=frames.device)
+        v_idx = torch.empty(shape, dtype=torch.int16, device=frames.device)
+    else:
+        h_idx, v_idx = out
+    with torch.cuda.device(frames.device):
+        check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
+                                 _ptr(h_idx), _ptr(v_idx), None, None, _stream()))
+    return h_idx, v_idx
+
+
+def decode_codes(frames: torch.Tensor, eps: float = 1.0):
+    """get_codes (decode_codes.py:231-248): tri-state ``h_codes, v_codes`` int8 ``([B,]n,H,W)``
+    plus the decoded indices (same launch)."""
+    _check_stack(frames)
+    b, f, h, w, batched = _stack_dims(frames)
+    n = (f - 2) // 4
+    cshape = (b, n, h, w) if batched else (n, h, w)
+    ishape = (b, h, w) if batched else (h, w)
+    dev = frames.device
+    h_codes = torch.empty(cshape, dtype=torch.int8, device=dev)
+    v_codes = torch.empty(cshape, dtype=torch.int8, device=dev)
+    h_idx = torch.empty(ishape, dtype=torch.int16, device=dev)
+    v_idx = torch.empty(ishape, dtype=torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
+                                 _ptr(h_idx), _ptr(v_idx), _ptr(h_codes), _ptr(v_codes), _stream()))
+    return h_codes, v_codes, h_idx, v_idx
+
+
+def direct_indirect(frames: torch.Tensor):
+    """get_direct_indirect (decode_codes.py:90-122): ``L_d, L_g`` float64 ``(H,W)``."""
+    _check_stack(frames)
+    b, f, h, w, batched = _stack_dims(frames)
+    if batched:
+        raise ValueError("direct_indirect takes one (F,H,W) stack")
+    l_d = torch.empty((h, w), dtype=torch.float64, device=frames.device)
+    l_g = torch.empty((h, w), dtype=torch.float64, device=frames.device)
+    with torch.cuda.device(frames.device):
+        check(lib().sl_direct_indirect(_ptr(frames), f, h, w, h * w, _ptr(l_d), _ptr(l_g), _stream()))
+    return l_d, l_g
+
+
+def is_lit(frames: torch.Tensor, l_d: torch.Tensor, l_g: torch.Tensor, eps: float = 1.0):
+    """get_is_lit (decode_codes.py:125-186) with caller-supplied L_d / L_g."""
+    _check_stack(frames)
+    b, f, h, w, batched = _stack_dims(frames)
+    if batched:
+        raise ValueError("is_lit takes one (F,H,W) stack")
+    n = (f - 2) // 4
+    l_d = l_d.to(device=frames.device, dtype=torch.float64).contiguous()
+    l_g = l_g.to(device=frames.device, dtype=torch.float64).contiguous()
+    if tuple(l_d.shape) != (h, w) or tuple(l_g.shape) != (h, w):
+        raise ValueError("L_d / L_g must be (H, W)")
+    h_codes = torch.empty((n, h, w), dtype=torch.int8, device=frames.device)
+    v_codes = torch.empty((n, h, w), dtype=torch.int8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        check(lib().sl_is_lit(_ptr(frames), f, h, w, h * w, _ptr(l_d), _ptr(l_g), float(eps),
+                              _ptr(h_codes), _ptr(v_codes), _stream()))
+    return h_codes, v_codes
+
+
+def codes_to_pixels(h_codes: torch.Tensor, v_codes: torch.Tensor):
+    """Run merge + Gray->decimal (src/3-capture_decode.py:95-100).
+
+    ``h_codes, v_codes``: int8 CUDA ``(n,H,W)`` or ``(R,n,H,W)`` (R capture runs).
+    """
+    for t in (h_codes, v_codes):
+        if not (t.is_cuda and t.dtype == torch.int8 and t.is_contiguous()):
+            raise TypeError("codes must be contiguous CUDA int8 tensors")
+    if h_codes.shape != v_codes.shape:
+        raise ValueError("h_codes and v_codes differ in shape")
+    if h_codes.dim() == 3:
+        r, (n, h, w) = 1, h_codes.shape
+    elif h_codes.dim() == 4:
+        r, n, h, w = h_codes.shape
+    else:
+        raise ValueError("codes must be (n,H,W) or (R,n,H,W)")
+    h_idx = torch.empty((h, w), dtype=torch.int16, device=h_codes.device)
+    v_idx = torch.empty((h, w), dtype=torch.int16, device=h_codes.device)
+    with torch.cuda.device(h_codes.device):
+        check(lib().sl_codes_to_pixels(_ptr(h_codes), _ptr(v_codes), r, n, h * w, n * h * w,
+                                       _ptr(h_idx), _ptr(v_idx), _stream()))
+    return h_idx, v_idx
+
+
+# --------------------------------------------------------------------------- stage 2
+def _idx16(t, device) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        a = np.asarray(t)
+        if a.size and (a.min() < -1 or a.max() > 32767):
+            raise ValueError("decoded indices must lie in -1..32767")
+        t = torch.from_numpy(np.ascontiguousarray(a.astype(np.int16)))
+    elif t.dtype != torch.int16:
+        if t.numel() and (int(t.min()) < -1 or int(t.max()) > 32767):
+            raise ValueError("decoded indices must lie in -1..32767")
+        t = t.to(torch.int16)
+    return t.to(device).contiguous()
+
+
+class _Offsets:
+    """Workspace + counts of one ordered compaction."""
+
+    def __init__(self, h_idx: torch.Tensor, v_idx: torch.Tensor):
+        if h_idx.shape != v_idx.shape:
+            raise ValueError("h_pixels and v_pixels differ in shape")
+        if h_idx.dim() == 2:
+            self.b, (self.h, self.w) = 1, h_idx.shape
+        elif h_idx.dim() == 3:
+            self.b, self.h, self.w = h_idx.shape
+        else:
+            raise ValueError("indices must be (H,W) or (B,H,W)")
+        dev = h_idx.device
+        nbytes = lib().sl_cloud_workspace_bytes(self.b, self.h, self.w)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.counts = torch.empty(self.b + 1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().sl_compact_offsets(_ptr(h_idx), _ptr(v_idx), self.b, self.h, self.w,
+                                           _ptr(self.ws), _ptr(self.counts), _stream()))
+
+
+def cam_proj_pairs(h_pixels, v_pixels, proj_size, img_white=None, device=None):
+    """Triangulate.get_cam_proj_pts (triangulate.py:39-71) for one image.
+
+    Returns CUDA tensors ``cam_pts (N,2) f32, proj_pts (N,2) f32, rgb (N,3) u8 | None``
+    in the reference's x-major order.
+    """
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h_idx, v_idx = _idx16(h_pixels, dev), _idx16(v_pixels, dev)
+    if h_idx.dim() != 2:
+        raise ValueError("cam_proj_pairs takes one (H,W) image")
+    white = None
+    if img_white is not None:
+        white = img_white if isinstance(img_white, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img_white))
+        if white.dtype != torch.uint8 or tuple(white.shape) != (*h_idx.shape, 3):
+            raise ValueError("img_white must be uint8 (H,W,3)")
+        white = white.to(dev).contiguous()
+    off = _Offsets(h_idx, v_idx)
+    n = int(off.counts[1].item())
+    cam = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    proj = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    rgb = torch.empty((n, 3), dtype=torch.uint8, device=dev) if white is not None else None
+    with torch.cuda.device(dev):
+        check(lib().sl_emit_pairs(_ptr(h_idx), _ptr(v_idx), _ptr(white), 1, off.h, off.w,
+                                  int(proj_size[0]), int(proj_size[1]), _ptr(off.ws), _ptr(cam),
+                                  _ptr(proj), _ptr(rgb), _stream()))
+    return cam, proj, rgb
+
+
+def triangulate_points(cam_pts, proj_pts, calib: Calibration, precision="fp64", device=None) -> torch.Tensor:
+    """Triangulate.triangulate (triangulate.py:73-97): ``(N,2)`` f32 pairs -> ``(3,N)`` f64 (CUDA)."""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def pts(a):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+        t = t.to(device=dev, dtype=torch.float32).reshape(-1, 2).contiguous()
+        return t
+
+    cam, proj = pts(cam_pts), pts(proj_pts)
+    if cam.shape != proj.shape:
+        raise ValueError("cam_pts and proj_pts differ in length")
+    n = cam.shape[0]
+    out = torch.empty((3, n), dtype=torch.float64, device=dev)
+    s = calib.struct()
+    with torch.cuda.device(dev):
+        check(lib().sl_triangulate_points(_ptr(cam), _ptr(proj), n, C.byref(s), _PREC[precision], _ptr(out), _stream()))
+    return out
+
+
+def filter_box(pts: torch.Tensor, colors: Optional[torch.Tensor], threshold: float = .5):
+    """Triangulate.filter_3d_pts (triangulate.py:99-122) on CUDA tensors ``(3,N)`` f64 / ``(N,3)`` f64."""
+    if not (pts.is_cuda and pts.dtype == torch.float64 and pts.dim() == 2 and pts.shape[0] == 3):
+        raise TypeError("pts must be a CUDA float64 (3,N) tensor")
+    pts = pts.contiguous()
+    n = pts.shape[1]
+    dev = pts.device
+    if colors is not None:
+        colors = colors.to(device=dev, dtype=torch.float64).contiguous()
+        if tuple(colors.shape) != (n, 3):
+            raise ValueError("colors must be (N,3)")
+    out_pts = torch.empty((3, n), dtype=torch.float64, device=dev)
+    out_col = torch.empty((n, 3), dtype=torch.float64, device=dev) if colors is not None else None
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    nbytes = lib().sl_filter_workspace_bytes(n)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().sl_filter_box(_ptr(pts), _ptr(colors), n, float(threshold), _ptr(out_pts), _ptr(out_col),
+                                  _ptr(cnt), _ptr(ws), nbytes, _stream()))
+    m = int(cnt.item())
+    return out_pts[:, :m], (out_col[:m] if out_col is not None else None)
+
+
+@dataclass
+class CloudBuffers:
+    """Pre-allocated device buffers so a scan_to_cloud call allocates nothing."""
+    h_idx: torch.Tensor
+    v_idx: torch.Tensor
+    ws: torch.Tensor
+    counts: torch.Tensor
+    xyz: torch.Tensor
+    rgb: torch.Tensor
+
+    @classmethod
+    def allocate(cls, b: int, h: int, w: int, device, cap_points: Optional[int] = None) -> "CloudBuffers":
+        cap = b * h * w if cap_points is None else int(cap_points)
+        shape = (b, h, w)
+        return cls(torch.empty(shape, dtype=torch.int16, device=device),
+                   torch.empty(shape, dtype=torch.int16, device=device),
+                   torch.empty(lib().sl_cloud_workspace_bytes(b, h, w), dtype=torch.uint8, device=device),
+                   torch.empty(b + 1, dtype=torch.int64, device=device),
+                   torch.empty((cap, 3), dtype=torch.float32, device=device),
+                   torch.empty((cap, 3), dtype=torch.uint8, device=device))
+
+
+def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
+                  precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
+                  calib_struct: Optional[SlCalib] = None) -> CloudBuffers:
+    """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
+    decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
+
+    Results are in the returned buffers: ``xyz[:counts[B]]`` / ``rgb[:counts[B]]`` packed scan
+    after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
+    Mirrors src/3-capture_decode.py:75-100 + src/4-triangulate.py:50-64.
+    """
+    _check_stack(frames)
+    b, f, h, w, _ = _stack_dims(frames)
+    dev = frames.device
+    if buffers is None:
+        buffers = CloudBuffers.allocate(b, h, w, dev)
+    if white_rgb is not None:
+        if not (white_rgb.is_cuda and white_rgb.dtype == torch.uint8 and white_rgb.is_contiguous()):
+            raise TypeError("white_rgb must be a contiguous CUDA uint8 tensor")
+        if white_rgb.numel() != b * h * w * 3:
+            raise ValueError("white_rgb must be ([B,]H,W,3)")
+    s = calib_struct if calib_struct is not None else calib.struct()
+    L = lib()
+    st = _stream()
+    with torch.cuda.device(dev):
+        check(L.sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
+                             _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, st))
+        check(L.sl_compact_offsets(_ptr(buffers.h_idx), _ptr(buffers.v_idx), b, h, w,
+                                   _ptr(buffers.ws), _ptr(buffers.counts), st))
+        check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
+                              _PREC[precision], b, h, w, _ptr(buffers.ws), _ptr(buffers.xyz),
+                              _ptr(buffers.rgb) if white_rgb is not None else None, st))
+    return buffers
+
+
+# --------------------------------------------------------------------------- host-buffer pipeline
+class Pipeline:
+    """Host-buffer path (``sl_scan_to_cloud_host``): frames in host memory (pinned memory makes
+    the copies asynchronous), H2D + kernels + D2H overlapped on a ring of CUDA streams."""
+
+    def __init__(self, f: int, h: int, w: int, max_batch: int = 1, device: Optional[int] = None):
+        _require_cuda()
+        self.f, self.h, self.w, self.max_batch = int(f), int(h), int(w), int(max_batch)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._h = C.c_void_p()
+        check(lib().sl_pipeline_create(C.byref(self._h), self.device, self.max_batch, self.f, self.h, self.w))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().sl_pipeline_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def _host_ptr(a):
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                raise TypeError("host buffer expected")
+            return C.c_void_p(a.data_ptr())
+        return C.c_void_p(a.ctypes.data)
+
+    def scan_to_cloud(self, frames, white_rgb, calib: Calibration, precision="fp32", eps: float = 1.0,
+                      xyz=None, rgb=None, counts=None, h_idx=None, v_idx=None):
+        """``frames`` host uint8 ``(B,F,H,W)`` (numpy or CPU torch, ideally pinned); outputs are
+        written into host buffers (allocated pinned when not supplied).  Returns
+        ``(xyz[:n], rgb[:n] | None, counts)``."""
+        shape = tuple(frames.shape)
+        if len(shape) == 3:
+            shape = (1, *shape)
+        b = shape[0]
+        if shape[1:] != (self.f, self.h, self.w):
+            raise ValueError(f"frames must be (B,{self.f},{self.h},{self.w})")
+        if getattr(frames, "dtype", None) not in (np.uint8, torch.uint8):
+            raise TypeError("frames must be uint8")
+        cap = b * self.h * self.w
+        if xyz is None:
+            xyz = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
+        if rgb is None and white_rgb is not None:
+            rgb = torch.empty((cap, 3), dtype=torch.uint8).pin_memory()
+        if counts is None:
+            counts = torch.empty(b + 1, dtype=torch.int64)
+        s = calib.struct()
+        check(lib().sl_scan_to_cloud_host(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), b,
+                                          C.byref(s), _PREC[precision], float(eps), self._host_ptr(h_idx),
+                                          self._host_ptr(v_idx), self._host_ptr(xyz), self._host_ptr(rgb),
+                                          int(xyz.shape[0]), self._host_ptr(counts)))
+        n = int(counts[b])
+        return xyz[:n], (rgb[:n] if rgb is not None else None), counts
+
+    def decode(self, frames, eps: float = 1.0, codes: bool = False):
+        """Host uint8 ``(B,F,H,W)`` -> host int16 ``h_pixels, v_pixels`` [+ int8 tri-state codes]."""
+        shape = tuple(frames.shape)
+        squeeze = len(shape) == 3
+        if squeeze:
+            shape = (1, *shape)
+        b = shape[0]
+        if shape[1:] != (self.f, self.h, self.w):
+            raise ValueError(f"frames must be (B,{self.f},{self.h},{self.w})")
+        n = (self.f - 2) // 4
+        h_idx = np.empty((b, self.h, self.w), dtype=np.int16)
+        v_idx = np.empty((b, self.h, self.w), dtype=np.int16)
+        h_codes = np.empty((b, n, self.h, self.w), dtype=np.int8) if codes else None
+        v_codes = np.empty((b, n, self.h, self.w), dtype=np.int8) if codes else None
+        check(lib().sl_decode_host(self._h, self._host_ptr(frames), b, float(eps), self._host_ptr(h_idx),
+                                   self._host_ptr(v_idx), self._host_ptr(h_codes), self._host_ptr(v_codes)))
+        if squeeze:
+            h_idx, v_idx = h_idx[0], v_idx[0]
+            if codes:
+                h_codes, v_codes = h_codes[0], v_codes[0]
+        return (h_idx, v_idx, h_codes, v_codes) if codes else (h_idx, v_idx)

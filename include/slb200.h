@@ -1,0 +1,169 @@
+/* slb200 -- C ABI of the B200 (sm_100a) Gray-code decode + triangulation hot path.
+ *
+ * The reference (guillaume-charron/3DScanner-GrayCode) is pure Python and has no FFI of
+ * its own; its boundary for this path is the module surface that src/3-capture_decode.py:5-8
+ * and src/4-triangulate.py:5-6 import.  Each entry point below names the reference
+ * function(s) (file:line, relative to the reference repo) it replaces; INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / CUDA types in the signatures
+ *    (`stream` is a cudaStream_t passed as void*, NULL = default stream);
+ *  - "device-pointer" entry points are asynchronous on `stream`, the caller owns every
+ *    buffer; "host" entry points (suffix _host) take HOST buffers, do their own staged
+ *    H2D/D2H copies and return when the results are in the caller's memory;
+ *  - return 0 on success or a negative SL_ERR_* code; sl_last_error() gives the message
+ *    (thread-local);
+ *  - sm_100 only: every entry point fails with SL_ERR_DEVICE on another GPU and there is
+ *    no CPU fallback.
+ */
+#ifndef SLB200_H_
+#define SLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SL_OK 0
+#define SL_ERR_BAD_ARG (-1)
+#define SL_ERR_CUDA (-2)
+#define SL_ERR_DEVICE (-3)
+#define SL_ERR_ALLOC (-4)
+#define SL_ERR_STATE (-5)
+
+/* precision of the triangulation arithmetic */
+#define SL_PREC_FP32 0 /* fp32 undistort + cross-product law of sines (<=1e-4 rel. of the reference) */
+#define SL_PREC_FP64 1 /* mirrors the reference dtype flow: fp64 undistort -> f32 rays -> fp64 angles */
+
+/* Calibration, converted once by the caller.  Matrices row-major.
+ * proj_K must already be scaled to the panel size (scanner/triangulation/triangulate.py:28-33). */
+typedef struct SlCalib {
+  double cam_K[9];
+  double cam_dist[8];  /* k1 k2 p1 p2 k3 k4 k5 k6, unused = 0 */
+  double proj_K[9];
+  double proj_dist[8];
+  double R[9];         /* proj_R: camera -> projector rotation (triangulate.py:84, R=) */
+  double T[3];         /* proj_T[:,0] (triangulate.py:86) */
+  int32_t proj_w;      /* clamp of decoded indices (triangulate.py:60-61) */
+  int32_t proj_h;
+  int32_t reserved[2];
+} SlCalib;
+
+const char* sl_last_error(void);
+int sl_version(void);
+/* 0 if `device` (or the current device when < 0) is an sm_100 GPU */
+int sl_device_check(int device);
+
+/* ---------------------------------------------------------------- decode (stage 1) */
+
+/* Fused decode of B frame stacks.
+ * Replaces get_codes -> get_direct_indirect + get_is_lit (scanner/grayCode/decode_codes.py:231-248,
+ * 90-122, 125-186) and the two per-pixel gray_to_decimal loops (src/3-capture_decode.py:99-100,
+ * decode_codes.py:189-229).
+ *   frames      device u8; frame f of scan b starts at frames + b*scan_pitch + f*frame_pitch,
+ *               H*W contiguous pixels per frame; F = 4n+2, 3 <= n <= 15, frame 0 black, 1 white
+ *   eps         the reference's `eps` (decode_codes.py:125); integer values 0..127 take the
+ *               byte-compare kernel, anything else the fp64-compare kernel (same results)
+ *   h_idx,v_idx device int16 [B][H*W]: projector column / row, -1 = invalid
+ *   h_codes,v_codes  nullable device int8 [B][n][H*W]: the tri-state arrays get_codes returns
+ */
+int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
+                 size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
+                 int8_t* v_codes, void* stream);
+
+/* get_direct_indirect (decode_codes.py:90-122): L_d, L_g device f64 [H*W] (NaN where
+ * white+black == 0, as in the reference). */
+int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
+                       double* L_g, void* stream);
+
+/* get_is_lit (decode_codes.py:125-186) with caller-supplied L_d / L_g (device f64 [H*W]):
+ * fp64 compares exactly as written in the reference; `m` has no effect there and is not taken. */
+int sl_is_lit(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, const double* L_d,
+              const double* L_g, double eps, int8_t* h_codes, int8_t* v_codes, void* stream);
+
+/* Per-bit max over R capture runs (src/3-capture_decode.py:95-96) followed by the per-pixel
+ * Gray -> decimal conversion (src/3-capture_decode.py:99-100).
+ *   h_codes,v_codes  device int8, run r at + r*run_pitch, [n][npix] each (values -1/0/1)
+ */
+int sl_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int n, int64_t npix,
+                       size_t run_pitch, int16_t* h_idx, int16_t* v_idx, void* stream);
+
+/* ---------------------------------------------------------- triangulation (stage 2) */
+
+/* Bytes of device scratch the compaction needs for B scans of H x W. */
+size_t sl_cloud_workspace_bytes(int B, int H, int W);
+
+/* Ordered-compaction offsets: counts the valid pixels (h != -1 and v != -1) and prepares
+ * `workspace` so the emit kernels write every scan in the reference's x-major order
+ * (triangulate.py:52-56).  counts: device int64 [B+1]: counts[b] = points of scan b,
+ * counts[B] = total.  Points of scan b start at sum(counts[0..b-1]) in the packed outputs. */
+int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H, int W,
+                       void* workspace, int64_t* counts, void* stream);
+
+/* Triangulate.get_cam_proj_pts (triangulate.py:39-71): emits, x-major,
+ * cam_pts (N,2) f32 = [x,y], proj_pts (N,2) f32 = [min(proj_w-1,h), min(proj_h-1,v)] and
+ * rgb (N,3) u8 = white_rgb[y,x,:] (nullable together with white_rgb).
+ * Requires sl_compact_offsets on the same workspace first. */
+int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, int B,
+                  int H, int W, int proj_w, int proj_h, const void* workspace, float* cam_pts,
+                  float* proj_pts, uint8_t* rgb, void* stream);
+
+/* Fused get_cam_proj_pts + triangulate (triangulate.py:39-97): undistorts both sides
+ * (5 Brown-Conrady iterations, cv2.undistortPoints semantics), law-of-sines depth, ordered
+ * compaction.  xyz (N,3) f32, rgb (N,3) u8 (nullable with white_rgb), packed over the batch.
+ * Requires sl_compact_offsets on the same workspace first. */
+int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                  const SlCalib* calib, int precision, int B, int H, int W, const void* workspace,
+                  float* xyz, uint8_t* rgb, void* stream);
+
+/* Triangulate.triangulate (triangulate.py:73-97) on caller-supplied point pairs.
+ * cam_pts, proj_pts device f32 (N,2); out device f64 (3,N) like the reference's return. */
+int sl_triangulate_points(const float* cam_pts, const float* proj_pts, int64_t N,
+                          const SlCalib* calib, int precision, double* out, void* stream);
+
+/* Triangulate.filter_3d_pts (triangulate.py:99-122): keeps points with |x|,|y|,|z| < threshold
+ * (strict), order preserved.  pts device f64 (3,N); colors device f64 (N,3) (nullable).
+ * out_pts device f64 with room for (3,N): row r of the result starts at out_pts + r*N and holds M
+ * values; out_colors device f64 (N,3) capacity, first M rows written; out_count device int64[1] = M.
+ * workspace: device scratch of sl_filter_workspace_bytes(N). */
+int sl_filter_box(const double* pts, const double* colors, int64_t N, double threshold,
+                  double* out_pts, double* out_colors, int64_t* out_count, void* workspace,
+                  size_t workspace_bytes, void* stream);
+size_t sl_filter_workspace_bytes(int64_t N);
+
+/* -------------------------------------------------------------- host-buffer pipeline */
+
+typedef struct SlPipeline SlPipeline;
+
+/* A pipeline owns device buffers, pinned staging and streams for scans of one geometry.
+ * max_batch scans of F frames of H x W are staged per call. */
+int sl_pipeline_create(SlPipeline** out, int device, int max_batch, int F, int H, int W);
+void sl_pipeline_destroy(SlPipeline* p);
+
+/* Whole path for B (<= max_batch) scans held in HOST memory:
+ * H2D of the frame stacks and white images, decode, compaction, triangulation, D2H.
+ *   frames_host     u8 [B][F][H][W]         white_rgb_host  u8 [B][H][W][3] (nullable)
+ *   h_idx_host, v_idx_host   nullable int16 [B][H][W]
+ *   xyz_host        f32, capacity cap_points*3      rgb_host  u8, capacity cap_points*3 (nullable)
+ *   counts_host     int64 [B+1] (last = total)
+ * Fails with SL_ERR_BAD_ARG if the total exceeds cap_points (counts_host is still written). */
+int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host,
+                          int B, const SlCalib* calib, int precision, double eps,
+                          int16_t* h_idx_host, int16_t* v_idx_host, float* xyz_host,
+                          uint8_t* rgb_host, int64_t cap_points, int64_t* counts_host);
+
+/* Decode only, HOST buffers (get_codes + gray_to_decimal loops for one or more scans). */
+int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
+                   int16_t* h_idx_host, int16_t* v_idx_host, int8_t* h_codes_host,
+                   int8_t* v_codes_host);
+
+/* Number of kernels this library has launched in the calling process (all streams). */
+int64_t sl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLB200_H_ */

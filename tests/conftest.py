@@ -1,0 +1,56 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "3dscanner-graycode_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+REFERENCE = "/root/reference"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def reference_modules():
+    """The unmodified reference, imported from /root/reference when it is mounted (CPU container)."""
+    if not os.path.isdir(os.path.join(REFERENCE, "scanner")):
+        pytest.skip("reference tree not mounted")
+    import importlib.util
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.dont_write_bytecode = True
+        spec.loader.exec_module(mod)
+        return mod
+
+    return {
+        "decode": load("_ref_decode_codes", "scanner/grayCode/decode_codes.py"),
+        "generate": load("_ref_generate_codes", "scanner/grayCode/generate_codes.py"),
+        "triangulate": load("_ref_triangulate", "scanner/triangulation/triangulate.py"),
+    }
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
