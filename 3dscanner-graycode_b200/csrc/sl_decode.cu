@@ -227,7 +227,15 @@ __global__ void __launch_bounds__(256) codes_to_pixels_kernel(const int8_t* __re
 template <int NB, bool CODES>
 static int launch_tma(const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
   auto k = decode_tma_kernel<NB, CODES>;
-  SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // opt in to > 48 KB dynamic shared memory once per device (not a stream operation, so it is
+  // done outside the launch path and never during CUDA-graph capture replays)
+  static bool configured[64] = {false};
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured[dev & 63] = true;
+  }
   k<<<grid, kDecodeThreads, smem, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());

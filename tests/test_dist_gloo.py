@@ -1,0 +1,94 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: scan sharding, the all-gather-v of
+packed clouds, and the row-band merge back into the reference's x-major order."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "3dscanner-graycode_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from slb200.dist import gather_clouds, shard_range
+    n_scans = 5
+    rng = np.random.default_rng(0)
+    per_scan = [int(x) for x in rng.integers(0, 50, n_scans)]
+    clouds = [torch.from_numpy(rng.random((n, 3)).astype(np.float32)) for n in per_scan]
+    colors = [torch.from_numpy(rng.integers(0, 256, (n, 3)).astype(np.uint8)) for n in per_scan]
+    lo, hi = shard_range(n_scans, rank, world)
+    xyz = torch.cat(clouds[lo:hi]) if hi > lo else torch.zeros((0, 3))
+    rgb = torch.cat(colors[lo:hi]) if hi > lo else torch.zeros((0, 3), dtype=torch.uint8)
+    counts = torch.tensor(per_scan[lo:hi] + [sum(per_scan[lo:hi])], dtype=torch.int64)
+    xyz_all, rgb_all, cnts = gather_clouds(xyz, rgb, counts)
+    ok = torch.equal(xyz_all, torch.cat(clouds)) and torch.equal(rgb_all, torch.cat(colors))
+    got = [int(c) for r in cnts for c in r[:-1]]
+    ok = ok and got == per_scan
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_clouds_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_range_and_bands():
+    from slb200.dist import row_bands, shard_range
+    for n in (0, 1, 7, 64):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    for h in (2160, 1080, 100):
+        for w in (2, 4, 8):
+            bands = row_bands(h, w)
+            assert bands[0][0] == 0 and bands[-1][1] == h
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(w - 1))
+            assert all(a % 32 == 0 for a, b in bands if b > a)
+
+
+def test_merge_row_bands_restores_x_major_order():
+    """Row-band clouds merged == the single-image x-major cloud (oracle ordering)."""
+    from oracle import graycode_oracle as O
+    from slb200.dist import merge_row_bands, row_bands
+    rng = np.random.default_rng(3)
+    h, w = 100, 37
+    hp = rng.integers(-1, 50, (h, w)); vp = rng.integers(-1, 50, (h, w))
+    white = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+    cam, proj, col = O.cam_proj_pairs(hp, vp, (64, 64), white)
+    full = np.concatenate([cam, proj], axis=1)[:, :3]
+    bx, bc, bcols = [], [], []
+    for (y0, y1) in row_bands(h, 3):
+        c, p, cl = O.cam_proj_pairs(hp[y0:y1], vp[y0:y1], (64, 64), white[y0:y1])
+        c = c + np.array([[0, y0]], dtype=np.float32)
+        bx.append(torch.from_numpy(np.concatenate([c, p], axis=1)[:, :3].copy()))
+        bc.append(torch.from_numpy(np.round(cl * 255).astype(np.uint8)))
+        valid = (hp[y0:y1] != -1) & (vp[y0:y1] != -1)
+        bcols.append(torch.from_numpy(valid.sum(axis=0).astype(np.int64)))
+    xyz, rgb = merge_row_bands(bx, bc, bcols)
+    np.testing.assert_array_equal(xyz.numpy(), full)
+    np.testing.assert_array_equal(rgb.numpy(), np.round(col * 255).astype(np.uint8))

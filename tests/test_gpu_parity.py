@@ -1,0 +1,378 @@
+"""GPU parity: the CUDA path (through the C ABI, via slb200 / the drop-in scanner package) against
+the oracle on the same seeded inputs.  Integer / byte / index results are compared bit-exactly;
+floating-point results with the tolerance written in each test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import graycode_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_inputs import adversarial_stack  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    import slb200
+    assert slb200.lib() is not None
+    return torch
+
+
+def dev_stack(T, st):
+    return T.from_numpy(np.ascontiguousarray(st)).cuda()
+
+
+def oracle_decode(st, eps=1):
+    f64 = st.astype(np.float64)
+    l_d, l_g = O.get_direct_indirect(f64)
+    h, v = O.get_is_lit(f64, l_d, l_g, eps=eps)
+    hp, vp = O.codes_to_pixels(h, v)
+    return h, v, hp, vp, l_d, l_g
+
+
+# ------------------------------------------------------------------ decode
+@pytest.mark.parametrize("n", [3, 5, 8, 9, 10, 11, 12, 13, 15])
+def test_decode_adversarial_all_bit_counts(T, n):
+    import slb200
+    rng = np.random.default_rng(40 + n)
+    st = adversarial_stack(rng, n, 40, 96)          # 3840 px: multiple of 16, several quads per warp
+    h, v, hp, vp, _, _ = oracle_decode(st)
+    hc, vc, hi, vi = slb200.decode_codes(dev_stack(T, st))
+    np.testing.assert_array_equal(hc.cpu().numpy(), h)
+    np.testing.assert_array_equal(vc.cpu().numpy(), v)
+    np.testing.assert_array_equal(hi.cpu().numpy(), hp)
+    np.testing.assert_array_equal(vi.cpu().numpy(), vp)
+    hi2, vi2 = slb200.decode_pixels(dev_stack(T, st))
+    np.testing.assert_array_equal(hi2.cpu().numpy(), hp)
+    np.testing.assert_array_equal(vi2.cpu().numpy(), vp)
+
+
+@pytest.mark.parametrize("shape", [(8, 16), (9, 17), (13, 31), (37, 53), (64, 1030), (3, 5), (1, 1), (1, 15), (2, 8), (129, 257)])
+def test_decode_ragged_shapes(T, shape):
+    """Odd widths, pixel counts that are not multiples of 16/4, tiles that end mid-way."""
+    import slb200
+    h_, w_ = shape
+    rng = np.random.default_rng(h_ * 1000 + w_)
+    n = 10
+    st = rng.integers(0, 256, (4 * n + 2, h_, w_)).astype(np.uint8)
+    st[0] = rng.integers(0, 30, (h_, w_)); st[1] = rng.integers(150, 256, (h_, w_))
+    h, v, hp, vp, _, _ = oracle_decode(st)
+    hc, vc, hi, vi = slb200.decode_codes(dev_stack(T, st))
+    np.testing.assert_array_equal(hi.cpu().numpy(), hp)
+    np.testing.assert_array_equal(vi.cpu().numpy(), vp)
+    np.testing.assert_array_equal(hc.cpu().numpy(), h)
+    np.testing.assert_array_equal(vc.cpu().numpy(), v)
+
+
+@pytest.mark.parametrize("eps", [0, 1, 2, 5, 127, 0.5, 3.25, 128, 300, -1])
+def test_decode_eps_variants(T, eps):
+    """Integer eps 0..127 runs the byte-compare kernel, everything else the fp64-compare kernel."""
+    import slb200
+    rng = np.random.default_rng(77)
+    st = adversarial_stack(rng, 6, 24, 64)
+    h, v, hp, vp, _, _ = oracle_decode(st, eps=eps)
+    hc, vc, hi, vi = slb200.decode_codes(dev_stack(T, st), eps=eps)
+    np.testing.assert_array_equal(hc.cpu().numpy(), h)
+    np.testing.assert_array_equal(vc.cpu().numpy(), v)
+    np.testing.assert_array_equal(hi.cpu().numpy(), hp)
+    np.testing.assert_array_equal(vi.cpu().numpy(), vp)
+
+
+def test_decode_batched_and_multi_tile(T):
+    """B scans in one launch; more tiles than CTAs * stages so every ring slot wraps."""
+    import slb200
+    rng = np.random.default_rng(9)
+    n, b, h_, w_ = 4, 3, 600, 1000          # 600k px / scan -> 586 tiles per scan
+    st = rng.integers(0, 256, (b, 4 * n + 2, h_, w_)).astype(np.uint8)
+    st[:, 0] = rng.integers(0, 30, (b, h_, w_)); st[:, 1] = rng.integers(150, 256, (b, h_, w_))
+    hi, vi = slb200.decode_pixels(dev_stack(T, st))
+    for k in range(b):
+        _, _, hp, vp, _, _ = oracle_decode(st[k])
+        np.testing.assert_array_equal(hi[k].cpu().numpy(), hp)
+        np.testing.assert_array_equal(vi[k].cpu().numpy(), vp)
+
+
+def test_direct_indirect_and_is_lit(T):
+    import slb200
+    rng = np.random.default_rng(3)
+    st = adversarial_stack(rng, 5, 16, 48)
+    h, v, _, _, l_d, l_g = oracle_decode(st)
+    ld, lg = slb200.direct_indirect(dev_stack(T, st))
+    np.testing.assert_array_equal(ld.cpu().numpy(), l_d)       # bit exact, NaN-aware
+    np.testing.assert_array_equal(lg.cpu().numpy(), l_g)
+    # caller-supplied (perturbed) thresholds are honoured
+    l_d2 = np.nan_to_num(l_d) * 0.9 + 3.3
+    l_g2 = np.nan_to_num(l_g) * 1.1 + 0.7
+    ho, vo = O.get_is_lit(st.astype(np.float64), l_d2, l_g2, eps=2)
+    hc, vc = slb200.is_lit(dev_stack(T, st), T.from_numpy(l_d2), T.from_numpy(l_g2), eps=2)
+    np.testing.assert_array_equal(hc.cpu().numpy(), ho)
+    np.testing.assert_array_equal(vc.cpu().numpy(), vo)
+
+
+def test_multi_run_merge(T, golden_dir):
+    """np.max merge of capture runs + per-pixel Gray->decimal against the reference's own loops."""
+    import slb200
+    g = np.load(os.path.join(golden_dir, "decode_golden.npz"))
+    for name in ("n5", "n10"):
+        stacks = g[f"decode_{name}_stacks"]
+        codes = [slb200.decode_codes(dev_stack(T, s))[:2] for s in stacks]
+        for r, (hc, vc) in enumerate(codes):
+            np.testing.assert_array_equal(hc.cpu().numpy(), g[f"decode_{name}_h_codes"][r])
+            np.testing.assert_array_equal(vc.cpu().numpy(), g[f"decode_{name}_v_codes"][r])
+        hi, vi = slb200.codes_to_pixels(T.stack([c[0] for c in codes]).contiguous(), T.stack([c[1] for c in codes]).contiguous())
+        np.testing.assert_array_equal(hi.cpu().numpy(), g[f"decode_{name}_h_pixels"])
+        np.testing.assert_array_equal(vi.cpu().numpy(), g[f"decode_{name}_v_pixels"])
+
+
+@pytest.mark.parametrize("name", ["n3", "n11", "n12"])
+def test_decode_golden_single_run(T, golden_dir, name):
+    import slb200
+    g = np.load(os.path.join(golden_dir, "decode_golden.npz"))
+    st = g[f"decode_{name}_stacks"][0]
+    hc, vc, hi, vi = slb200.decode_codes(dev_stack(T, st))
+    np.testing.assert_array_equal(hc.cpu().numpy(), g[f"decode_{name}_h_codes"][0])
+    np.testing.assert_array_equal(vc.cpu().numpy(), g[f"decode_{name}_v_codes"][0])
+    np.testing.assert_array_equal(hi.cpu().numpy(), g[f"decode_{name}_h_pixels"])
+    np.testing.assert_array_equal(vi.cpu().numpy(), g[f"decode_{name}_v_pixels"])
+
+
+def test_ideal_sequence_identity_full_size(T):
+    """Size-independent property at BASELINE's full 1080p size: the rendered sequence decodes to the
+    identity map (projector pixel == camera pixel)."""
+    import slb200
+    from scanner.grayCode.generate_codes import get_gray_codes, get_image_sequence
+    pw, ph = 1920, 1080
+    seq = get_image_sequence(get_gray_codes(pw, ph), pw, ph)
+    hi, vi = slb200.decode_pixels(dev_stack(T, seq))
+    xs = T.arange(pw, dtype=T.int16, device="cuda")[None, :].expand(ph, pw)
+    ys = T.arange(ph, dtype=T.int16, device="cuda")[:, None].expand(ph, pw)
+    assert bool((hi == xs).all()) and bool((vi == ys).all())
+
+
+def test_full_size_synthetic_scan_vs_oracle(T):
+    """Config 1 (1280x720 camera, 1024x768 projector) end to end against the oracle."""
+    import slb200
+    from slb200 import synth
+    cam_size, proj_size = (1280, 720), (1024, 768)
+    frames, white = synth.render_scan(cam_size, proj_size, seed=1, device="cuda")
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    bufs = slb200.scan_to_cloud(frames, white, calib, precision="fp32")
+    bufs64 = slb200.scan_to_cloud(frames, white, calib, precision="fp64")
+    hp, vp = O.decode_pixels(frames.cpu().numpy().astype(np.float64))
+    np.testing.assert_array_equal(bufs.h_idx[0].cpu().numpy(), hp)
+    np.testing.assert_array_equal(bufs.v_idx[0].cpu().numpy(), vp)
+    cam, proj, col = O.cam_proj_pairs(hp, vp, proj_size, white.cpu().numpy())
+    pts = O.triangulate(cam, proj, calib.cam_mtx, calib.cam_dist, calib.proj_mtx, calib.proj_dist, calib.proj_R, calib.proj_T)
+    n = int(bufs.counts[1])
+    assert n == pts.shape[1] == int(bufs.counts[0])
+    assert n > 0.8 * 1280 * 720
+    np.testing.assert_array_equal(bufs.rgb[:n].cpu().numpy(), np.round(col * 255).astype(np.uint8))
+    scale = np.linalg.norm(pts, axis=0)
+    err32 = np.linalg.norm(bufs.xyz[:n].cpu().numpy().astype(np.float64).T - pts, axis=0) / scale
+    err64 = np.linalg.norm(bufs64.xyz[:n].cpu().numpy().astype(np.float64).T - pts, axis=0) / scale
+    # tolerance (north_star): 1e-4 relative in fp32; the fp64 mode is limited by the f32 output rounding
+    assert err32.max() < 1e-4, err32.max()
+    assert err64.max() < 2e-7, err64.max()
+
+
+# ------------------------------------------------------------------ triangulation
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_pairs_and_triangulate_golden(T, golden_dir, name):
+    import slb200
+    g = np.load(os.path.join(golden_dir, "triangulate_golden.npz"))
+    k = lambda s: g[f"{name}_{s}"]
+    proj_size = tuple(int(x) for x in k("proj_size"))
+    cam, proj, rgb = slb200.cam_proj_pairs(k("h_pixels"), k("v_pixels"), proj_size, k("white"))
+    np.testing.assert_array_equal(cam.cpu().numpy(), k("cam_pts"))          # order, count: exact
+    np.testing.assert_array_equal(proj.cpu().numpy(), k("proj_pts"))
+    np.testing.assert_array_equal(rgb.cpu().numpy().astype(np.float64) / 255.0, k("colors"))
+    calib = slb200.Calibration(k("cam_mtx"), k("cam_dist"), k("proj_mtx_scaled"), k("proj_dist"), g["R"], g["T"], proj_size)
+    ref = k("pts")
+    pts64 = slb200.triangulate_points(k("cam_full"), k("proj_pts"), calib, precision="fp64").cpu().numpy()
+    assert pts64.shape == ref.shape and pts64.dtype == np.float64
+    fin = np.isfinite(ref).all(axis=0)
+    # fp64 mode mirrors the reference dtype flow; only libm-vs-CUDA acos/sin ulps remain
+    np.testing.assert_allclose(pts64[:, fin], ref[:, fin], rtol=1e-9, atol=0)
+    if name != "c":      # case c evaluates the projector lens far outside its calibrated domain (chaotic in fp32)
+        pts32 = slb200.triangulate_points(k("cam_full"), k("proj_pts"), calib, precision="fp32").cpu().numpy()
+        rel = np.linalg.norm(pts32[:, fin] - ref[:, fin], axis=0) / np.linalg.norm(ref[:, fin], axis=0)
+        assert rel.max() < 1e-4, rel.max()
+
+
+@pytest.mark.parametrize("thr,key", [(.5, "filt"), (1.25, "filt125")])
+def test_filter_box_golden(T, golden_dir, thr, key):
+    import slb200
+    g = np.load(os.path.join(golden_dir, "triangulate_golden.npz"))
+    for name in ("a", "b"):
+        pts, col = g[f"{name}_pts"], g[f"{name}_colors"]
+        fp, fc = slb200.filter_box(T.from_numpy(pts).cuda(), T.from_numpy(col).cuda(), thr)
+        np.testing.assert_array_equal(fp.cpu().numpy(), g[f"{name}_{key}_pts"])
+        np.testing.assert_array_equal(fc.cpu().numpy(), g[f"{name}_{key}_colors"])
+
+
+def test_filter_box_large_and_empty(T):
+    import slb200
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-1, 1, (3, 300001))
+    pts[:, ::7] = np.nan
+    col = rng.random((300001, 3))
+    fp, fc = slb200.filter_box(T.from_numpy(pts).cuda(), T.from_numpy(col).cuda(), .5)
+    rp, rc = O.filter_3d_pts(pts, col, .5)
+    np.testing.assert_array_equal(fp.cpu().numpy(), rp)
+    np.testing.assert_array_equal(fc.cpu().numpy(), rc)
+    fp, fc = slb200.filter_box(T.zeros((3, 0), dtype=T.float64, device="cuda"), T.zeros((0, 3), dtype=T.float64, device="cuda"), .5)
+    assert fp.shape == (3, 0) and fc.shape == (0, 3)
+
+
+def test_pairs_edge_cases(T):
+    import slb200
+    # nothing valid / everything valid / single column / ragged sizes
+    for (h_, w_), fill in (((5, 7), -1), ((33, 65), 5), ((70, 1), 3), ((1, 130), 2)):
+        hp = np.full((h_, w_), fill, dtype=np.int64); vp = np.full((h_, w_), fill, dtype=np.int64)
+        white = np.arange(h_ * w_ * 3, dtype=np.uint8).reshape(h_, w_, 3)
+        cam, proj, rgb = slb200.cam_proj_pairs(hp, vp, (4, 3), white)
+        co, po, colo = O.cam_proj_pairs(hp, vp, (4, 3), white)
+        np.testing.assert_array_equal(cam.cpu().numpy(), co)
+        np.testing.assert_array_equal(proj.cpu().numpy(), po)
+        np.testing.assert_array_equal(rgb.cpu().numpy().astype(np.float64) / 255.0, colo)
+    rng = np.random.default_rng(4)
+    hp = rng.integers(-1, 3000, (211, 333)); vp = rng.integers(-1, 3000, (211, 333))
+    hp[rng.random(hp.shape) < .5] = -1
+    cam, proj, rgb = slb200.cam_proj_pairs(hp, vp, (1920, 1080), None)
+    co, po, _ = O.cam_proj_pairs(hp, vp, (1920, 1080), None)
+    assert rgb is None
+    np.testing.assert_array_equal(cam.cpu().numpy(), co)
+    np.testing.assert_array_equal(proj.cpu().numpy(), po)
+
+
+def test_batched_cloud_matches_single(T):
+    """Packed batch output == the scans done one by one (order inside a scan, counts, bytes)."""
+    import slb200
+    from slb200 import synth
+    cam_size, proj_size = (320, 200), (1024, 768)
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    pats = synth.pattern_stack(proj_size, "cuda")
+    scans = [synth.render_scan(cam_size, proj_size, seed=s, device="cuda", patterns=pats, calib=calib) for s in range(3)]
+    frames = T.stack([s[0] for s in scans]).contiguous()
+    white = T.stack([s[1] for s in scans]).contiguous()
+    bufs = slb200.scan_to_cloud(frames, white, calib)
+    counts = bufs.counts.cpu().numpy()
+    assert counts[-1] == counts[:-1].sum()
+    start = 0
+    for b in range(3):
+        one = slb200.scan_to_cloud(scans[b][0], scans[b][1], calib)
+        n = int(one.counts[1])
+        assert n == counts[b]
+        assert T.equal(one.xyz[:n], bufs.xyz[start:start + n])
+        assert T.equal(one.rgb[:n], bufs.rgb[start:start + n])
+        assert T.equal(one.h_idx[0], bufs.h_idx[b])
+        start += n
+
+
+# ------------------------------------------------------------------ host-buffer pipeline + drop-in API
+def test_pipeline_host_buffers(T):
+    import slb200
+    from slb200 import synth
+    cam_size, proj_size = (320, 200), (1024, 768)
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    scans = [synth.render_scan(cam_size, proj_size, seed=s, device="cpu") for s in range(5)]
+    frames = T.stack([s[0] for s in scans]).contiguous().pin_memory()
+    white = T.stack([s[1] for s in scans]).contiguous().pin_memory()
+    pipe = slb200.Pipeline(frames.shape[1], 200, 320, max_batch=5)
+    h_idx = np.empty((5, 200, 320), np.int16); v_idx = np.empty((5, 200, 320), np.int16)
+    xyz, rgb, counts = pipe.scan_to_cloud(frames, white, calib, h_idx=h_idx, v_idx=v_idx)
+    dev = slb200.scan_to_cloud(frames.cuda(), white.cuda(), calib)
+    n = int(dev.counts[-1])
+    assert int(counts[-1]) == n and xyz.shape[0] == n
+    np.testing.assert_array_equal(counts.numpy(), dev.counts.cpu().numpy())
+    assert T.equal(xyz, dev.xyz[:n].cpu()) and T.equal(rgb, dev.rgb[:n].cpu())
+    np.testing.assert_array_equal(h_idx, dev.h_idx.cpu().numpy())
+    np.testing.assert_array_equal(v_idx, dev.v_idx.cpu().numpy())
+    hi, vi, hc, vc = pipe.decode(frames[:2].numpy(), codes=True)
+    for b in range(2):
+        h, v, hp, vp, _, _ = oracle_decode(frames[b].numpy())
+        np.testing.assert_array_equal(hi[b], hp); np.testing.assert_array_equal(vi[b], vp)
+        np.testing.assert_array_equal(hc[b], h); np.testing.assert_array_equal(vc[b], v)
+    with pytest.raises(slb200.SlError):
+        pipe.scan_to_cloud(frames, white, calib, xyz=T.empty((10, 3), dtype=T.float32))   # cap too small
+    pipe.close()
+
+
+def test_dropin_scripts_flow(T):
+    """The logic of src/3-capture_decode.py:75-104 and src/4-triangulate.py:50-71 against the drop-in
+    `scanner` package, with the oracle standing in for the reference."""
+    from scanner.grayCode import decode_codes as dc
+    from scanner.triangulation import Triangulate, Triangulation
+    from slb200 import synth, calib_data
+    assert Triangulation is Triangulate
+    cam_size, proj_size = (160, 96), (1024, 768)
+    runs = [synth.render_scan(cam_size, proj_size, seed=s, device="cpu") for s in (1, 1)]
+    runs[1] = (runs[1][0].clone(), runs[1][1])
+    runs[1][0][:, :, 100:] = 0                     # second run lost part of the image
+    cache_h, cache_v = [], []
+    for frames, _ in runs:
+        gray_images = frames.numpy().astype(np.float64)          # the script's float64 stack (:69)
+        h_codes, v_codes = dc.get_codes(gray_images)             # :75
+        ho, vo = O.get_codes(gray_images)
+        assert h_codes.dtype == np.int8
+        np.testing.assert_array_equal(h_codes, ho); np.testing.assert_array_equal(v_codes, vo)
+        cache_h.append(h_codes); cache_v.append(v_codes)
+    best_h = np.max(cache_h, axis=0); best_v = np.max(cache_v, axis=0)       # :95-96
+    hp_ref, vp_ref = O.codes_to_pixels(best_h, best_v)
+    h_pixels, v_pixels = dc.codes_to_pixels(cache_h, cache_v)    # replaces the loops at :99-100
+    assert h_pixels.dtype == np.int64 and h_pixels.shape == (96, 160)
+    np.testing.assert_array_equal(h_pixels, hp_ref); np.testing.assert_array_equal(v_pixels, vp_ref)
+    h2, v2 = dc.decode_pixels(None, runs=[r[0].numpy() for r in runs])
+    np.testing.assert_array_equal(h2, hp_ref); np.testing.assert_array_equal(v2, vp_ref)
+    for (y, x) in ((0, 0), (50, 80), (95, 159)):                 # scalar helper == reference semantics
+        assert dc.gray_to_decimal(best_h[:, y, x]) == hp_ref[y, x]
+        assert dc.gray_to_decimal(np.flip(best_v[:, y, x])) == vp_ref[y, x]
+    l_d, l_g = dc.get_direct_indirect(runs[0][0].numpy().astype(np.float64))
+    ldo, lgo = O.get_direct_indirect(runs[0][0].numpy().astype(np.float64))
+    np.testing.assert_array_equal(l_d, ldo); np.testing.assert_array_equal(l_g, lgo)
+    hl, vl = dc.get_is_lit(runs[0][0].numpy().astype(np.float64), l_d, l_g)
+    np.testing.assert_array_equal(hl, cache_h[0])
+    with pytest.raises(ValueError):
+        dc.get_codes(runs[0][0].numpy().astype(np.float64) + 0.25)   # non-integer grey levels: refuse, don't diverge
+
+    # ---- src/4-triangulate.py
+    img_white = runs[0][1].numpy()
+    cal = synth.synthetic_calibration(cam_size, proj_size)
+    proj_mtx = calib_data.PROJ_MTX.copy()
+    tri = Triangulate(h_pixels, v_pixels, cam_size, cal.cam_mtx, cal.cam_dist, proj_size, calib_data.PROJ_CALIB_SIZE,
+                      proj_mtx, cal.proj_dist, cal.proj_R, cal.proj_T, "unused")
+    np.testing.assert_array_equal(proj_mtx, cal.proj_mtx)        # scaled in place like the reference (:28-33)
+    cam_pts, proj_pts, colors = tri.get_cam_proj_pts(img_white)  # :63
+    co, po, colo = O.cam_proj_pairs(hp_ref, vp_ref, proj_size, img_white)
+    assert cam_pts.dtype == np.float32 and colors.dtype == np.float64
+    np.testing.assert_array_equal(cam_pts, co); np.testing.assert_array_equal(proj_pts, po)
+    np.testing.assert_array_equal(colors, colo)
+    pts_3d = tri.triangulate(cam_pts, proj_pts)                  # :64
+    ref = O.triangulate(co, po, cal.cam_mtx, cal.cam_dist, cal.proj_mtx, cal.proj_dist, cal.proj_R, cal.proj_T)
+    assert pts_3d.shape == ref.shape and pts_3d.dtype == np.float64
+    np.testing.assert_allclose(pts_3d, ref, rtol=1e-9)
+    fp, fc = tri.filter_3d_pts(pts_3d, colors, threshold=0.9)    # :71
+    rp, rc = O.filter_3d_pts(pts_3d, colors, 0.9)
+    np.testing.assert_array_equal(fp, rp); np.testing.assert_array_equal(fc, rc)
+    pts_f, col_f = tri.point_cloud(img_white)
+    np.testing.assert_allclose(pts_f, ref, rtol=2e-7); np.testing.assert_array_equal(col_f, colo)
+    with pytest.raises(UnboundLocalError):
+        tri.get_cam_proj_pts()                                    # reference behaviour (:66-71)
+    Triangulate()                                                 # all-default constructor (src/4-triangulate.py:24)
+
+
+def test_error_codes(T):
+    import slb200
+    with pytest.raises(slb200.SlError):
+        slb200.decode_pixels(T.zeros((13, 4, 4), dtype=T.uint8, device="cuda"))      # F != 4n+2
+    with pytest.raises(slb200.SlError):
+        slb200.decode_pixels(T.zeros((70, 4, 4), dtype=T.uint8, device="cuda"))      # n = 17 > 15
+    with pytest.raises(TypeError):
+        slb200.decode_pixels(T.zeros((14, 4, 4), dtype=T.uint8))                      # host tensor
+    assert slb200.launch_count() > 0
