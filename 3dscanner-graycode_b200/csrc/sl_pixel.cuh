@@ -83,7 +83,13 @@ SL_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
 // PRMT (byte permute).  Selector nibble k picks byte (nibble & 7) of {lo: bytes 0-3,
 // hi: bytes 4-7}; nibble bit 3 replicates that byte's msb over the whole byte.
 #if defined(__CUDA_ARCH__)
-SL_HD uint32_t byte_perm(uint32_t lo, uint32_t hi, uint32_t sel) { return __byte_perm(lo, hi, sel); }
+// (inline PTX: the __byte_perm intrinsic masks the selector with 0x7777 and drops the
+// sign-replicate bit that prmt.b32 itself implements)
+SL_HD uint32_t byte_perm(uint32_t lo, uint32_t hi, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+  return r;
+}
 #else
 SL_HD uint32_t byte_perm(uint32_t lo, uint32_t hi, uint32_t sel) {
   const uint64_t src = ((uint64_t)hi << 32) | lo;
