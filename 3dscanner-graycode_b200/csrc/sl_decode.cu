@@ -1,14 +1,16 @@
 // Stage 1: fused Gray-code decode kernels (sm_100a).
 //
-// K1  decode_tma_kernel     persistent, one CTA per SM.  A producer warp streams row tiles of
-//                           all F frames into a ring of shared-memory stages with TMA bulk copies
-//                           (cp.async.bulk + mbarrier complete_tx); consumer warps read them as
+// K1  decode_tma_kernel     persistent, one CTA per SM.  A producer thread streams [F x 1024 px]
+//                           tiles into a ring of shared-memory stages, ONE TMA tensor load per
+//                           tile (cp.async.bulk.tensor.3d + mbarrier complete_tx; the stack is
+//                           described as a (pixels/4 x F x B) uint32 tensor); consumer warps read them as
 //                           conflict-free 32-bit words (4 pixels / thread), keep every per-pixel
 //                           decision in registers as byte-SWAR flags and write two int16 indices.
 //                           Bound: HBM.  Algorithmic bytes / pixel = F + 4.
 // K1g decode_generic_kernel any alignment / any eps: direct loads, fp64 compares exactly as
 //                           scanner/grayCode/decode_codes.py:172-182 writes them.
 // K1m codes_to_pixels_kernel run merge (src/3-capture_decode.py:95-96) + Gray->decimal (:99-100).
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include "sl_common.cuh"
 #include "sl_decode_quad.cuh"
 #include "sl_kernels.h"
@@ -32,14 +34,15 @@ struct DecodeArgs {
   int8_t* h_codes;
   int8_t* v_codes;
   long long npix;        // pixels per scan
-  long long npix16;      // npix rounded down to a multiple of 16 (TMA part)
+  long long npix4;       // npix rounded down to a multiple of 4 (part handled by this kernel)
   long long total_tiles; // B * tiles_per_scan
   int tiles_per_scan;
   int n, F, e, stages;
 };
 
 template <int NB, bool CODES>
-__global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        const DecodeArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int n = NB ? NB : a.n;
   const int F = 4 * n + 2;
@@ -61,21 +64,17 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const Dec
   if (warp == kConsumerWarps) {
     // ------------------------------------------------------------ producer (one lane)
     if (lane == 0) {
+      tma_prefetch_desc(&tmap);
       const uint64_t pol = policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
-        const long long b = t / a.tiles_per_scan;
-        const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
-        const long long rem = a.npix16 - px0;
-        const uint32_t bytes = (uint32_t)(rem < kTilePx ? rem : kTilePx);
+        const int b = (int)(t / a.tiles_per_scan);
+        const int tile = (int)(t - (long long)b * a.tiles_per_scan);
         const uint32_t full = smem_u32(&bars[s]);
-        mbar_arrive_expect_tx(full, bytes * (uint32_t)F);
-        const uint8_t* src = a.frames + (size_t)b * a.scan_pitch + (size_t)px0;
-        const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
-        for (int f = 0; f < F; ++f)
-          bulk_g2s(dst + (uint32_t)f * kTilePx, src + (size_t)f * a.frame_pitch, bytes, full, pol);
+        mbar_arrive_expect_tx(full, stage_bytes);          // the box is always written in full
+        tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, tile * (kTilePx / 4), 0, b, full, pol);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const Dec
 
     const long long b = t / a.tiles_per_scan;
     const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
-    const long long rem = a.npix16 - px0;
+    const long long rem = a.npix4 - px0;
     const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
     if (off < cnt) {
       const uint32_t* base = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + (off >> 2);
@@ -224,8 +223,42 @@ __global__ void __launch_bounds__(256) codes_to_pixels_kernel(const int8_t* __re
 }
 
 // ------------------------------------------------------------------ launchers
+// cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link dependency
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_frames_tensor_map(CUtensorMap* out, const uint8_t* frames, long long npix4, int F, int B,
+                                  size_t frame_pitch, size_t scan_pitch) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled not available from this driver");
+      return kErrCuda;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  // tensor of uint32 (4 pixels): dim0 = npix4/4 along a frame, dim1 = frame, dim2 = scan
+  const cuuint64_t dims[3] = {(cuuint64_t)(npix4 / 4), (cuuint64_t)F, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)frame_pitch, (cuuint64_t)(B > 1 ? scan_pitch : frame_pitch * F)};
+  const cuuint32_t box[3] = {(cuuint32_t)(kTilePx / 4), (cuuint32_t)F, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (npix4=%lld F=%d B=%d pitch=%zu/%zu)", (int)r, npix4, F, B,
+              frame_pitch, scan_pitch);
+    return kErrCuda;
+  }
+  return kOk;
+}
+
 template <int NB, bool CODES>
-static int launch_tma(const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+static int launch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
   auto k = decode_tma_kernel<NB, CODES>;
   // opt in to > 48 KB dynamic shared memory once per device (not a stream operation, so it is
   // done outside the launch path and never during CUDA-graph capture replays)
@@ -236,21 +269,21 @@ static int launch_tma(const DecodeArgs& a, int grid, size_t smem, cudaStream_t s
     SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured[dev & 63] = true;
   }
-  k<<<grid, kDecodeThreads, smem, st>>>(a);
+  k<<<grid, kDecodeThreads, smem, st>>>(tmap, a);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
 }
 
 template <bool CODES>
-static int dispatch_tma(const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+static int dispatch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
   switch (a.n) {
-    case 8:  return launch_tma<8, CODES>(a, grid, smem, st);
-    case 9:  return launch_tma<9, CODES>(a, grid, smem, st);
-    case 10: return launch_tma<10, CODES>(a, grid, smem, st);
-    case 11: return launch_tma<11, CODES>(a, grid, smem, st);
-    case 12: return launch_tma<12, CODES>(a, grid, smem, st);
-    default: return launch_tma<0, CODES>(a, grid, smem, st);
+    case 8:  return launch_tma<8, CODES>(tmap, a, grid, smem, st);
+    case 9:  return launch_tma<9, CODES>(tmap, a, grid, smem, st);
+    case 10: return launch_tma<10, CODES>(tmap, a, grid, smem, st);
+    case 11: return launch_tma<11, CODES>(tmap, a, grid, smem, st);
+    case 12: return launch_tma<12, CODES>(tmap, a, grid, smem, st);
+    default: return launch_tma<0, CODES>(tmap, a, grid, smem, st);
   }
 }
 
@@ -264,13 +297,14 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
                        ((uintptr_t)v_idx % 8 == 0) && (npix % 4 == 0 || B == 1) &&
                        (!h_codes || (((uintptr_t)h_codes % 4 == 0) && ((uintptr_t)v_codes % 4 == 0) &&
                                      npix % 4 == 0));
-  long long tma_px = (int_eps && aligned) ? (npix & ~15LL) : 0;
+  long long tma_px = (int_eps && aligned) ? (npix & ~3LL) : 0;
+  if (frame_pitch >= (1ull << 40) || scan_pitch >= (1ull << 40)) tma_px = 0;   // tensor-map stride limit
 
   if (tma_px > 0) {
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
-    a.npix = npix; a.npix16 = tma_px;
+    a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
     a.n = n; a.F = F; a.e = (int)eps;
@@ -283,7 +317,10 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
       a.stages = stages;
       const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
       const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
-      const int rc = h_codes ? dispatch_tma<true>(a, grid, smem, st) : dispatch_tma<false>(a, grid, smem, st);
+      CUtensorMap tmap;
+      int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch);
+      if (rc != kOk) return rc;
+      rc = h_codes ? dispatch_tma<true>(tmap, a, grid, smem, st) : dispatch_tma<false>(tmap, a, grid, smem, st);
       if (rc != kOk) return rc;
     }
   }

@@ -290,6 +290,8 @@ def cam_proj_pairs(h_pixels, v_pixels, proj_size, img_white=None, device=None):
     cam = torch.empty((n, 2), dtype=torch.float32, device=dev)
     proj = torch.empty((n, 2), dtype=torch.float32, device=dev)
     rgb = torch.empty((n, 3), dtype=torch.uint8, device=dev) if white is not None else None
+    if n == 0:
+        return cam, proj, rgb
     with torch.cuda.device(dev):
         check(lib().sl_emit_pairs(_ptr(h_idx), _ptr(v_idx), _ptr(white), 1, off.h, off.w,
                                   int(proj_size[0]), int(proj_size[1]), _ptr(off.ws), _ptr(cam),
