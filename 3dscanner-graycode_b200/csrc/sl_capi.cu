@@ -157,16 +157,26 @@ int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
                            (cudaStream_t)stream);
 }
 
+int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+                   void* stream) {
+  if (!calib || !cam_rays || !proj_rays) { set_error("null buffer"); return kErrBadArg; }
+  if (cam_w < 1 || cam_h < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_lens_tables(*calib, cam_w, cam_h, cam_rays, proj_rays, (cudaStream_t)stream);
+}
+
 int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
-                  const SlCalib* calib, int precision, int B, int H, int W, const void* workspace,
-                  float* xyz, uint8_t* rgb, void* stream) {
+                  const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                  int B, int H, int W, const void* workspace, float* xyz, uint8_t* rgb, void* stream) {
   if (!h_idx || !v_idx || !workspace || !xyz || !calib) { set_error("null buffer"); return kErrBadArg; }
+  if ((cam_rays == nullptr) != (proj_rays == nullptr)) { set_error("cam_rays and proj_rays go together"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
-  return launch_emit_cloud(h_idx, v_idx, white_rgb, *calib, precision, B, H, W, workspace, xyz, rgb,
-                           (cudaStream_t)stream);
+  return launch_emit_cloud(h_idx, v_idx, white_rgb, *calib, precision, cam_rays, proj_rays, B, H, W, workspace,
+                           xyz, rgb, (cudaStream_t)stream);
 }
 
 int sl_triangulate_points(const float* cam_pts, const float* proj_pts, int64_t N,
@@ -213,6 +223,12 @@ struct SlPipeline {
   } slot[kSlots];
   int8_t* h_codes = nullptr;   // lazily allocated for sl_decode_host with codes
   int8_t* v_codes = nullptr;
+  // lens tables of the last calibration seen (rebuilt when the calibration changes)
+  SlCalib table_calib;
+  bool have_tables = false;
+  float* cam_rays = nullptr;
+  float* proj_rays = nullptr;
+  size_t proj_rays_elems = 0;
 };
 
 static void pipeline_free(SlPipeline* p) {
@@ -226,6 +242,7 @@ static void pipeline_free(SlPipeline* p) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   cudaFree(p->h_codes); cudaFree(p->v_codes);
+  cudaFree(p->cam_rays); cudaFree(p->proj_rays);
   delete p;
 }
 
@@ -284,6 +301,23 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
   const size_t npix = (size_t)p->H * p->W;
   const size_t stack = (size_t)p->F * npix;
   const int S = SlPipeline::kSlots;
+  if (calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad projector size"); return kErrBadArg; }
+  if (!p->have_tables || memcmp(&p->table_calib, calib, sizeof(SlCalib)) != 0) {
+    // (re)build the lens tables for this calibration; all slots must be idle while they change
+    for (auto& s : p->slot) SL_CUDA(cudaStreamSynchronize(s.stream));
+    const size_t pe = (size_t)calib->proj_w * calib->proj_h * 2;
+    if (!p->cam_rays) SL_CUDA(cudaMalloc(&p->cam_rays, npix * 2 * sizeof(float)));
+    if (pe > p->proj_rays_elems) {
+      cudaFree(p->proj_rays); p->proj_rays = nullptr; p->proj_rays_elems = 0;
+      SL_CUDA(cudaMalloc(&p->proj_rays, pe * sizeof(float)));
+      p->proj_rays_elems = pe;
+    }
+    int trc = launch_lens_tables(*calib, p->W, p->H, p->cam_rays, p->proj_rays, p->slot[0].stream);
+    if (trc) return trc;
+    SL_CUDA(cudaStreamSynchronize(p->slot[0].stream));
+    p->table_calib = *calib;
+    p->have_tables = true;
+  }
   long long total = 0;
   bool overflow = false;
   int rc = kOk;
@@ -322,8 +356,8 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     rc = launch_compact_offsets(s.h, s.v, 1, p->H, p->W, s.ws, s.counts, s.stream);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
-    rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, 1, p->H, p->W, s.ws,
-                           s.xyz, (white_rgb_host && rgb_host) ? s.rgb : nullptr, s.stream);
+    rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
+                           1, p->H, p->W, s.ws, s.xyz, (white_rgb_host && rgb_host) ? s.rgb : nullptr, s.stream);
     if (rc) break;
     SL_CUDA(cudaEventRecord(s.counted, s.stream));
   }

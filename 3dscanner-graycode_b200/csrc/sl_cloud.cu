@@ -213,6 +213,11 @@ __device__ __forceinline__ void undistort_fp32(float u, float v, const Lens<floa
   oy = yy * ww;
 }
 
+__device__ __forceinline__ void rays_to_point_fp64(float cx, float cy, float px, float py, const CalibDev& c,
+                                                   double& X, double& Y, double& Z);
+__device__ __forceinline__ void rays_to_point_fp32(float cx, float cy, float px, float py, const CalibDev& c,
+                                                   float& X, float& Y, float& Z);
+
 // triangulate.py:86-95 with the reference's dtype flow: rays f32, camera ray normalised in f32,
 // angles / lengths f64.
 __device__ __forceinline__ void triangulate_fp64(float u, float v, float pu, float pv, const CalibDev& c,
@@ -220,6 +225,23 @@ __device__ __forceinline__ void triangulate_fp64(float u, float v, float pu, flo
   float cx, cy, px, py;
   undistort_fp64(u, v, c.cam_d, cx, cy);
   undistort_fp64(pu, pv, c.proj_d, px, py);
+  rays_to_point_fp64(cx, cy, px, py, c, X, Y, Z);
+}
+
+// fp32: same triangle, but sin/cos of the angles taken from cross/dot products
+// (sin(gamma) = sin(alpha+beta)); no arccos.  With a = T x c, b = T x p:
+//   P = c * |T|^2 |b| / (|a| (T.p) - (T.c) |b|)
+__device__ __forceinline__ void triangulate_fp32(float u, float v, float pu, float pv, const CalibDev& c,
+                                                 float& X, float& Y, float& Z) {
+  float cx, cy, px, py;
+  undistort_fp32(u, v, c.cam_f, cx, cy);
+  undistort_fp32(pu, pv, c.proj_f, px, py);
+  rays_to_point_fp32(cx, cy, px, py, c, X, Y, Z);
+}
+
+// Same two formulas starting from already-undistorted rays (lens tables).
+__device__ __forceinline__ void rays_to_point_fp64(float cx, float cy, float px, float py, const CalibDev& c,
+                                                   double& X, double& Y, double& Z) {
   const float cn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), 1.0f));
   const float lx = __fdiv_rn(cx, cn), ly = __fdiv_rn(cy, cn), lz = __fdiv_rn(1.0f, cn);
   const double d_tl = dadd(dadd(dmul(c.T[0], (double)lx), dmul(c.T[1], (double)ly)), dmul(c.T[2], (double)lz));
@@ -234,14 +256,8 @@ __device__ __forceinline__ void triangulate_fp64(float u, float v, float pu, flo
   Z = dmul((double)lz, p_len);
 }
 
-// fp32: same triangle, but sin/cos of the angles taken from cross/dot products
-// (sin(gamma) = sin(alpha+beta)); no arccos.  With a = T x c, b = T x p:
-//   P = c * |T|^2 |b| / (|a| (T.p) - (T.c) |b|)
-__device__ __forceinline__ void triangulate_fp32(float u, float v, float pu, float pv, const CalibDev& c,
-                                                 float& X, float& Y, float& Z) {
-  float cx, cy, px, py;
-  undistort_fp32(u, v, c.cam_f, cx, cy);
-  undistort_fp32(pu, pv, c.proj_f, px, py);
+__device__ __forceinline__ void rays_to_point_fp32(float cx, float cy, float px, float py, const CalibDev& c,
+                                                   float& X, float& Y, float& Z) {
   const float t0 = c.Tf[0], t1 = c.Tf[1], t2 = c.Tf[2];
   const float ax = t1 - t2 * cy, ay = t2 * cx - t0, az = t0 * cy - t1 * cx;     // T x (cx,cy,1)
   const float bx = t1 - t2 * py, by = t2 * px - t0, bz = t0 * py - t1 * px;     // T x (px,py,1)
@@ -253,8 +269,24 @@ __device__ __forceinline__ void triangulate_fp32(float u, float v, float pu, flo
   X = cx * s; Y = cy * s; Z = s;
 }
 
+// Lens table: the undistorted, normalised ray of every lattice point (u, v) in [0,w) x [0,h),
+// computed ONCE per calibration with the exact fp64 iteration (bit-identical to
+// cv2.undistortPoints, triangulate.py:84-85).  The camera pixel grid and the projector pixel grid
+// never change between scans, so the per-scan kernels look the rays up instead of iterating.
+__global__ void __launch_bounds__(256) lens_table_kernel(const Lens<double> lens, int w, int h,
+                                                         float2* __restrict__ table) {
+  const long long n = (long long)w * h;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+    float ox, oy;
+    undistort_fp64((float)x, (float)y, lens, ox, oy);
+    table[i] = make_float2(ox, oy);
+  }
+}
+
 // ------------------------------------------------------------------ K2 emit
-enum { kModePairs = 0, kModeCloud32 = 1, kModeCloud64 = 2 };
+enum { kModePairs = 0, kModeCloud32 = 1, kModeCloud64 = 2, kModeTable32 = 3, kModeTable64 = 4 };
 
 struct EmitArgs {
   const int16_t* h;
@@ -265,6 +297,8 @@ struct EmitArgs {
   float* out_a;             // pairs: cam_pts (N,2)   cloud: xyz (N,3)
   float* out_b;             // pairs: proj_pts (N,2)
   uint8_t* rgb;             // nullable
+  const float2* cam_rays;   // table modes: [H][W] undistorted camera rays (rotated by R)
+  const float2* proj_rays;  // table modes: [proj_h][proj_w] undistorted projector rays
   int H, W, bands;
   CalibDev cal;
 };
@@ -324,6 +358,18 @@ __global__ void __launch_bounds__(kEmitThreads) emit_kernel(const EmitArgs a) {
       float X, Y, Z;
       triangulate_fp32(u, w, pu, pv, a.cal, X, Y, Z);
       a.out_a[o * 3 + 0] = X; a.out_a[o * 3 + 1] = Y; a.out_a[o * 3 + 2] = Z;
+    } else if (MODE == kModeTable32 || MODE == kModeTable64) {
+      const float2 c = __ldg(a.cam_rays + (size_t)(y0 + lane) * a.W + x);
+      const float2 p = __ldg(a.proj_rays + (size_t)min(a.cal.proj_h - 1, vv) * a.cal.proj_w + min(a.cal.proj_w - 1, hv));
+      if (MODE == kModeTable32) {
+        float X, Y, Z;
+        rays_to_point_fp32(c.x, c.y, p.x, p.y, a.cal, X, Y, Z);
+        a.out_a[o * 3 + 0] = X; a.out_a[o * 3 + 1] = Y; a.out_a[o * 3 + 2] = Z;
+      } else {
+        double X, Y, Z;
+        rays_to_point_fp64(c.x, c.y, p.x, p.y, a.cal, X, Y, Z);
+        a.out_a[o * 3 + 0] = (float)X; a.out_a[o * 3 + 1] = (float)Y; a.out_a[o * 3 + 2] = (float)Z;
+      }
     } else {
       double X, Y, Z;
       triangulate_fp64(u, w, pu, pv, a.cal, X, Y, Z);
@@ -436,6 +482,7 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
   EmitArgs a;
   a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_base = c.col_base;
   a.out_a = out_a; a.out_b = out_b; a.rgb = rgb; a.H = H; a.W = W; a.bands = c.bands;
+  a.cam_rays = nullptr; a.proj_rays = nullptr;
   return a;
 }
 
@@ -452,13 +499,30 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
   return kOk;
 }
 
+int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+                       cudaStream_t st) {
+  const CalibDev cal = make_calib(calib);
+  auto blocks = [](long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); };
+  lens_table_kernel<<<blocks((long long)cam_w * cam_h), 256, 0, st>>>(cal.cam_d, cam_w, cam_h, (float2*)cam_rays);
+  count_launch();
+  lens_table_kernel<<<blocks((long long)cal.proj_w * cal.proj_h), 256, 0, st>>>(cal.proj_d, cal.proj_w, cal.proj_h,
+                                                                               (float2*)proj_rays);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
-                      int precision, int B, int H, int W, const void* ws, float* xyz, uint8_t* rgb,
-                      cudaStream_t st) {
+                      int precision, const float* cam_rays, const float* proj_rays, int B, int H, int W,
+                      const void* ws, float* xyz, uint8_t* rgb, cudaStream_t st) {
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, xyz, nullptr, rgb);
   a.cal = make_calib(calib);
+  a.cam_rays = (const float2*)cam_rays; a.proj_rays = (const float2*)proj_rays;
   dim3 g((W + kTileCols - 1) / kTileCols, a.bands, B);
-  if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, kEmitThreads, 0, st>>>(a);
+  if (cam_rays) {
+    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, kEmitThreads, 0, st>>>(a);
+    else emit_kernel<kModeTable32><<<g, kEmitThreads, 0, st>>>(a);
+  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, kEmitThreads, 0, st>>>(a);
   else emit_kernel<kModeCloud32><<<g, kEmitThreads, 0, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());

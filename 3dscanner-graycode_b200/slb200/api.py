@@ -365,11 +365,29 @@ class CloudBuffers:
                    torch.empty((cap, 3), dtype=torch.uint8, device=device))
 
 
+class LensTables:
+    """Undistorted rays of the camera and projector pixel lattices for one calibration
+    (``sl_lens_tables``); build once, reuse for every scan."""
+
+    def __init__(self, calib: Calibration, cam_size: Tuple[int, int], device):
+        w, h = int(cam_size[0]), int(cam_size[1])
+        pw, ph = calib.proj_size
+        self.cam_size, self.proj_size = (w, h), (pw, ph)
+        self.cam = torch.empty((h, w, 2), dtype=torch.float32, device=device)
+        self.proj = torch.empty((ph, pw, 2), dtype=torch.float32, device=device)
+        s = calib.struct()
+        with torch.cuda.device(device):
+            check(lib().sl_lens_tables(C.byref(s), w, h, _ptr(self.cam), _ptr(self.proj), _stream()))
+
+
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
                   precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
-                  calib_struct: Optional[SlCalib] = None) -> CloudBuffers:
+                  calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None) -> CloudBuffers:
     """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
     decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
+
+    ``tables`` (LensTables of the same calibration / sizes) replaces the per-pixel undistortion
+    iterations by look-ups of exact precomputed rays; without it the iterations run in the kernel.
 
     Results are in the returned buffers: ``xyz[:counts[B]]`` / ``rgb[:counts[B]]`` packed scan
     after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
@@ -386,6 +404,8 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
         if white_rgb.numel() != b * h * w * 3:
             raise ValueError("white_rgb must be ([B,]H,W,3)")
     s = calib_struct if calib_struct is not None else calib.struct()
+    if tables is not None and (tables.cam_size != (w, h) or tables.proj_size != tuple(calib.proj_size)):
+        raise ValueError("lens tables were built for another image / panel size")
     L = lib()
     st = _stream()
     with torch.cuda.device(dev):
@@ -394,7 +414,9 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
         check(L.sl_compact_offsets(_ptr(buffers.h_idx), _ptr(buffers.v_idx), b, h, w,
                                    _ptr(buffers.ws), _ptr(buffers.counts), st))
         check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
-                              _PREC[precision], b, h, w, _ptr(buffers.ws), _ptr(buffers.xyz),
+                              _PREC[precision], _ptr(tables.cam) if tables is not None else None,
+                              _ptr(tables.proj) if tables is not None else None,
+                              b, h, w, _ptr(buffers.ws), _ptr(buffers.xyz),
                               _ptr(buffers.rgb) if white_rgb is not None else None, st))
     return buffers
 

@@ -229,11 +229,12 @@ def run_gpu(args):
         ring_frames.append(fr); ring_white.append(wh)
     del pats
     bufs = CloudBuffers.allocate(1, H, W, dev)
+    tables = None if args.lens == "iterate" else slb200.LensTables(calib, CAM_SIZE, dev)   # once per calibration
     torch.cuda.synchronize()
 
     def step(i):
         slb200.scan_to_cloud(ring_frames[i % RING], ring_white[i % RING], calib, precision="fp32",
-                             buffers=bufs, calib_struct=cstruct)
+                             buffers=bufs, calib_struct=cstruct, tables=tables)
 
     # one CUDA graph per ring slot: the 5 launches of a step replay without host launch latency
     before = slb200.launch_count()
@@ -367,7 +368,10 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_scan": N_FRAMES, "n_bits": N_BITS,
                        "scans_per_step_per_gpu": 1, "valid_fraction": valid_pts / (W * H),
-                       "triangulation_precision": "fp32", "parallelism": f"scan-sharded x{world}",
+                       "triangulation_precision": "fp32",
+                       "lens": ("exact fp64 ray tables built once per calibration (sl_lens_tables)" if tables is not None
+                                else "5 Brown-Conrady iterations per valid pixel in the emit kernel"),
+                       "parallelism": f"scan-sharded x{world}",
                        "l2": f"inputs rotate over a ring of {RING} resident scans ({RING * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "CUDA graph per scan (decode, count, band-prefix, column-scan, emit)"},
             "scans_per_s": world * K / (ms_total * 1e-3),
@@ -390,6 +394,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lens", default="tables", choices=["tables", "iterate"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

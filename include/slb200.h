@@ -111,13 +111,23 @@ int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
                   int H, int W, int proj_w, int proj_h, const void* workspace, float* cam_pts,
                   float* proj_pts, uint8_t* rgb, void* stream);
 
-/* Fused get_cam_proj_pts + triangulate (triangulate.py:39-97): undistorts both sides
- * (5 Brown-Conrady iterations, cv2.undistortPoints semantics), law-of-sines depth, ordered
- * compaction.  xyz (N,3) f32, rgb (N,3) u8 (nullable with white_rgb), packed over the batch.
+/* Lens tables: the undistorted normalised ray of every camera pixel (rotated by R) and of every
+ * projector pixel -- cv2.undistortPoints (triangulate.py:84-85: 5 Brown-Conrady fixed-point
+ * iterations, fp64 arithmetic, f32 result) evaluated once per calibration on the two pixel
+ * lattices, which never change between scans.  cam_rays device f32 [cam_h][cam_w][2],
+ * proj_rays device f32 [proj_h][proj_w][2]. */
+int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+                   void* stream);
+
+/* Fused get_cam_proj_pts + triangulate (triangulate.py:39-97): undistortion of both sides,
+ * law-of-sines depth, ordered compaction.  With cam_rays/proj_rays (from sl_lens_tables, same
+ * calibration and sizes) the rays are looked up; with both NULL the 5 Brown-Conrady iterations
+ * run in the kernel for every valid pixel (fp32 or fp64 per `precision`).
+ * xyz (N,3) f32, rgb (N,3) u8 (nullable with white_rgb), packed over the batch.
  * Requires sl_compact_offsets on the same workspace first. */
 int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
-                  const SlCalib* calib, int precision, int B, int H, int W, const void* workspace,
-                  float* xyz, uint8_t* rgb, void* stream);
+                  const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                  int B, int H, int W, const void* workspace, float* xyz, uint8_t* rgb, void* stream);
 
 /* Triangulate.triangulate (triangulate.py:73-97) on caller-supplied point pairs.
  * cam_pts, proj_pts device f32 (N,2); out device f64 (3,N) like the reference's return. */

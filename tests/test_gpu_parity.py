@@ -285,6 +285,49 @@ def test_batched_cloud_matches_single(T):
         start += n
 
 
+def test_lens_tables_exact_and_table_modes(T):
+    """sl_lens_tables reproduces cv2.undistortPoints (via the pinned oracle restatement) bit for bit on
+    both pixel lattices, and the table-driven emit agrees with the in-kernel iteration."""
+    import slb200
+    from slb200 import synth
+    cam_size, proj_size = (320, 200), (1024, 768)
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    tab = slb200.LensTables(calib, cam_size, "cuda")
+    ys, xs = np.mgrid[0:200, 0:320]
+    lattice = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.float32)
+    ref_cam = O.undistort_points(lattice, calib.cam_mtx, calib.cam_dist, R=calib.proj_R).reshape(200, 320, 2)
+    np.testing.assert_array_equal(tab.cam.cpu().numpy(), ref_cam)
+    ys, xs = np.mgrid[0:768, 0:1024]
+    lattice = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.float32)
+    ref_proj = O.undistort_points(lattice, calib.proj_mtx, calib.proj_dist).reshape(768, 1024, 2)
+    np.testing.assert_array_equal(tab.proj.cpu().numpy(), ref_proj)
+    # out-of-domain lens (shipped projector intrinsics on a 1920x1080 panel): still exact, incl. the icdist<0 bail-out
+    from slb200 import calib_data as cd
+    wild = slb200.Calibration.from_reference(cd.CAM_1440_MTX, cd.CAM_1440_DIST, cd.PROJ_MTX, cd.PROJ_DIST, calib.proj_R,
+                                             calib.proj_T, (1920, 1080), (1920, 1080))
+    tab2 = slb200.LensTables(wild, (64, 48), "cuda")
+    ys, xs = np.mgrid[0:1080, 0:1920]
+    lattice = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.float32)
+    ref2 = O.undistort_points(lattice, wild.proj_mtx, wild.proj_dist).reshape(1080, 1920, 2)
+    np.testing.assert_array_equal(tab2.proj.cpu().numpy(), ref2)
+
+    frames, white = synth.render_scan(cam_size, proj_size, seed=5, device="cuda")
+    it64 = slb200.scan_to_cloud(frames, white, calib, precision="fp64")
+    tb64 = slb200.scan_to_cloud(frames, white, calib, precision="fp64", tables=tab)
+    tb32 = slb200.scan_to_cloud(frames, white, calib, precision="fp32", tables=tab)
+    n = int(it64.counts[1])
+    assert n == int(tb64.counts[1]) == int(tb32.counts[1]) and n > 0
+    assert T.equal(it64.xyz[:n], tb64.xyz[:n])              # same rays, same fp64 formula -> identical
+    assert T.equal(it64.rgb[:n], tb32.rgb[:n])
+    hp, vp = O.decode_pixels(frames.cpu().numpy().astype(np.float64))
+    cam, proj, _ = O.cam_proj_pairs(hp, vp, proj_size, white.cpu().numpy())
+    pts = O.triangulate(cam, proj, calib.cam_mtx, calib.cam_dist, calib.proj_mtx, calib.proj_dist, calib.proj_R, calib.proj_T)
+    rel = np.linalg.norm(tb32.xyz[:n].cpu().numpy().astype(np.float64).T - pts, axis=0) / np.linalg.norm(pts, axis=0)
+    assert rel.max() < 1e-4, rel.max()                       # north_star tolerance, fp32
+    with pytest.raises(ValueError):
+        slb200.scan_to_cloud(frames, white, calib, tables=tab2)
+
+
 # ------------------------------------------------------------------ host-buffer pipeline + drop-in API
 def test_pipeline_host_buffers(T):
     import slb200

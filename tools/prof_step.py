@@ -19,6 +19,7 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--size", default="1080p")
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--precision", default="fp32")
+ap.add_argument("--lens", default="tables")
 a = ap.parse_args()
 cam, proj = SIZES[a.size]
 dev = torch.device("cuda", 0)
@@ -32,8 +33,9 @@ else:
     frames = [s[0] for s in scans]
     white = [s[1] for s in scans]
 bufs = slb200.api.CloudBuffers.allocate(a.batch, cam[1], cam[0], dev)
+tables = slb200.LensTables(calib, cam, dev) if a.lens == "tables" else None
 torch.cuda.synchronize()
 for i in range(a.steps):
-    slb200.scan_to_cloud(frames[i % len(frames)], white[i % len(white)], calib, precision=a.precision, buffers=bufs)
+    slb200.scan_to_cloud(frames[i % len(frames)], white[i % len(white)], calib, precision=a.precision, buffers=bufs, tables=tables)
 torch.cuda.synchronize()
 print("valid fraction", float(bufs.counts[-1]) / (a.batch * cam[0] * cam[1]))
