@@ -81,7 +81,7 @@ int sl_device_check(int device) {
 
 int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                 int8_t* v_codes, void* stream) {
+                 int8_t* v_codes, void* cloud_workspace, void* stream) {
   int rc = check_decode_shape(B, F, H, W);
   if (rc) return rc;
   if (!frames || !h_idx || !v_idx) { set_error("frames, h_idx, v_idx must be non-null"); return kErrBadArg; }
@@ -92,8 +92,11 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
   if (!(eps == eps)) { set_error("eps is NaN"); return kErrBadArg; }
   int sms = 0;
   if ((rc = device_gate(&sms))) return rc;
+  uint32_t* bitmap = nullptr;
+  long long words = 0;
+  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words);
   return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, h_codes, v_codes,
-                       sms, (cudaStream_t)stream);
+                       bitmap, words, sms, (cudaStream_t)stream);
 }
 
 int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
@@ -144,6 +147,14 @@ int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H,
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
   return launch_compact_offsets(h_idx, v_idx, B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
+}
+
+int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream) {
+  if (!workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_offsets_from_bitmap(B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
 }
 
 int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, int B,
@@ -347,13 +358,16 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     SL_CUDA(cudaMemcpyAsync(s.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, s.stream));
     if (white_rgb_host)
       SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host + (size_t)i * npix * 3, npix * 3, cudaMemcpyHostToDevice, s.stream));
-    rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, p->sms, s.stream);
+    long long bm_words = 0;
+    uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words);
+    rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
+                       p->sms, s.stream);
     if (rc) break;
     if (h_idx_host) {
       SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, s.h, npix * 2, cudaMemcpyDeviceToHost, s.stream));
       SL_CUDA(cudaMemcpyAsync(v_idx_host + (size_t)i * npix, s.v, npix * 2, cudaMemcpyDeviceToHost, s.stream));
     }
-    rc = launch_compact_offsets(s.h, s.v, 1, p->H, p->W, s.ws, s.counts, s.stream);
+    rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
     rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
@@ -400,7 +414,7 @@ int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
     auto& u = h_codes_host ? p->slot[0] : s;
     SL_CUDA(cudaMemcpyAsync(u.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, st));
     rc = launch_decode(u.frames, 1, p->F, (long long)npix, npix, stack, eps, u.h, u.v,
-                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, p->sms, st);
+                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, nullptr, 0, p->sms, st);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, u.h, npix * 2, cudaMemcpyDeviceToHost, st));
     SL_CUDA(cudaMemcpyAsync(v_idx_host + (size_t)i * npix, u.v, npix * 2, cudaMemcpyDeviceToHost, st));

@@ -3,11 +3,13 @@
 // The reference emits points x-major (outer loop over camera x, inner over y:
 // scanner/triangulation/triangulate.py:52-53).  To reproduce that order deterministically and
 // without atomics the image is cut into bands of 32 rows:
-//   K3a count_kernel       valid pixels per (scan, band, column)
-//   K3b bandprefix_kernel  exclusive prefix down each column + column totals
-//   K3c colscan_kernel     exclusive scan of the column totals in (scan, x) order -> packed bases
-//   K2  emit_kernel        one warp per column of a 32-row band (lane = row): warp ballot gives the
-//                          rank inside the band, so a warp writes a contiguous run of points.
+//   (K1 writes a flat validity bitmap, 1 bit per pixel; K3a builds it from caller-supplied indices)
+//   K3b strip_prefix_kernel  one warp per 32-column strip: 32x32 ballot transposes of the bitmap give
+//                            per-(band, column) counts, prefixed down each column + column totals
+//   K3c colscan_kernel       exclusive scan of the column totals in (scan, x) order -> packed bases
+//   K2  emit_kernel          one warp per 32-row x 16-column tile; compute phase has lane = row, so a
+//                            warp ballot gives the rank inside the band and the warp writes a
+//                            contiguous run of points per column.
 // K2 stages its tile through shared memory so the global reads stay row-major / coalesced.
 #include <cmath>
 #include "sl_common.cuh"
@@ -16,23 +18,31 @@
 
 namespace sl {
 
-constexpr int kBandRows = 32;
-constexpr int kTileCols = 64;
-constexpr int kEmitThreads = 256;
+constexpr int kBandRows = 32;       // rows per band = lanes per warp
+constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
+constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
+constexpr int kEmitWarps = 8;
 
 // ------------------------------------------------------------------ workspace
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static size_t bitmap_words(long long npix) { return (size_t)((npix + 31) / 32) + 1; }   // +1: funnel reads
+
 size_t cloud_workspace_bytes(int B, int H, int W) {
   const size_t bands = (size_t)(H + kBandRows - 1) / kBandRows;
-  return align_up((size_t)B * bands * W * 4, 256) + align_up((size_t)B * W * 4, 256) +
-         align_up((size_t)B * W * 8, 256);
+  return align_up((size_t)B * bitmap_words((long long)H * W) * 4, 256) +      // validity bitmap
+         align_up((size_t)B * bands * W * 4, 256) +                            // band_pre
+         align_up((size_t)B * W * 4, 256) +                                    // col_tot
+         align_up((size_t)B * W * 8, 256);                                     // col_base
 }
 
 CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
   CloudWorkspace c;
   c.bands = (H + kBandRows - 1) / kBandRows;
+  c.bitmap_words = (long long)bitmap_words((long long)H * W);
   uint8_t* p = static_cast<uint8_t*>(ws);
+  c.bitmap = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)B * c.bitmap_words * 4, 256);
   c.band_cnt = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)B * c.bands * W * 4, 256);
   c.col_tot = reinterpret_cast<uint32_t*>(p);
@@ -41,39 +51,68 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
   return c;
 }
 
-// ------------------------------------------------------------------ K3a..c offsets
-__global__ void __launch_bounds__(128) count_kernel(const int16_t* __restrict__ h,
-                                                     const int16_t* __restrict__ v, int H, int W,
-                                                     uint32_t* __restrict__ band_cnt) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int band = blockIdx.y, b = blockIdx.z, bands = gridDim.y;
-  if (x >= W) return;
-  const size_t img = (size_t)b * H * W;
-  const int y0 = band * kBandRows;
-  const int y1 = min(H, y0 + kBandRows);
-  uint32_t c = 0;
-#pragma unroll 8
-  for (int y = y0; y < y1; ++y) {
-    const size_t i = img + (size_t)y * W + x;
-    c += (h[i] != -1 && v[i] != -1) ? 1u : 0u;     // triangulate.py:56
+// ------------------------------------------------------------------ K3 offsets
+// K3a (only when the indices come from the caller rather than from the decode kernel):
+// validity bitmap, bit i of scan b = (h[i] != -1 && v[i] != -1)   (triangulate.py:56)
+__global__ void __launch_bounds__(256) bitmap_from_idx_kernel(const int16_t* __restrict__ h,
+                                                               const int16_t* __restrict__ v, long long npix,
+                                                               long long words_per_scan, int B,
+                                                               uint32_t* __restrict__ bitmap) {
+  const long long padded = (npix + 31) & ~31LL;
+  const long long total = padded * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / padded, px = i - b * padded;
+    bool ok = false;
+    if (px < npix) ok = (h[b * npix + px] != -1) && (v[b * npix + px] != -1);
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) bitmap[b * words_per_scan + (px >> 5)] = m;
   }
-  band_cnt[((size_t)b * bands + band) * W + x] = c;
 }
 
-__global__ void __launch_bounds__(256) bandprefix_kernel(uint32_t* __restrict__ band_cnt,
-                                                          uint32_t* __restrict__ col_tot, int B,
-                                                          int bands, int W) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= (long long)B * W) return;
-  const int b = (int)(i / W), x = (int)(i - (long long)b * W);
+// K3b: one warp per strip of 32 columns walks down the bands.  Lane r fetches the 32 validity bits
+// of row (band*32 + r) in the strip (funnel shift out of the flat bitmap), 32 ballots transpose the
+// 32x32 bit block so lane c holds the column word of column x0+c; its popcount feeds the running
+// prefix down the column.  Outputs: band_pre[b][band][x] (exclusive prefix) and col_tot[b][x].
+__global__ void __launch_bounds__(128) strip_prefix_kernel(const uint32_t* __restrict__ bitmap,
+                                                            long long words_per_scan, int B, int H, int W,
+                                                            int bands, uint32_t* __restrict__ band_pre,
+                                                            uint32_t* __restrict__ col_tot) {
+  const int strips = (W + kStripCols - 1) / kStripCols;
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_id >= (long long)B * strips) return;
+  const int b = (int)(warp_id / strips), strip = (int)(warp_id - (long long)b * strips);
+  const int x0 = strip * kStripCols, x = x0 + lane;
+  const uint32_t* bm = bitmap + (size_t)b * words_per_scan;
+  const uint32_t colmask = (W - x0 >= 32) ? 0xffffffffu : ((1u << (W - x0)) - 1u);
   uint32_t run = 0;
-  for (int k = 0; k < bands; ++k) {
-    uint32_t* p = band_cnt + ((size_t)b * bands + k) * W + x;
-    const uint32_t c = *p;
-    *p = run;
-    run += c;
+  uint32_t next = 0;
+  {   // prefetch band 0
+    const int y = lane;
+    if (y < H) {
+      const long long i = (long long)y * W + x0;
+      next = __funnelshift_r(bm[i >> 5], bm[(i >> 5) + 1], (uint32_t)(i & 31)) & colmask;
+    }
   }
-  col_tot[i] = run;
+  for (int band = 0; band < bands; ++band) {
+    const uint32_t rowword = next;
+    next = 0;
+    const int yn = (band + 1) * kBandRows + lane;
+    if (band + 1 < bands && yn < H) {
+      const long long i = (long long)yn * W + x0;
+      next = __funnelshift_r(bm[i >> 5], bm[(i >> 5) + 1], (uint32_t)(i & 31)) & colmask;
+    }
+    uint32_t colword = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const uint32_t bits = __ballot_sync(0xffffffffu, (rowword >> c) & 1u);
+      if (lane == c) colword = bits;
+    }
+    if (x < W) band_pre[((size_t)b * bands + band) * W + x] = run;
+    run += __popc(colword);
+  }
+  if (x < W) col_tot[(size_t)b * W + x] = run;
 }
 
 // single block: exclusive scan of m uint32 values into int64, plus per-scan totals
@@ -299,85 +338,133 @@ struct EmitArgs {
   uint8_t* rgb;             // nullable
   const float2* cam_rays;   // table modes: [H][W] undistorted camera rays (rotated by R)
   const float2* proj_rays;  // table modes: [proj_h][proj_w] undistorted projector rays
-  int H, W, bands;
+  int H, W, bands, tiles_x;
+  long long total_tiles;
   CalibDev cal;
 };
 
-constexpr int kIdxPitch = kTileCols + 2;          // int16 elements; 33 words -> conflict-free column reads
-constexpr int kRgbPitch = kTileCols * 3 + 4;      // bytes; 49 words
+// Shared-memory tile of one warp: 32 rows x kEmitCols columns, padded so that the column-major
+// reads (lane = row) hit 32 different banks.
+constexpr int kIdxPitch = kEmitCols + 2;              // int16: 18 -> 9 words per row (odd)
+constexpr int kRgbPitch = kEmitCols * 3 + 4;          // bytes: 52 -> 13 words per row (odd)
+struct EmitTile {
+  int16_t h[kBandRows * kIdxPitch];
+  int16_t v[kBandRows * kIdxPitch];
+  uint8_t c[kBandRows * kRgbPitch];
+};
 
+// One warp per tile of 32 rows x kEmitCols columns.  Load phase is row-major (coalesced, vector
+// loads when the row pitch allows); compute phase is column-major (lane = row), so the warp ballot
+// gives each valid pixel its rank inside the column and the warp writes one contiguous run of
+// points per column -- the reference's x-major order (triangulate.py:52-53), no atomics.
 template <int MODE>
-__global__ void __launch_bounds__(kEmitThreads) emit_kernel(const EmitArgs a) {
-  __shared__ int16_t sh[kBandRows * kIdxPitch];
-  __shared__ int16_t sv[kBandRows * kIdxPitch];
-  __shared__ __align__(4) uint8_t sc[kBandRows * kRgbPitch];
-  const int x0 = blockIdx.x * kTileCols, band = blockIdx.y, b = blockIdx.z;
-  const int y0 = band * kBandRows;
-  const int rows = min(kBandRows, a.H - y0), cols = min(kTileCols, a.W - x0);
+__global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a) {
+  __shared__ __align__(16) EmitTile tiles[kEmitWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kEmitWarps + warp;
+  if (t >= a.total_tiles) return;
+  EmitTile& tile = tiles[warp];
+  const int tx = (int)(t % a.tiles_x);
+  const long long rest = t / a.tiles_x;
+  const int band = (int)(rest % a.bands), b = (int)(rest / a.bands);
+  const int x0 = tx * kEmitCols, y0 = band * kBandRows;
+  const int rows = min(kBandRows, a.H - y0), cols = min(kEmitCols, a.W - x0);
   const size_t img = (size_t)b * a.H * a.W;
   const bool has_rgb = a.white != nullptr && a.rgb != nullptr;
 
-  // row-major, coalesced staging of the tile
-  for (int i = threadIdx.x; i < kBandRows * kTileCols; i += kEmitThreads) {
-    const int r = i / kTileCols, cidx = i - r * kTileCols;
-    int16_t hv = -1, vv = -1;
-    if (r < rows && cidx < cols) {
-      const size_t g = img + (size_t)(y0 + r) * a.W + x0 + cidx;
-      hv = a.h[g]; vv = a.v[g];
-    }
-    sh[r * kIdxPitch + cidx] = hv;
-    sv[r * kIdxPitch + cidx] = vv;
-  }
-  if (has_rgb) {
-    for (int i = threadIdx.x; i < kBandRows * kTileCols * 3; i += kEmitThreads) {
-      const int r = i / (kTileCols * 3), cb = i - r * (kTileCols * 3);
-      uint8_t val = 0;
-      if (r < rows && cb < cols * 3) val = a.white[(img + (size_t)(y0 + r) * a.W + x0) * 3 + cb];
-      sc[r * kRgbPitch + cb] = val;
-    }
-  }
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int cidx = warp; cidx < cols; cidx += kEmitThreads / 32) {
-    const int hv = sh[lane * kIdxPitch + cidx], vv = sv[lane * kIdxPitch + cidx];
-    const bool valid = (hv != -1) && (vv != -1);
-    const uint32_t m = __ballot_sync(0xffffffffu, valid);
-    if (m == 0) continue;
-    const int x = x0 + cidx;
-    const long long base = a.col_base[(size_t)b * a.W + x] +
-                           (long long)a.band_pre[((size_t)b * a.bands + band) * a.W + x];
-    if (!valid) continue;
-    const long long o = base + __popc(m & ((1u << lane) - 1u));
-    const float u = (float)x, w = (float)(y0 + lane);
-    const float pu = (float)min(a.cal.proj_w - 1, hv), pv = (float)min(a.cal.proj_h - 1, vv);   // triangulate.py:60-61
-    if (MODE == kModePairs) {
-      reinterpret_cast<float2*>(a.out_a)[o] = make_float2(u, w);
-      reinterpret_cast<float2*>(a.out_b)[o] = make_float2(pu, pv);
-    } else if (MODE == kModeCloud32) {
-      float X, Y, Z;
-      triangulate_fp32(u, w, pu, pv, a.cal, X, Y, Z);
-      a.out_a[o * 3 + 0] = X; a.out_a[o * 3 + 1] = Y; a.out_a[o * 3 + 2] = Z;
-    } else if (MODE == kModeTable32 || MODE == kModeTable64) {
-      const float2 c = __ldg(a.cam_rays + (size_t)(y0 + lane) * a.W + x);
-      const float2 p = __ldg(a.proj_rays + (size_t)min(a.cal.proj_h - 1, vv) * a.cal.proj_w + min(a.cal.proj_w - 1, hv));
-      if (MODE == kModeTable32) {
-        float X, Y, Z;
-        rays_to_point_fp32(c.x, c.y, p.x, p.y, a.cal, X, Y, Z);
-        a.out_a[o * 3 + 0] = X; a.out_a[o * 3 + 1] = Y; a.out_a[o * 3 + 2] = Z;
-      } else {
-        double X, Y, Z;
-        rays_to_point_fp64(c.x, c.y, p.x, p.y, a.cal, X, Y, Z);
-        a.out_a[o * 3 + 0] = (float)X; a.out_a[o * 3 + 1] = (float)Y; a.out_a[o * 3 + 2] = (float)Z;
+  // ---- load phase
+  if ((a.W & 3) == 0 && cols == kEmitCols) {
+    // 16 int16 per row = 4 x 8 bytes: lane -> (row = lane/4 + 8*it, 4 columns at (lane%4)*4)
+    const int rr = lane >> 2, c4 = (lane & 3) * 4;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = rr + 8 * it;
+      uint2 hv = make_uint2(0xffffffffu, 0xffffffffu), vv = hv;
+      if (r < rows) {
+        const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+        hv = __ldg(reinterpret_cast<const uint2*>(a.h + g));
+        vv = __ldg(reinterpret_cast<const uint2*>(a.v + g));
       }
-    } else {
-      double X, Y, Z;
-      triangulate_fp64(u, w, pu, pv, a.cal, X, Y, Z);
-      a.out_a[o * 3 + 0] = (float)X; a.out_a[o * 3 + 1] = (float)Y; a.out_a[o * 3 + 2] = (float)Z;
+      uint32_t* dh = reinterpret_cast<uint32_t*>(tile.h + r * kIdxPitch + c4);
+      uint32_t* dv = reinterpret_cast<uint32_t*>(tile.v + r * kIdxPitch + c4);
+      dh[0] = hv.x; dh[1] = hv.y; dv[0] = vv.x; dv[1] = vv.y;
     }
     if (has_rgb) {
-      const uint8_t* s = sc + lane * kRgbPitch + cidx * 3;
-      a.rgb[o * 3 + 0] = s[0]; a.rgb[o * 3 + 1] = s[1]; a.rgb[o * 3 + 2] = s[2];     // triangulate.py:64
+      // 48 bytes per row = 12 words: 384 words per tile, 12 iterations of 32 lanes
+#pragma unroll
+      for (int it = 0; it < 12; ++it) {
+        const int wi = it * 32 + lane, r = wi / 12, cw = wi - r * 12;
+        uint32_t val = 0;
+        if (r < rows) val = __ldg(reinterpret_cast<const uint32_t*>(a.white + (img + (size_t)(y0 + r) * a.W + x0) * 3) + cw);
+        *reinterpret_cast<uint32_t*>(tile.c + r * kRgbPitch + cw * 4) = val;
+      }
+    }
+  } else {
+    for (int i = lane; i < kBandRows * kEmitCols; i += 32) {
+      const int r = i / kEmitCols, cidx = i - r * kEmitCols;
+      int16_t hv = -1, vv = -1;
+      if (r < rows && cidx < cols) {
+        const size_t g = img + (size_t)(y0 + r) * a.W + x0 + cidx;
+        hv = a.h[g]; vv = a.v[g];
+      }
+      tile.h[r * kIdxPitch + cidx] = hv;
+      tile.v[r * kIdxPitch + cidx] = vv;
+    }
+    if (has_rgb) {
+      for (int i = lane; i < kBandRows * kEmitCols * 3; i += 32) {
+        const int r = i / (kEmitCols * 3), cb = i - r * (kEmitCols * 3);
+        uint8_t val = 0;
+        if (r < rows && cb < cols * 3) val = a.white[(img + (size_t)(y0 + r) * a.W + x0) * 3 + cb];
+        tile.c[r * kRgbPitch + cb] = val;
+      }
+    }
+  }
+  // packed output offset of each column's first point in this band (lane c <-> column x0+c)
+  long long my_base = 0;
+  if (lane < cols)
+    my_base = a.col_base[(size_t)b * a.W + x0 + lane] +
+              (long long)a.band_pre[((size_t)b * a.bands + band) * a.W + x0 + lane];
+  __syncwarp();
+
+  // ---- compute phase
+#pragma unroll 2
+  for (int cidx = 0; cidx < cols; ++cidx) {
+    const int hv = tile.h[lane * kIdxPitch + cidx], vv = tile.v[lane * kIdxPitch + cidx];
+    const bool valid = (hv != -1) && (vv != -1);
+    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
+    if (!valid) continue;
+    const int x = x0 + cidx;
+    const long long o = base + __popc(m & ((1u << lane) - 1u));
+    const float u = (float)x, w = (float)(y0 + lane);
+    const int hc = min(a.cal.proj_w - 1, hv), vc = min(a.cal.proj_h - 1, vv);       // triangulate.py:60-61
+    if (MODE == kModePairs) {
+      reinterpret_cast<float2*>(a.out_a)[o] = make_float2(u, w);
+      reinterpret_cast<float2*>(a.out_b)[o] = make_float2((float)hc, (float)vc);
+    } else {
+      float X, Y, Z;
+      if (MODE == kModeCloud32) {
+        triangulate_fp32(u, w, (float)hc, (float)vc, a.cal, X, Y, Z);
+      } else if (MODE == kModeCloud64) {
+        double dx, dy, dz;
+        triangulate_fp64(u, w, (float)hc, (float)vc, a.cal, dx, dy, dz);
+        X = (float)dx; Y = (float)dy; Z = (float)dz;
+      } else {
+        const float2 c = __ldg(a.cam_rays + (size_t)(y0 + lane) * a.W + x);
+        const float2 p = __ldg(a.proj_rays + (size_t)vc * a.cal.proj_w + hc);
+        if (MODE == kModeTable32) {
+          rays_to_point_fp32(c.x, c.y, p.x, p.y, a.cal, X, Y, Z);
+        } else {
+          double dx, dy, dz;
+          rays_to_point_fp64(c.x, c.y, p.x, p.y, a.cal, dx, dy, dz);
+          X = (float)dx; Y = (float)dy; Z = (float)dz;
+        }
+      }
+      a.out_a[o * 3 + 0] = X; a.out_a[o * 3 + 1] = Y; a.out_a[o * 3 + 2] = Z;
+    }
+    if (has_rgb) {
+      const uint8_t* sc = tile.c + lane * kRgbPitch + cidx * 3;
+      a.rgb[o * 3 + 0] = sc[0]; a.rgb[o * 3 + 1] = sc[1]; a.rgb[o * 3 + 2] = sc[2];     // triangulate.py:64
     }
   }
 }
@@ -461,19 +548,40 @@ __global__ void __launch_bounds__(256) filter_emit_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------ launchers
-int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int W, void* ws,
-                           long long* counts, cudaStream_t st) {
+static int grid_for(long long items, int per_block, int cap = 1 << 20) {
+  long long g = (items + per_block - 1) / per_block;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// offsets from a validity bitmap that is already in the workspace (written by the decode kernel)
+int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts, cudaStream_t st) {
   const CloudWorkspace c = carve_workspace(ws, B, H, W);
-  dim3 g1((W + 127) / 128, c.bands, B);
-  count_kernel<<<g1, 128, 0, st>>>(h, v, H, W, c.band_cnt);
+  const int strips = (W + kStripCols - 1) / kStripCols;
+  const long long warps = (long long)B * strips;
+  strip_prefix_kernel<<<grid_for(warps, 4), 128, 0, st>>>(c.bitmap, c.bitmap_words, B, H, W, c.bands, c.band_cnt,
+                                                         c.col_tot);
   count_launch();
-  const long long m = (long long)B * W;
-  bandprefix_kernel<<<(int)((m + 255) / 256), 256, 0, st>>>(c.band_cnt, c.col_tot, B, c.bands, W);
-  count_launch();
-  colscan_kernel<<<1, 1024, 0, st>>>(c.col_tot, c.col_base, m, B, W, counts);
+  colscan_kernel<<<1, 1024, 0, st>>>(c.col_tot, c.col_base, (long long)B * W, B, W, counts);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
+}
+
+int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int W, void* ws,
+                           long long* counts, cudaStream_t st) {
+  const CloudWorkspace c = carve_workspace(ws, B, H, W);
+  const long long npix = (long long)H * W;
+  const long long padded = ((npix + 31) & ~31LL) * B;
+  bitmap_from_idx_kernel<<<grid_for(padded, 256, 148 * 16), 256, 0, st>>>(h, v, npix, c.bitmap_words, B, c.bitmap);
+  count_launch();
+  return launch_offsets_from_bitmap(B, H, W, ws, counts, st);
+}
+
+uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan) {
+  const CloudWorkspace c = carve_workspace(ws, B, H, W);
+  *words_per_scan = c.bitmap_words;
+  return c.bitmap;
 }
 
 static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
@@ -483,6 +591,8 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
   a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_base = c.col_base;
   a.out_a = out_a; a.out_b = out_b; a.rgb = rgb; a.H = H; a.W = W; a.bands = c.bands;
   a.cam_rays = nullptr; a.proj_rays = nullptr;
+  a.tiles_x = (W + kEmitCols - 1) / kEmitCols;
+  a.total_tiles = (long long)a.tiles_x * a.bands * B;
   return a;
 }
 
@@ -492,8 +602,7 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, cam_pts, proj_pts, rgb);
   a.cal = CalibDev();
   a.cal.proj_w = proj_w; a.cal.proj_h = proj_h;
-  dim3 g((W + kTileCols - 1) / kTileCols, a.bands, B);
-  emit_kernel<kModePairs><<<g, kEmitThreads, 0, st>>>(a);
+  emit_kernel<kModePairs><<<grid_for(a.total_tiles, kEmitWarps), kEmitWarps * 32, 0, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
@@ -518,12 +627,13 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, xyz, nullptr, rgb);
   a.cal = make_calib(calib);
   a.cam_rays = (const float2*)cam_rays; a.proj_rays = (const float2*)proj_rays;
-  dim3 g((W + kTileCols - 1) / kTileCols, a.bands, B);
+  const int g = grid_for(a.total_tiles, kEmitWarps);
+  const int thr = kEmitWarps * 32;
   if (cam_rays) {
-    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, kEmitThreads, 0, st>>>(a);
-    else emit_kernel<kModeTable32><<<g, kEmitThreads, 0, st>>>(a);
-  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, kEmitThreads, 0, st>>>(a);
-  else emit_kernel<kModeCloud32><<<g, kEmitThreads, 0, st>>>(a);
+    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, 0, st>>>(a);
+    else emit_kernel<kModeTable32><<<g, thr, 0, st>>>(a);
+  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, 0, st>>>(a);
+  else emit_kernel<kModeCloud32><<<g, thr, 0, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;

@@ -33,6 +33,8 @@ struct DecodeArgs {
   int16_t* v_idx;
   int8_t* h_codes;
   int8_t* v_codes;
+  uint32_t* bitmap;      // nullable: flat validity bits, scan b at bitmap + b*bitmap_words
+  long long bitmap_words;
   long long npix;        // pixels per scan
   long long npix4;       // npix rounded down to a multiple of 4 (part handled by this kernel)
   long long total_tiles; // B * tiles_per_scan
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __g
     const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
     const long long rem = a.npix4 - px0;
     const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
+    uint32_t nib = 0;
     if (off < cnt) {
       const uint32_t* base = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + (off >> 2);
       auto ld = [&](int f) { return base[f * (kTilePx / 4)]; };
@@ -108,6 +111,13 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __g
       const QuadOut o = decode_quad<NB, CODES>(ld, st, n, a.e);
       st_global_v2(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23);
       st_global_v2(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23);
+      nib = ((o.valid & kMsb4) * 0x00204081u) >> 28;      // the 4 msb flags gathered into bits 0..3
+    }
+    if (a.bitmap) {
+      // 8 neighbouring lanes hold the 32 validity bits of 32 consecutive pixels
+      const uint32_t word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
+      if ((lane & 7) == 0 && px0 + off < a.npix)
+        a.bitmap[(size_t)b * a.bitmap_words + ((px0 + off) >> 5)] = word;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));
@@ -125,6 +135,8 @@ struct GenericArgs {
   long long npix, px_begin, px_end;   // per-scan pixel range [px_begin, px_end)
   int n, B;
   double eps;
+  uint32_t* bitmap;       // nullable: validity bits are OR-ed in (the launcher zeroes the words first)
+  long long bitmap_words;
   const double* ld_in;    // nullable: caller-supplied L_d / L_g (get_is_lit, decode_codes.py:125)
   const double* lg_in;
   double* ld_out;         // nullable: get_direct_indirect outputs (decode_codes.py:90-122)
@@ -193,6 +205,7 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericArgs a
       a.h_idx[(size_t)b * a.npix + px] = okh ? (int16_t)gray_to_binary16(gh) : (int16_t)-1;
       a.v_idx[(size_t)b * a.npix + px] = okv ? (int16_t)gray_to_binary16(gv) : (int16_t)-1;
     }
+    if (a.bitmap && okh && okv) atomicOr(a.bitmap + (size_t)b * a.bitmap_words + (px >> 5), 1u << (px & 31));
   }
 }
 
@@ -289,7 +302,8 @@ static int dispatch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, 
 
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                  int8_t* v_codes, int num_sms, cudaStream_t st) {
+                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, int num_sms,
+                  cudaStream_t st) {
   const int n = (F - 2) / 4;
   const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
   const bool aligned = ((uintptr_t)frames % 16 == 0) && (frame_pitch % 16 == 0) &&
@@ -299,11 +313,14 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
                                      npix % 4 == 0));
   long long tma_px = (int_eps && aligned) ? (npix & ~3LL) : 0;
   if (frame_pitch >= (1ull << 40) || scan_pitch >= (1ull << 40)) tma_px = 0;   // tensor-map stride limit
+  if (valid_bitmap && tma_px < npix)   // some pixels go through the generic kernel, which ORs its bits in
+    SL_CUDA(cudaMemsetAsync(valid_bitmap, 0, (size_t)B * bitmap_words * sizeof(uint32_t), st));
 
   if (tma_px > 0) {
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words;
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
@@ -329,6 +346,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = scan_pitch;
     g.h_idx = h_idx; g.v_idx = v_idx; g.h_codes = h_codes; g.v_codes = v_codes;
     g.npix = npix; g.px_begin = tma_px; g.px_end = npix; g.n = n; g.B = B; g.eps = eps;
+    g.bitmap = valid_bitmap; g.bitmap_words = bitmap_words;
     g.ld_in = g.lg_in = nullptr; g.ld_out = g.lg_out = nullptr;
     const long long total = (npix - tma_px) * B;
     long long blocks = (total + 255) / 256;
@@ -349,6 +367,7 @@ int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t fra
   g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = 0;
   g.h_idx = nullptr; g.v_idx = nullptr; g.h_codes = h_codes; g.v_codes = v_codes;
   g.npix = npix; g.px_begin = 0; g.px_end = npix; g.n = (F - 2) / 4; g.B = 1; g.eps = eps;
+  g.bitmap = nullptr; g.bitmap_words = 0;
   g.ld_in = ld_in; g.lg_in = lg_in; g.ld_out = ld_out; g.lg_out = lg_out;
   long long blocks = (npix + 255) / 256;
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;

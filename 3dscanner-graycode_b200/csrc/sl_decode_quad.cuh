@@ -15,6 +15,7 @@ namespace sl {
 struct QuadOut {
   uint32_t h01, h23;   // int16 lanes: projector column of pixels {0,1} / {2,3}; 0xffff = -1
   uint32_t v01, v23;   // projector row
+  uint32_t valid;      // bit 7 of lane k set iff pixel k decoded on both axes
 };
 
 // Tri-state bytes (1, 0, 0xff=-1) of one bit for 4 pixels (decode_codes.py:162-182 output).
@@ -110,6 +111,7 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
       if (CODES) st(0, j, tristate4(one, valid));
     }
     finish_axis(accA, accB, allv, n, out.h01, out.h23);
+    out.valid = allv;
   }
   // ---- row bits: stored LSB first (flipped by the caller at src/3-capture_decode.py:100)
   {
@@ -126,6 +128,7 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
       if (CODES) st(1, i, tristate4(one, valid));
     }
     finish_axis(accA, accB, allv, n, out.v01, out.v23);
+    out.valid &= allv;
   }
   return out;
 }

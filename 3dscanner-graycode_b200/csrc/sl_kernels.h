@@ -10,9 +10,11 @@ namespace sl {
 void count_launch();   // bumps the process-wide kernel launch counter
 
 // ---- stage 1 (sl_decode.cu)
+// valid_bitmap (nullable): flat validity bits, scan b at valid_bitmap + b*bitmap_words
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                  int8_t* v_codes, int num_sms, cudaStream_t st);
+                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, int num_sms,
+                  cudaStream_t st);
 int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t frame_pitch, double eps,
                         const double* ld_in, const double* lg_in, double* ld_out, double* lg_out,
                         int8_t* h_codes, int8_t* v_codes, int num_sms, cudaStream_t st);
@@ -22,7 +24,9 @@ int launch_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, 
 
 // ---- stage 2 (sl_cloud.cu)
 struct CloudWorkspace {      // views into the caller's workspace buffer
-  uint32_t* band_cnt;        // [B][bands][W]  count, then exclusive prefix down the column
+  uint32_t* bitmap;          // [B][bitmap_words] flat validity bits (bit i of word i/32 = pixel i)
+  long long bitmap_words;
+  uint32_t* band_cnt;        // [B][bands][W]  exclusive prefix of valid pixels down the column, per band
   uint32_t* col_tot;         // [B][W]
   long long* col_base;       // [B][W] packed offset of the first point of column x of scan b
   int bands;
@@ -32,6 +36,8 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W);
 
 int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int W, void* ws,
                            long long* counts, cudaStream_t st);
+int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts, cudaStream_t st);
+uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan);
 int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
                       int proj_w, int proj_h, const void* ws, float* cam_pts, float* proj_pts,
                       uint8_t* rgb, cudaStream_t st);

@@ -37,12 +37,13 @@ SIGNATURES = {
     "sl_last_error": (C.c_char_p, []),
     "sl_version": (_i, []),
     "sl_device_check": (_i, [_i]),
-    "sl_decode_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp, _vp]),
+    "sl_decode_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sl_direct_indirect": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp]),
     "sl_is_lit": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _d, _vp, _vp, _vp]),
     "sl_codes_to_pixels": (_i, [_vp, _vp, _i, _i, _i64, _sz, _vp, _vp, _vp]),
     "sl_cloud_workspace_bytes": (_sz, [_i, _i, _i]),
     "sl_compact_offsets": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sl_compact_offsets_decoded": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "sl_emit_pairs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _vp, _vp, _vp]),
     "sl_emit_cloud": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -154,7 +154,7 @@ def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[to
         h_idx, v_idx = out
     with torch.cuda.device(frames.device):
         check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
-                                 _ptr(h_idx), _ptr(v_idx), None, None, _stream()))
+                                 _ptr(h_idx), _ptr(v_idx), None, None, None, _stream()))
     return h_idx, v_idx
 
 
@@ -173,7 +173,7 @@ def decode_codes(frames: torch.Tensor, eps: float = 1.0):
     v_idx = torch.empty(ishape, dtype=torch.int16, device=dev)
     with torch.cuda.device(dev):
         check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
-                                 _ptr(h_idx), _ptr(v_idx), _ptr(h_codes), _ptr(v_codes), _stream()))
+                                 _ptr(h_idx), _ptr(v_idx), _ptr(h_codes), _ptr(v_codes), None, _stream()))
     return h_codes, v_codes, h_idx, v_idx
 
 
@@ -410,9 +410,8 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     st = _stream()
     with torch.cuda.device(dev):
         check(L.sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
-                             _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, st))
-        check(L.sl_compact_offsets(_ptr(buffers.h_idx), _ptr(buffers.v_idx), b, h, w,
-                                   _ptr(buffers.ws), _ptr(buffers.counts), st))
+                             _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, _ptr(buffers.ws), st))
+        check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
         check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
                               _PREC[precision], _ptr(tables.cam) if tables is not None else None,
                               _ptr(tables.proj) if tables is not None else None,

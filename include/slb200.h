@@ -69,10 +69,13 @@ int sl_device_check(int device);
  *               byte-compare kernel, anything else the fp64-compare kernel (same results)
  *   h_idx,v_idx device int16 [B][H*W]: projector column / row, -1 = invalid
  *   h_codes,v_codes  nullable device int8 [B][n][H*W]: the tri-state arrays get_codes returns
+ *   cloud_workspace  nullable device scratch of sl_cloud_workspace_bytes(B,H,W): when given, the
+ *               kernel also leaves the per-pixel validity bitmap there, so the compaction can start
+ *               from it (sl_compact_offsets_decoded) instead of re-reading the indices
  */
 int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                 int8_t* v_codes, void* stream);
+                 int8_t* v_codes, void* cloud_workspace, void* stream);
 
 /* get_direct_indirect (decode_codes.py:90-122): L_d, L_g device f64 [H*W] (NaN where
  * white+black == 0, as in the reference). */
@@ -102,6 +105,9 @@ size_t sl_cloud_workspace_bytes(int B, int H, int W);
  * counts[B] = total.  Points of scan b start at sum(counts[0..b-1]) in the packed outputs. */
 int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H, int W,
                        void* workspace, int64_t* counts, void* stream);
+
+/* Same, for a workspace whose validity bitmap was already written by sl_decode_u8 (same B,H,W). */
+int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream);
 
 /* Triangulate.get_cam_proj_pts (triangulate.py:39-71): emits, x-major,
  * cam_pts (N,2) f32 = [x,y], proj_pts (N,2) f32 = [min(proj_w-1,h), min(proj_h-1,v)] and

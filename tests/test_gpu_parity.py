@@ -261,6 +261,38 @@ def test_pairs_edge_cases(T):
     np.testing.assert_array_equal(proj.cpu().numpy(), po)
 
 
+@pytest.mark.parametrize("shape", [(37, 53), (40, 50), (33, 64), (5, 3), (64, 130)])
+def test_cloud_ragged_shapes(T, shape):
+    """Fused decode -> bitmap -> offsets -> emit on shapes where W % 4 != 0, H*W % 4 != 0, partial bands and
+    partial column tiles: indices, count, order (pinned by the colours) and points against the oracle."""
+    import slb200
+    from slb200 import synth
+    h_, w_ = shape
+    rng = np.random.default_rng(h_ * 100 + w_)
+    n = 4
+    st = adversarial_stack(rng, n, max(h_, 8), w_)[:, :h_]
+    white = rng.integers(0, 256, (h_, w_, 3)).astype(np.uint8)
+    calib = synth.synthetic_calibration((w_, h_), (16, 16))
+    for tables in (None, slb200.LensTables(calib, (w_, h_), "cuda")):
+        bufs = slb200.scan_to_cloud(dev_stack(T, st), T.from_numpy(white).cuda(), calib, precision="fp64", tables=tables)
+        _, _, hp, vp, _, _ = oracle_decode(st)
+        np.testing.assert_array_equal(bufs.h_idx[0].cpu().numpy(), hp)
+        np.testing.assert_array_equal(bufs.v_idx[0].cpu().numpy(), vp)
+        cam, proj, col = O.cam_proj_pairs(hp, vp, (16, 16), white)
+        cnt = int(bufs.counts[1])
+        assert cnt == cam.shape[0] == int(bufs.counts[0])
+        np.testing.assert_array_equal(bufs.rgb[:cnt].cpu().numpy(), np.round(col * 255).astype(np.uint8))
+        if cnt:
+            pts = O.triangulate(cam, proj, calib.cam_mtx, calib.cam_dist, calib.proj_mtx, calib.proj_dist, calib.proj_R, calib.proj_T)
+            got = bufs.xyz[:cnt].cpu().numpy().astype(np.float64).T
+            fin = np.isfinite(pts).all(axis=0) & (np.abs(pts).max(axis=0) < 1e6)
+            np.testing.assert_allclose(got[:, fin], pts[:, fin].astype(np.float32), rtol=1e-5)
+    # the index-driven compaction (bitmap rebuilt from h/v) gives the same pairs
+    cam_g, proj_g, rgb_g = slb200.cam_proj_pairs(hp, vp, (16, 16), white)
+    np.testing.assert_array_equal(cam_g.cpu().numpy(), cam)
+    np.testing.assert_array_equal(proj_g.cpu().numpy(), proj)
+
+
 def test_batched_cloud_matches_single(T):
     """Packed batch output == the scans done one by one (order inside a scan, counts, bytes)."""
     import slb200
@@ -340,7 +372,8 @@ def test_pipeline_host_buffers(T):
     pipe = slb200.Pipeline(frames.shape[1], 200, 320, max_batch=5)
     h_idx = np.empty((5, 200, 320), np.int16); v_idx = np.empty((5, 200, 320), np.int16)
     xyz, rgb, counts = pipe.scan_to_cloud(frames, white, calib, h_idx=h_idx, v_idx=v_idx)
-    dev = slb200.scan_to_cloud(frames.cuda(), white.cuda(), calib)
+    tables = slb200.LensTables(calib, cam_size, "cuda")      # the pipeline builds the same tables internally
+    dev = slb200.scan_to_cloud(frames.cuda(), white.cuda(), calib, tables=tables)
     n = int(dev.counts[-1])
     assert int(counts[-1]) == n and xyz.shape[0] == n
     np.testing.assert_array_equal(counts.numpy(), dev.counts.cpu().numpy())
