@@ -21,7 +21,7 @@ namespace sl {
 constexpr int kBandRows = 32;       // rows per band = lanes per warp
 constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
 constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
-constexpr int kEmitWarps = 8;
+constexpr int kEmitWarps = 4;
 
 // ------------------------------------------------------------------ workspace
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -70,38 +70,31 @@ __global__ void __launch_bounds__(256) bitmap_from_idx_kernel(const int16_t* __r
   }
 }
 
-// K3b: one warp per strip of 32 columns walks down the bands.  Lane r fetches the 32 validity bits
-// of row (band*32 + r) in the strip (funnel shift out of the flat bitmap), 32 ballots transpose the
-// 32x32 bit block so lane c holds the column word of column x0+c; its popcount feeds the running
-// prefix down the column.  Outputs: band_pre[b][band][x] (exclusive prefix) and col_tot[b][x].
-__global__ void __launch_bounds__(128) strip_prefix_kernel(const uint32_t* __restrict__ bitmap,
-                                                            long long words_per_scan, int B, int H, int W,
-                                                            int bands, uint32_t* __restrict__ band_pre,
-                                                            uint32_t* __restrict__ col_tot) {
-  const int strips = (W + kStripCols - 1) / kStripCols;
-  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp_id >= (long long)B * strips) return;
-  const int b = (int)(warp_id / strips), strip = (int)(warp_id - (long long)b * strips);
+// K3b: one CTA per strip of 32 columns, one warp per band (round-robin).  Lane r fetches the 32
+// validity bits of row (band*32 + r) in the strip (funnel shift out of the flat bitmap); 32 ballots
+// transpose the 32x32 bit block so lane c holds the column word of column x0+c, whose popcount is
+// the number of valid pixels of that column in the band.  The counts meet in shared memory, are
+// prefixed down each column, and leave as band_pre[b][band][x] (exclusive) and col_tot[b][x].
+constexpr int kStripWarps = 16;
+constexpr int kMaxBands = 1024;      // H <= 32768
+
+__global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const uint32_t* __restrict__ bitmap,
+                                                                         long long words_per_scan, int H, int W,
+                                                                         int bands, int strips,
+                                                                         uint32_t* __restrict__ band_pre,
+                                                                         uint32_t* __restrict__ col_tot) {
+  extern __shared__ uint32_t cnt[];            // [bands][32] counts, then exclusive prefixes
+  const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = strip * kStripCols, x = x0 + lane;
   const uint32_t* bm = bitmap + (size_t)b * words_per_scan;
   const uint32_t colmask = (W - x0 >= 32) ? 0xffffffffu : ((1u << (W - x0)) - 1u);
-  uint32_t run = 0;
-  uint32_t next = 0;
-  {   // prefetch band 0
-    const int y = lane;
+  for (int band = warp; band < bands; band += kStripWarps) {
+    const int y = band * kBandRows + lane;
+    uint32_t rowword = 0;
     if (y < H) {
       const long long i = (long long)y * W + x0;
-      next = __funnelshift_r(bm[i >> 5], bm[(i >> 5) + 1], (uint32_t)(i & 31)) & colmask;
-    }
-  }
-  for (int band = 0; band < bands; ++band) {
-    const uint32_t rowword = next;
-    next = 0;
-    const int yn = (band + 1) * kBandRows + lane;
-    if (band + 1 < bands && yn < H) {
-      const long long i = (long long)yn * W + x0;
-      next = __funnelshift_r(bm[i >> 5], bm[(i >> 5) + 1], (uint32_t)(i & 31)) & colmask;
+      rowword = __funnelshift_r(bm[i >> 5], bm[(i >> 5) + 1], (uint32_t)(i & 31)) & colmask;
     }
     uint32_t colword = 0;
 #pragma unroll
@@ -109,10 +102,22 @@ __global__ void __launch_bounds__(128) strip_prefix_kernel(const uint32_t* __res
       const uint32_t bits = __ballot_sync(0xffffffffu, (rowword >> c) & 1u);
       if (lane == c) colword = bits;
     }
-    if (x < W) band_pre[((size_t)b * bands + band) * W + x] = run;
-    run += __popc(colword);
+    cnt[band * 32 + lane] = __popc(colword);
   }
-  if (x < W) col_tot[(size_t)b * W + x] = run;
+  __syncthreads();
+  if (warp == 0) {                              // prefix down the column (bands <= ~70 in practice)
+    uint32_t run = 0;
+    for (int band = 0; band < bands; ++band) {
+      const uint32_t c = cnt[band * 32 + lane];
+      cnt[band * 32 + lane] = run;
+      run += c;
+    }
+    if (x < W) col_tot[(size_t)b * W + x] = run;
+  }
+  __syncthreads();
+  if (x < W)
+    for (int band = warp; band < bands; band += kStripWarps)
+      band_pre[((size_t)b * bands + band) * W + x] = cnt[band * 32 + lane];
 }
 
 // single block: exclusive scan of m uint32 values into int64, plus per-scan totals
@@ -343,27 +348,29 @@ struct EmitArgs {
   CalibDev cal;
 };
 
-// Shared-memory tile of one warp: 32 rows x kEmitCols columns, padded so that the column-major
-// reads (lane = row) hit 32 different banks.
-constexpr int kIdxPitch = kEmitCols + 2;              // int16: 18 -> 9 words per row (odd)
-constexpr int kRgbPitch = kEmitCols * 3 + 4;          // bytes: 52 -> 13 words per row (odd)
+// Per-warp shared memory: the result tile (one uint4 per pixel: 3 payload words + colour/valid word)
+// and two small run buffers used to write each column's points as one contiguous run.
+constexpr int kResPitch = kEmitCols + 1;              // uint4 per row: 17 -> 68 words, conflict-free columns
 struct EmitTile {
-  int16_t h[kBandRows * kIdxPitch];
-  int16_t v[kBandRows * kIdxPitch];
-  uint8_t c[kBandRows * kRgbPitch];
+  uint4 res[kBandRows * kResPitch];
+  uint32_t run[2][kBandRows * 3];                      // xyz words (cloud) / proj_pts + cam_pts words (pairs)
+  uint8_t rgb[2][kBandRows * 3];
 };
 
-// One warp per tile of 32 rows x kEmitCols columns.  Load phase is row-major (coalesced, vector
-// loads when the row pitch allows); compute phase is column-major (lane = row), so the warp ballot
-// gives each valid pixel its rank inside the column and the warp writes one contiguous run of
-// points per column -- the reference's x-major order (triangulate.py:52-53), no atomics.
+// One warp per tile of 32 rows x kEmitCols columns.
+//  Phase A (row-major; a lane owns 4 neighbouring pixels of a row): vector loads of the indices, the
+//    colour and the camera rays, gathers of the projector rays (neighbouring pixels hit neighbouring
+//    projector pixels), the triangulation, results into the shared tile.
+//  Phase B (column-major; lane = row): warp ballot -> rank of every valid pixel inside the column;
+//    the column's points are packed into a run buffer and leave as contiguous words.  Runs of
+//    successive bands / columns abut, which is the reference's x-major order (triangulate.py:52-53).
 template <int MODE>
 __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a) {
-  __shared__ __align__(16) EmitTile tiles[kEmitWarps];
+  extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
   if (t >= a.total_tiles) return;
-  EmitTile& tile = tiles[warp];
+  EmitTile& tile = reinterpret_cast<EmitTile*>(emit_smem)[warp];
   const int tx = (int)(t % a.tiles_x);
   const long long rest = t / a.tiles_x;
   const int band = (int)(rest % a.bands), b = (int)(rest / a.bands);
@@ -371,101 +378,133 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   const int rows = min(kBandRows, a.H - y0), cols = min(kEmitCols, a.W - x0);
   const size_t img = (size_t)b * a.H * a.W;
   const bool has_rgb = a.white != nullptr && a.rgb != nullptr;
+  const bool vec = ((a.W & 3) == 0) && cols == kEmitCols;
+  constexpr bool kTable = (MODE == kModeTable32 || MODE == kModeTable64);
 
-  // ---- load phase
-  if ((a.W & 3) == 0 && cols == kEmitCols) {
-    // 16 int16 per row = 4 x 8 bytes: lane -> (row = lane/4 + 8*it, 4 columns at (lane%4)*4)
-    const int rr = lane >> 2, c4 = (lane & 3) * 4;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = rr + 8 * it;
-      uint2 hv = make_uint2(0xffffffffu, 0xffffffffu), vv = hv;
-      if (r < rows) {
-        const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
-        hv = __ldg(reinterpret_cast<const uint2*>(a.h + g));
-        vv = __ldg(reinterpret_cast<const uint2*>(a.v + g));
-      }
-      uint32_t* dh = reinterpret_cast<uint32_t*>(tile.h + r * kIdxPitch + c4);
-      uint32_t* dv = reinterpret_cast<uint32_t*>(tile.v + r * kIdxPitch + c4);
-      dh[0] = hv.x; dh[1] = hv.y; dv[0] = vv.x; dv[1] = vv.y;
-    }
-    if (has_rgb) {
-      // 48 bytes per row = 12 words: 384 words per tile, 12 iterations of 32 lanes
-#pragma unroll
-      for (int it = 0; it < 12; ++it) {
-        const int wi = it * 32 + lane, r = wi / 12, cw = wi - r * 12;
-        uint32_t val = 0;
-        if (r < rows) val = __ldg(reinterpret_cast<const uint32_t*>(a.white + (img + (size_t)(y0 + r) * a.W + x0) * 3) + cw);
-        *reinterpret_cast<uint32_t*>(tile.c + r * kRgbPitch + cw * 4) = val;
-      }
-    }
-  } else {
-    for (int i = lane; i < kBandRows * kEmitCols; i += 32) {
-      const int r = i / kEmitCols, cidx = i - r * kEmitCols;
-      int16_t hv = -1, vv = -1;
-      if (r < rows && cidx < cols) {
-        const size_t g = img + (size_t)(y0 + r) * a.W + x0 + cidx;
-        hv = a.h[g]; vv = a.v[g];
-      }
-      tile.h[r * kIdxPitch + cidx] = hv;
-      tile.v[r * kIdxPitch + cidx] = vv;
-    }
-    if (has_rgb) {
-      for (int i = lane; i < kBandRows * kEmitCols * 3; i += 32) {
-        const int r = i / (kEmitCols * 3), cb = i - r * (kEmitCols * 3);
-        uint8_t val = 0;
-        if (r < rows && cb < cols * 3) val = a.white[(img + (size_t)(y0 + r) * a.W + x0) * 3 + cb];
-        tile.c[r * kRgbPitch + cb] = val;
-      }
-    }
-  }
   // packed output offset of each column's first point in this band (lane c <-> column x0+c)
   long long my_base = 0;
   if (lane < cols)
     my_base = a.col_base[(size_t)b * a.W + x0 + lane] +
               (long long)a.band_pre[((size_t)b * a.bands + band) * a.W + x0 + lane];
-  __syncwarp();
 
-  // ---- compute phase
-#pragma unroll 2
-  for (int cidx = 0; cidx < cols; ++cidx) {
-    const int hv = tile.h[lane * kIdxPitch + cidx], vv = tile.v[lane * kIdxPitch + cidx];
-    const bool valid = (hv != -1) && (vv != -1);
-    const uint32_t m = __ballot_sync(0xffffffffu, valid);
-    const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
-    if (!valid) continue;
-    const int x = x0 + cidx;
-    const long long o = base + __popc(m & ((1u << lane) - 1u));
-    const float u = (float)x, w = (float)(y0 + lane);
-    const int hc = min(a.cal.proj_w - 1, hv), vc = min(a.cal.proj_h - 1, vv);       // triangulate.py:60-61
-    if (MODE == kModePairs) {
-      reinterpret_cast<float2*>(a.out_a)[o] = make_float2(u, w);
-      reinterpret_cast<float2*>(a.out_b)[o] = make_float2((float)hc, (float)vc);
-    } else {
-      float X, Y, Z;
-      if (MODE == kModeCloud32) {
-        triangulate_fp32(u, w, (float)hc, (float)vc, a.cal, X, Y, Z);
-      } else if (MODE == kModeCloud64) {
-        double dx, dy, dz;
-        triangulate_fp64(u, w, (float)hc, (float)vc, a.cal, dx, dy, dz);
-        X = (float)dx; Y = (float)dy; Z = (float)dz;
+  // ---- phase A
+  const int rr = lane >> 2, c4 = (lane & 3) * 4;
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int r = rr + 8 * it;
+    int hq[4] = {-1, -1, -1, -1}, vq[4] = {-1, -1, -1, -1};
+    uint32_t col[4] = {0, 0, 0, 0};
+    float2 cray[4];
+    if (r < rows) {
+      const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+      if (vec) {
+        const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
+        const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
+        hq[0] = (int16_t)(h2.x & 0xffff); hq[1] = (int16_t)(h2.x >> 16); hq[2] = (int16_t)(h2.y & 0xffff); hq[3] = (int16_t)(h2.y >> 16);
+        vq[0] = (int16_t)(v2.x & 0xffff); vq[1] = (int16_t)(v2.x >> 16); vq[2] = (int16_t)(v2.y & 0xffff); vq[3] = (int16_t)(v2.y >> 16);
+        if (has_rgb) {
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);
+          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);   // 12 bytes = 4 RGB pixels
+          col[0] = w0 & 0xffffffu;
+          col[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+          col[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
+          col[3] = w2 >> 8;
+        }
+        if (kTable) {
+          const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
+          const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
+          cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
+        }
       } else {
-        const float2 c = __ldg(a.cam_rays + (size_t)(y0 + lane) * a.W + x);
-        const float2 p = __ldg(a.proj_rays + (size_t)vc * a.cal.proj_w + hc);
-        if (MODE == kModeTable32) {
-          rays_to_point_fp32(c.x, c.y, p.x, p.y, a.cal, X, Y, Z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (c4 + k < cols) {
+            hq[k] = a.h[g + k]; vq[k] = a.v[g + k];
+            if (has_rgb) {
+              const uint8_t* wp = a.white + (g + k) * 3;
+              col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);
+            }
+            if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4 + k);
+          }
+        }
+      }
+    }
+    bool ok[4];
+    float2 pray[4];
+    int hc[4], vc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ok[k] = (hq[k] != -1) && (vq[k] != -1);                        // triangulate.py:56
+      hc[k] = min(a.cal.proj_w - 1, hq[k]); vc[k] = min(a.cal.proj_h - 1, vq[k]);     // triangulate.py:60-61
+      if (kTable && ok[k]) pray[k] = __ldg(a.proj_rays + (size_t)vc[k] * a.cal.proj_w + hc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float X = 0.f, Y = 0.f, Z = 0.f;
+      if (ok[k]) {
+        const float u = (float)(x0 + c4 + k), w = (float)(y0 + r);
+        if (MODE == kModePairs) {
+          X = (float)hc[k]; Y = (float)vc[k];
+        } else if (MODE == kModeCloud32) {
+          triangulate_fp32(u, w, (float)hc[k], (float)vc[k], a.cal, X, Y, Z);
+        } else if (MODE == kModeCloud64) {
+          double dx, dy, dz;
+          triangulate_fp64(u, w, (float)hc[k], (float)vc[k], a.cal, dx, dy, dz);
+          X = (float)dx; Y = (float)dy; Z = (float)dz;
+        } else if (MODE == kModeTable32) {
+          rays_to_point_fp32(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, X, Y, Z);
         } else {
           double dx, dy, dz;
-          rays_to_point_fp64(c.x, c.y, p.x, p.y, a.cal, dx, dy, dz);
+          rays_to_point_fp64(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, dx, dy, dz);
           X = (float)dx; Y = (float)dy; Z = (float)dz;
         }
       }
-      a.out_a[o * 3 + 0] = X; a.out_a[o * 3 + 1] = Y; a.out_a[o * 3 + 2] = Z;
+      tile.res[r * kResPitch + c4 + k] =
+          make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), col[k] | (ok[k] ? 0x01000000u : 0u));
     }
-    if (has_rgb) {
-      const uint8_t* sc = tile.c + lane * kRgbPitch + cidx * 3;
-      a.rgb[o * 3 + 0] = sc[0]; a.rgb[o * 3 + 1] = sc[1]; a.rgb[o * 3 + 2] = sc[2];     // triangulate.py:64
+  }
+  __syncwarp();
+
+  // ---- phase B
+  int flip = 0;     // run buffers alternate between NON-EMPTY columns (each of those has a __syncwarp)
+  for (int cidx = 0; cidx < cols; ++cidx) {
+    const uint4 q = tile.res[lane * kResPitch + cidx];
+    const bool valid = (q.w >> 24) != 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
+    if (m == 0) continue;
+    const int cnt = __popc(m);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    uint32_t* run = tile.run[flip];
+    uint8_t* rgbrun = tile.rgb[flip];
+    flip ^= 1;
+    if (MODE == kModePairs) {
+      // run[0..2cnt) = proj_pts words, run[2cnt..4cnt) = cam_pts words
+      if (valid) {
+        run[rank * 2] = q.x; run[rank * 2 + 1] = q.y;
+        run[2 * cnt + rank * 2] = __float_as_uint((float)(x0 + cidx));
+        run[2 * cnt + rank * 2 + 1] = __float_as_uint((float)(y0 + lane));
+      }
+    } else if (valid) {
+      run[rank * 3] = q.x; run[rank * 3 + 1] = q.y; run[rank * 3 + 2] = q.z;
     }
+    if (has_rgb && valid) {
+      rgbrun[rank * 3] = (uint8_t)q.w; rgbrun[rank * 3 + 1] = (uint8_t)(q.w >> 8); rgbrun[rank * 3 + 2] = (uint8_t)(q.w >> 16);
+    }
+    __syncwarp();
+    if (MODE == kModePairs) {
+      for (int w = lane; w < 2 * cnt; w += 32) {
+        a.out_b[base * 2 + w] = __uint_as_float(run[w]);
+        a.out_a[base * 2 + w] = __uint_as_float(run[2 * cnt + w]);
+      }
+    } else {
+      for (int w = lane; w < 3 * cnt; w += 32) a.out_a[base * 3 + w] = __uint_as_float(run[w]);
+    }
+    if (has_rgb)
+      for (int w = lane; w < 3 * cnt; w += 32) a.rgb[base * 3 + w] = rgbrun[w];        // triangulate.py:64
+    // the other run buffer serves the next non-empty column; this one is reused by the one after
+    // that, i.e. after every lane has passed that column's __syncwarp
   }
 }
 
@@ -559,8 +598,10 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   const CloudWorkspace c = carve_workspace(ws, B, H, W);
   const int strips = (W + kStripCols - 1) / kStripCols;
   const long long warps = (long long)B * strips;
-  strip_prefix_kernel<<<grid_for(warps, 4), 128, 0, st>>>(c.bitmap, c.bitmap_words, B, H, W, c.bands, c.band_cnt,
-                                                         c.col_tot);
+  (void)warps;
+  if (c.bands > kMaxBands) { set_error("image too tall (%d rows)", H); return kErrBadArg; }
+  strip_prefix_kernel<<<B * strips, kStripWarps * 32, (size_t)c.bands * 32 * sizeof(uint32_t), st>>>(
+      c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_tot);
   count_launch();
   colscan_kernel<<<1, 1024, 0, st>>>(c.col_tot, c.col_base, (long long)B * W, B, W, counts);
   count_launch();
@@ -584,6 +625,23 @@ uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_s
   return c.bitmap;
 }
 
+constexpr int kEmitSmem = (int)(sizeof(EmitTile) * kEmitWarps);
+
+// > 48 KB of dynamic shared memory needs an opt-in per kernel, once per device
+static int emit_configure() {
+  static bool done[64] = {false};
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (done[dev & 63]) return kOk;
+  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModePairs>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  done[dev & 63] = true;
+  return kOk;
+}
+
 static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
                           const void* ws, float* out_a, float* out_b, uint8_t* rgb) {
   const CloudWorkspace c = carve_workspace(const_cast<void*>(ws), B, H, W);
@@ -602,7 +660,9 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, cam_pts, proj_pts, rgb);
   a.cal = CalibDev();
   a.cal.proj_w = proj_w; a.cal.proj_h = proj_h;
-  emit_kernel<kModePairs><<<grid_for(a.total_tiles, kEmitWarps), kEmitWarps * 32, 0, st>>>(a);
+  int rc = emit_configure();
+  if (rc) return rc;
+  emit_kernel<kModePairs><<<grid_for(a.total_tiles, kEmitWarps), kEmitWarps * 32, kEmitSmem, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
@@ -629,11 +689,13 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   a.cam_rays = (const float2*)cam_rays; a.proj_rays = (const float2*)proj_rays;
   const int g = grid_for(a.total_tiles, kEmitWarps);
   const int thr = kEmitWarps * 32;
+  int rc = emit_configure();
+  if (rc) return rc;
   if (cam_rays) {
-    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, 0, st>>>(a);
-    else emit_kernel<kModeTable32><<<g, thr, 0, st>>>(a);
-  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, 0, st>>>(a);
-  else emit_kernel<kModeCloud32><<<g, thr, 0, st>>>(a);
+    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmem, st>>>(a);
+    else emit_kernel<kModeTable32><<<g, thr, kEmitSmem, st>>>(a);
+  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmem, st>>>(a);
+  else emit_kernel<kModeCloud32><<<g, thr, kEmitSmem, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
