@@ -353,7 +353,7 @@ struct EmitArgs {
 constexpr int kResPitch = kEmitCols + 1;              // uint4 per row: 17 -> 68 words, conflict-free columns
 struct EmitTile {
   uint4 res[kBandRows * kResPitch];
-  uint32_t run[2][kBandRows * 3];                      // xyz words (cloud) / proj_pts + cam_pts words (pairs)
+  uint32_t run[2][kBandRows * 4];                      // 3 xyz words per point (cloud) / 2 + 2 words (pairs)
   uint8_t rgb[2][kBandRows * 3];
 };
 
