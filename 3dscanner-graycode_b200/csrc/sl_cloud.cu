@@ -32,6 +32,7 @@ size_t cloud_workspace_bytes(int B, int H, int W) {
   const size_t bands = (size_t)(H + kBandRows - 1) / kBandRows;
   return align_up((size_t)B * bitmap_words((long long)H * W) * 4, 256) +      // validity bitmap
          align_up((size_t)B * bands * W * 4, 256) +                            // band_pre
+         align_up((size_t)B * bands * W * 4, 256) +                            // col_bits
          align_up((size_t)B * W * 4, 256) +                                    // col_tot
          align_up((size_t)B * W * 8, 256);                                     // col_base
 }
@@ -44,6 +45,8 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
   c.bitmap = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)B * c.bitmap_words * 4, 256);
   c.band_cnt = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)B * c.bands * W * 4, 256);
+  c.col_bits = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)B * c.bands * W * 4, 256);
   c.col_tot = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)B * W * 4, 256);
@@ -74,7 +77,8 @@ __global__ void __launch_bounds__(256) bitmap_from_idx_kernel(const int16_t* __r
 // validity bits of row (band*32 + r) in the strip (funnel shift out of the flat bitmap); 32 ballots
 // transpose the 32x32 bit block so lane c holds the column word of column x0+c, whose popcount is
 // the number of valid pixels of that column in the band.  The counts meet in shared memory, are
-// prefixed down each column, and leave as band_pre[b][band][x] (exclusive) and col_tot[b][x].
+// prefixed down each column, and leave as band_pre[b][band][x] (exclusive) and col_tot[b][x]; the
+// column words themselves are kept (col_bits) -- the emit kernel ranks pixels with them.
 constexpr int kStripWarps = 16;
 constexpr int kMaxBands = 1024;      // H <= 32768
 
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
                                                                          long long words_per_scan, int H, int W,
                                                                          int bands, int strips,
                                                                          uint32_t* __restrict__ band_pre,
+                                                                         uint32_t* __restrict__ col_bits,
                                                                          uint32_t* __restrict__ col_tot) {
   extern __shared__ uint32_t cnt[];            // [bands][32] counts, then exclusive prefixes
   const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
@@ -103,6 +108,7 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
       if (lane == c) colword = bits;
     }
     cnt[band * 32 + lane] = __popc(colword);
+    if (x < W) col_bits[((size_t)b * bands + band) * W + x] = colword;    // bit r = pixel (band*32+r, x) valid
   }
   __syncthreads();
   if (warp == 0) {                              // prefix down the column (bands <= ~70 in practice)
@@ -305,11 +311,11 @@ __device__ __forceinline__ void rays_to_point_fp32(float cx, float cy, float px,
   const float t0 = c.Tf[0], t1 = c.Tf[1], t2 = c.Tf[2];
   const float ax = t1 - t2 * cy, ay = t2 * cx - t0, az = t0 * cy - t1 * cx;     // T x (cx,cy,1)
   const float bx = t1 - t2 * py, by = t2 * px - t0, bz = t0 * py - t1 * px;     // T x (px,py,1)
-  const float an = sqrtf(ax * ax + ay * ay + az * az);
-  const float bn = sqrtf(bx * bx + by * by + bz * bz);
+  const float an = __fsqrt_rn(ax * ax + ay * ay + az * az);
+  const float bn = __fsqrt_rn(bx * bx + by * by + bz * bz);
   const float tc = t0 * cx + t1 * cy + t2;
   const float tp = t0 * px + t1 * py + t2;
-  const float s = c.t_len2f * bn / (an * tp - tc * bn);
+  const float s = __fdividef(c.t_len2f * bn, an * tp - tc * bn);
   X = cx * s; Y = cy * s; Z = s;
 }
 
@@ -337,6 +343,7 @@ struct EmitArgs {
   const int16_t* v;
   const uint8_t* white;     // nullable
   const uint32_t* band_pre;
+  const uint32_t* col_bits;
   const long long* col_base;
   float* out_a;             // pairs: cam_pts (N,2)   cloud: xyz (N,3)
   float* out_b;             // pairs: proj_pts (N,2)
@@ -348,22 +355,23 @@ struct EmitArgs {
   CalibDev cal;
 };
 
-// Per-warp shared memory: the result tile (one uint4 per pixel: 3 payload words + colour/valid word)
-// and two small run buffers used to write each column's points as one contiguous run.
-constexpr int kResPitch = kEmitCols + 1;              // uint4 per row: 17 -> 68 words, conflict-free columns
+// Per-warp shared memory: for each of the tile's columns a run of up to 32 compacted points
+// (kPtWords payload words each, +1 word of padding per column against bank conflicts) and their colours.
+constexpr int kPtWords = 4;                            // 3 used by the cloud modes, 4 by the pairs mode
+constexpr int kRunPitch = kBandRows * kPtWords + 1;    // words per column
+constexpr int kRgbRunPitch = kBandRows * 3 + 4;        // bytes per column
 struct EmitTile {
-  uint4 res[kBandRows * kResPitch];
-  uint32_t run[2][kBandRows * 4];                      // 3 xyz words per point (cloud) / 2 + 2 words (pairs)
-  uint8_t rgb[2][kBandRows * 3];
+  uint32_t pts[kEmitCols * kRunPitch];
+  uint8_t rgb[kEmitCols * kRgbRunPitch];
 };
 
 // One warp per tile of 32 rows x kEmitCols columns.
 //  Phase A (row-major; a lane owns 4 neighbouring pixels of a row): vector loads of the indices, the
 //    colour and the camera rays, gathers of the projector rays (neighbouring pixels hit neighbouring
-//    projector pixels), the triangulation, results into the shared tile.
-//  Phase B (column-major; lane = row): warp ballot -> rank of every valid pixel inside the column;
-//    the column's points are packed into a run buffer and leave as contiguous words.  Runs of
-//    successive bands / columns abut, which is the reference's x-major order (triangulate.py:52-53).
+//    projector pixels), the triangulation.  The rank of a valid pixel inside its column is
+//    popc(col_bits & rows-above), so every result goes straight to its slot of the column's run.
+//  Phase B: each column's run leaves shared memory as contiguous words.  Runs of successive bands /
+//    columns abut in the output, which is the reference's x-major order (triangulate.py:52-53).
 template <int MODE>
 __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a) {
   extern __shared__ __align__(16) uint8_t emit_smem[];
@@ -377,134 +385,128 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   const int x0 = tx * kEmitCols, y0 = band * kBandRows;
   const int rows = min(kBandRows, a.H - y0), cols = min(kEmitCols, a.W - x0);
   const size_t img = (size_t)b * a.H * a.W;
+  const size_t cell = ((size_t)b * a.bands + band) * a.W + x0;       // (scan, band, column x0)
   const bool has_rgb = a.white != nullptr && a.rgb != nullptr;
   const bool vec = ((a.W & 3) == 0) && cols == kEmitCols;
   constexpr bool kTable = (MODE == kModeTable32 || MODE == kModeTable64);
+  constexpr int kW = (MODE == kModePairs) ? 4 : 3;                    // payload words per point
 
-  // packed output offset of each column's first point in this band (lane c <-> column x0+c)
+  // lane c <-> column x0+c: packed output offset of the column's first point in this band, and its bits
   long long my_base = 0;
-  if (lane < cols)
-    my_base = a.col_base[(size_t)b * a.W + x0 + lane] +
-              (long long)a.band_pre[((size_t)b * a.bands + band) * a.W + x0 + lane];
+  uint32_t my_bits = 0;
+  if (lane < cols) {
+    my_base = a.col_base[(size_t)b * a.W + x0 + lane] + (long long)a.band_pre[cell + lane];
+    my_bits = a.col_bits[cell + lane];
+  }
 
   // ---- phase A
   const int rr = lane >> 2, c4 = (lane & 3) * 4;
+  uint32_t cb[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const int r = rr + 8 * it;
-    int hq[4] = {-1, -1, -1, -1}, vq[4] = {-1, -1, -1, -1};
+    const uint32_t below = (1u << r) - 1u;
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ok[k] = (cb[k] >> r) & 1u;            // == (h != -1 && v != -1), triangulate.py:56
+    if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+    int hq[4], vq[4];
     uint32_t col[4] = {0, 0, 0, 0};
     float2 cray[4];
-    if (r < rows) {
-      const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
-      if (vec) {
-        const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
-        const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
-        hq[0] = (int16_t)(h2.x & 0xffff); hq[1] = (int16_t)(h2.x >> 16); hq[2] = (int16_t)(h2.y & 0xffff); hq[3] = (int16_t)(h2.y >> 16);
-        vq[0] = (int16_t)(v2.x & 0xffff); vq[1] = (int16_t)(v2.x >> 16); vq[2] = (int16_t)(v2.y & 0xffff); vq[3] = (int16_t)(v2.y >> 16);
-        if (has_rgb) {
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);
-          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);   // 12 bytes = 4 RGB pixels
-          col[0] = w0 & 0xffffffu;
-          col[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
-          col[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
-          col[3] = w2 >> 8;
-        }
-        if (kTable) {
-          const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
-          const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-          cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
-          cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
-        }
-      } else {
+    const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+    if (vec) {
+      const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
+      const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
+      hq[0] = h2.x & 0xffff; hq[1] = h2.x >> 16; hq[2] = h2.y & 0xffff; hq[3] = h2.y >> 16;
+      vq[0] = v2.x & 0xffff; vq[1] = v2.x >> 16; vq[2] = v2.y & 0xffff; vq[3] = v2.y >> 16;
+      if (has_rgb) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);   // 12 bytes = 4 RGB pixels
+        col[0] = w0 & 0xffffffu;
+        col[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+        col[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
+        col[3] = w2 >> 8;
+      }
+      if (kTable) {
+        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
+        cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
+      }
+    } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (c4 + k < cols) {
-            hq[k] = a.h[g + k]; vq[k] = a.v[g + k];
-            if (has_rgb) {
-              const uint8_t* wp = a.white + (g + k) * 3;
-              col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);
-            }
-            if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4 + k);
+      for (int k = 0; k < 4; ++k) {
+        hq[k] = vq[k] = 0;
+        if (ok[k]) {                                    // ok implies the pixel is inside the image
+          hq[k] = (uint16_t)a.h[g + k]; vq[k] = (uint16_t)a.v[g + k];
+          if (has_rgb) {
+            const uint8_t* wp = a.white + (g + k) * 3;
+            col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);
           }
+          if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4 + k);
         }
       }
     }
-    bool ok[4];
     float2 pray[4];
     int hc[4], vc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      ok[k] = (hq[k] != -1) && (vq[k] != -1);                        // triangulate.py:56
       hc[k] = min(a.cal.proj_w - 1, hq[k]); vc[k] = min(a.cal.proj_h - 1, vq[k]);     // triangulate.py:60-61
       if (kTable && ok[k]) pray[k] = __ldg(a.proj_rays + (size_t)vc[k] * a.cal.proj_w + hc[k]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float X = 0.f, Y = 0.f, Z = 0.f;
-      if (ok[k]) {
-        const float u = (float)(x0 + c4 + k), w = (float)(y0 + r);
-        if (MODE == kModePairs) {
-          X = (float)hc[k]; Y = (float)vc[k];
-        } else if (MODE == kModeCloud32) {
-          triangulate_fp32(u, w, (float)hc[k], (float)vc[k], a.cal, X, Y, Z);
-        } else if (MODE == kModeCloud64) {
-          double dx, dy, dz;
-          triangulate_fp64(u, w, (float)hc[k], (float)vc[k], a.cal, dx, dy, dz);
-          X = (float)dx; Y = (float)dy; Z = (float)dz;
-        } else if (MODE == kModeTable32) {
-          rays_to_point_fp32(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, X, Y, Z);
-        } else {
-          double dx, dy, dz;
-          rays_to_point_fp64(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, dx, dy, dz);
-          X = (float)dx; Y = (float)dy; Z = (float)dz;
-        }
+      if (!ok[k]) continue;
+      float X, Y, Z = 0.f, Q = 0.f;
+      const float u = (float)(x0 + c4 + k), w = (float)(y0 + r);
+      if (MODE == kModePairs) {
+        X = u; Y = w; Z = (float)hc[k]; Q = (float)vc[k];
+      } else if (MODE == kModeCloud32) {
+        triangulate_fp32(u, w, (float)hc[k], (float)vc[k], a.cal, X, Y, Z);
+      } else if (MODE == kModeCloud64) {
+        double dx, dy, dz;
+        triangulate_fp64(u, w, (float)hc[k], (float)vc[k], a.cal, dx, dy, dz);
+        X = (float)dx; Y = (float)dy; Z = (float)dz;
+      } else if (MODE == kModeTable32) {
+        rays_to_point_fp32(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, X, Y, Z);
+      } else {
+        double dx, dy, dz;
+        rays_to_point_fp64(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, dx, dy, dz);
+        X = (float)dx; Y = (float)dy; Z = (float)dz;
       }
-      tile.res[r * kResPitch + c4 + k] =
-          make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), col[k] | (ok[k] ? 0x01000000u : 0u));
+      const int rank = __popc(cb[k] & below);
+      uint32_t* dst = tile.pts + (c4 + k) * kRunPitch + rank * kW;
+      dst[0] = __float_as_uint(X); dst[1] = __float_as_uint(Y); dst[2] = __float_as_uint(Z);
+      if (MODE == kModePairs) dst[3] = __float_as_uint(Q);
+      if (has_rgb) {
+        uint8_t* dc = tile.rgb + (c4 + k) * kRgbRunPitch + rank * 3;
+        dc[0] = (uint8_t)col[k]; dc[1] = (uint8_t)(col[k] >> 8); dc[2] = (uint8_t)(col[k] >> 16);    // triangulate.py:64
+      }
     }
   }
   __syncwarp();
 
   // ---- phase B
-  int flip = 0;     // run buffers alternate between NON-EMPTY columns (each of those has a __syncwarp)
   for (int cidx = 0; cidx < cols; ++cidx) {
-    const uint4 q = tile.res[lane * kResPitch + cidx];
-    const bool valid = (q.w >> 24) != 0;
-    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, cidx));
     const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
-    if (m == 0) continue;
-    const int cnt = __popc(m);
-    const int rank = __popc(m & ((1u << lane) - 1u));
-    uint32_t* run = tile.run[flip];
-    uint8_t* rgbrun = tile.rgb[flip];
-    flip ^= 1;
+    if (cnt == 0) continue;
+    const uint32_t* run = tile.pts + cidx * kRunPitch;
     if (MODE == kModePairs) {
-      // run[0..2cnt) = proj_pts words, run[2cnt..4cnt) = cam_pts words
-      if (valid) {
-        run[rank * 2] = q.x; run[rank * 2 + 1] = q.y;
-        run[2 * cnt + rank * 2] = __float_as_uint((float)(x0 + cidx));
-        run[2 * cnt + rank * 2 + 1] = __float_as_uint((float)(y0 + lane));
-      }
-    } else if (valid) {
-      run[rank * 3] = q.x; run[rank * 3 + 1] = q.y; run[rank * 3 + 2] = q.z;
-    }
-    if (has_rgb && valid) {
-      rgbrun[rank * 3] = (uint8_t)q.w; rgbrun[rank * 3 + 1] = (uint8_t)(q.w >> 8); rgbrun[rank * 3 + 2] = (uint8_t)(q.w >> 16);
-    }
-    __syncwarp();
-    if (MODE == kModePairs) {
-      for (int w = lane; w < 2 * cnt; w += 32) {
-        a.out_b[base * 2 + w] = __uint_as_float(run[w]);
-        a.out_a[base * 2 + w] = __uint_as_float(run[2 * cnt + w]);
+      for (int w = lane; w < 2 * cnt; w += 32) {           // point p, component j <- run[4p + j] / run[4p + 2 + j]
+        const int pt = w >> 1, j = w & 1;
+        a.out_a[base * 2 + w] = __uint_as_float(run[pt * 4 + j]);
+        a.out_b[base * 2 + w] = __uint_as_float(run[pt * 4 + 2 + j]);
       }
     } else {
       for (int w = lane; w < 3 * cnt; w += 32) a.out_a[base * 3 + w] = __uint_as_float(run[w]);
     }
-    if (has_rgb)
-      for (int w = lane; w < 3 * cnt; w += 32) a.rgb[base * 3 + w] = rgbrun[w];        // triangulate.py:64
-    // the other run buffer serves the next non-empty column; this one is reused by the one after
-    // that, i.e. after every lane has passed that column's __syncwarp
+    if (has_rgb) {
+      const uint8_t* rc = tile.rgb + cidx * kRgbRunPitch;
+      for (int w = lane; w < 3 * cnt; w += 32) a.rgb[base * 3 + w] = rc[w];
+    }
   }
 }
 
@@ -601,7 +603,7 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   (void)warps;
   if (c.bands > kMaxBands) { set_error("image too tall (%d rows)", H); return kErrBadArg; }
   strip_prefix_kernel<<<B * strips, kStripWarps * 32, (size_t)c.bands * 32 * sizeof(uint32_t), st>>>(
-      c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_tot);
+      c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot);
   count_launch();
   colscan_kernel<<<1, 1024, 0, st>>>(c.col_tot, c.col_base, (long long)B * W, B, W, counts);
   count_launch();
@@ -646,7 +648,7 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
                           const void* ws, float* out_a, float* out_b, uint8_t* rgb) {
   const CloudWorkspace c = carve_workspace(const_cast<void*>(ws), B, H, W);
   EmitArgs a;
-  a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_base = c.col_base;
+  a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_bits = c.col_bits; a.col_base = c.col_base;
   a.out_a = out_a; a.out_b = out_b; a.rgb = rgb; a.H = H; a.W = W; a.bands = c.bands;
   a.cam_rays = nullptr; a.proj_rays = nullptr;
   a.tiles_x = (W + kEmitCols - 1) / kEmitCols;

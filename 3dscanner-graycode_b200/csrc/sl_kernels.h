@@ -27,6 +27,7 @@ struct CloudWorkspace {      // views into the caller's workspace buffer
   uint32_t* bitmap;          // [B][bitmap_words] flat validity bits (bit i of word i/32 = pixel i)
   long long bitmap_words;
   uint32_t* band_cnt;        // [B][bands][W]  exclusive prefix of valid pixels down the column, per band
+  uint32_t* col_bits;        // [B][bands][W]  bit r = pixel (band*32 + r, x) valid
   uint32_t* col_tot;         // [B][W]
   long long* col_base;       // [B][W] packed offset of the first point of column x of scan b
   int bands;
