@@ -306,13 +306,19 @@ __device__ __forceinline__ void rays_to_point_fp64(float cx, float cy, float px,
   Z = dmul((double)lz, p_len);
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ void rays_to_point_fp32(float cx, float cy, float px, float py, const CalibDev& c,
                                                    float& X, float& Y, float& Z) {
   const float t0 = c.Tf[0], t1 = c.Tf[1], t2 = c.Tf[2];
   const float ax = t1 - t2 * cy, ay = t2 * cx - t0, az = t0 * cy - t1 * cx;     // T x (cx,cy,1)
   const float bx = t1 - t2 * py, by = t2 * px - t0, bz = t0 * py - t1 * px;     // T x (px,py,1)
-  const float an = __fsqrt_rn(ax * ax + ay * ay + az * az);
-  const float bn = __fsqrt_rn(bx * bx + by * by + bz * bz);
+  const float an = sqrt_approx(ax * ax + ay * ay + az * az);     // ~1 ulp; the fp32 mode's tolerance is 1e-4
+  const float bn = sqrt_approx(bx * bx + by * by + bz * bz);
   const float tc = t0 * cx + t1 * cy + t2;
   const float tp = t0 * px + t1 * py + t2;
   const float s = __fdividef(c.t_len2f * bn, an * tp - tc * bn);
@@ -357,10 +363,10 @@ struct EmitArgs {
 
 // Per-warp shared memory: for each of the tile's columns a run of up to 32 compacted points
 // (kPtWords payload words each, +1 word of padding per column against bank conflicts) and their colours.
-constexpr int kPtWords = 4;                            // 3 used by the cloud modes, 4 by the pairs mode
-constexpr int kRunPitch = kBandRows * kPtWords + 1;    // words per column
 constexpr int kRgbRunPitch = kBandRows * 3 + 4;        // bytes per column
+template <int KW>                                      // payload words per point: 3 (cloud) or 4 (pairs)
 struct EmitTile {
+  static constexpr int kRunPitch = kBandRows * KW + 1; // words per column
   uint32_t pts[kEmitCols * kRunPitch];
   uint8_t rgb[kEmitCols * kRgbRunPitch];
 };
@@ -373,15 +379,22 @@ struct EmitTile {
 //  Phase B: each column's run leaves shared memory as contiguous words.  Runs of successive bands /
 //    columns abut in the output, which is the reference's x-major order (triangulate.py:52-53).
 template <int MODE>
-__global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs a) {
   extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
   if (t >= a.total_tiles) return;
-  EmitTile& tile = reinterpret_cast<EmitTile*>(emit_smem)[warp];
-  const int tx = (int)(t % a.tiles_x);
-  const long long rest = t / a.tiles_x;
-  const int band = (int)(rest % a.bands), b = (int)(rest / a.bands);
+  constexpr int kW = (MODE == kModePairs) ? 4 : 3;                    // payload words per point
+  using Tile = EmitTile<kW>;
+  constexpr int kRunPitch = Tile::kRunPitch;
+  Tile& tile = reinterpret_cast<Tile*>(emit_smem)[warp];
+  // tile -> (scan, band, column block); 32-bit arithmetic (total_tiles < 2^31 is checked by the launcher)
+  const uint32_t ti = (uint32_t)t;
+  const uint32_t per_scan = (uint32_t)a.tiles_x * (uint32_t)a.bands;
+  const int b = (int)(ti / per_scan);
+  const uint32_t in_scan = ti - (uint32_t)b * per_scan;
+  const int band = (int)(in_scan / (uint32_t)a.tiles_x);
+  const int tx = (int)(in_scan - (uint32_t)band * (uint32_t)a.tiles_x);
   const int x0 = tx * kEmitCols, y0 = band * kBandRows;
   const int rows = min(kBandRows, a.H - y0), cols = min(kEmitCols, a.W - x0);
   const size_t img = (size_t)b * a.H * a.W;
@@ -389,7 +402,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   const bool has_rgb = a.white != nullptr && a.rgb != nullptr;
   const bool vec = ((a.W & 3) == 0) && cols == kEmitCols;
   constexpr bool kTable = (MODE == kModeTable32 || MODE == kModeTable64);
-  constexpr int kW = (MODE == kModePairs) ? 4 : 3;                    // payload words per point
 
   // lane c <-> column x0+c: packed output offset of the column's first point in this band, and its bits
   long long my_base = 0;
@@ -404,37 +416,55 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   uint32_t cb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
+  // first-level loads of an iteration (vector path), issued one iteration ahead of their use
+  struct RowLoads { uint2 h2, v2; uint32_t w0, w1, w2; float4 r0, r1; };
+  auto fetch = [&](int r, RowLoads& L) {
+    const uint32_t any = ((cb[0] | cb[1] | cb[2] | cb[3]) >> r) & 1u;
+    if (!any) return;
+    const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+    L.h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
+    L.v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
+    if (has_rgb) {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);       // 12 bytes = 4 RGB pixels
+      L.w0 = __ldg(wp); L.w1 = __ldg(wp + 1); L.w2 = __ldg(wp + 2);
+    }
+    if (kTable) {
+      const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
+      L.r0 = __ldg(rp); L.r1 = __ldg(rp + 1);
+    }
+  };
+  RowLoads cur, nxt;
+  cur.h2 = cur.v2 = nxt.h2 = nxt.v2 = make_uint2(0, 0);
+  cur.w0 = cur.w1 = cur.w2 = nxt.w0 = nxt.w1 = nxt.w2 = 0;
+  cur.r0 = cur.r1 = nxt.r0 = nxt.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) fetch(rr, cur);
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const int r = rr + 8 * it;
+    if (vec && it < 3) fetch(r + 8, nxt);
     const uint32_t below = (1u << r) - 1u;
     bool ok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) ok[k] = (cb[k] >> r) & 1u;            // == (h != -1 && v != -1), triangulate.py:56
-    if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+    if (!(ok[0] | ok[1] | ok[2] | ok[3])) { cur = nxt; continue; }
     int hq[4], vq[4];
     uint32_t col[4] = {0, 0, 0, 0};
     float2 cray[4];
     const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
     if (vec) {
-      const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
-      const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
-      hq[0] = h2.x & 0xffff; hq[1] = h2.x >> 16; hq[2] = h2.y & 0xffff; hq[3] = h2.y >> 16;
-      vq[0] = v2.x & 0xffff; vq[1] = v2.x >> 16; vq[2] = v2.y & 0xffff; vq[3] = v2.y >> 16;
+      hq[0] = cur.h2.x & 0xffff; hq[1] = cur.h2.x >> 16; hq[2] = cur.h2.y & 0xffff; hq[3] = cur.h2.y >> 16;
+      vq[0] = cur.v2.x & 0xffff; vq[1] = cur.v2.x >> 16; vq[2] = cur.v2.y & 0xffff; vq[3] = cur.v2.y >> 16;
       if (has_rgb) {
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);
-        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);   // 12 bytes = 4 RGB pixels
-        col[0] = w0 & 0xffffffu;
-        col[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
-        col[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
-        col[3] = w2 >> 8;
+        col[0] = cur.w0 & 0xffffffu;
+        col[1] = (cur.w0 >> 24) | ((cur.w1 & 0xffffu) << 8);
+        col[2] = (cur.w1 >> 16) | ((cur.w2 & 0xffu) << 16);
+        col[3] = cur.w2 >> 8;
       }
       if (kTable) {
-        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
-        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-        cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
-        cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
+        cray[0] = make_float2(cur.r0.x, cur.r0.y); cray[1] = make_float2(cur.r0.z, cur.r0.w);
+        cray[2] = make_float2(cur.r1.x, cur.r1.y); cray[3] = make_float2(cur.r1.z, cur.r1.w);
       }
+      cur = nxt;
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -627,7 +657,8 @@ uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_s
   return c.bitmap;
 }
 
-constexpr int kEmitSmem = (int)(sizeof(EmitTile) * kEmitWarps);
+constexpr int kEmitSmem = (int)(sizeof(EmitTile<4>) * kEmitWarps);       // pairs mode
+constexpr int kEmitSmemCloud = (int)(sizeof(EmitTile<3>) * kEmitWarps);
 
 // > 48 KB of dynamic shared memory needs an opt-in per kernel, once per device
 static int emit_configure() {
@@ -644,6 +675,11 @@ static int emit_configure() {
   return kOk;
 }
 
+static int check_emit_size(const EmitArgs& a) {
+  if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one emit launch"); return kErrBadArg; }
+  return kOk;
+}
+
 static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
                           const void* ws, float* out_a, float* out_b, uint8_t* rgb) {
   const CloudWorkspace c = carve_workspace(const_cast<void*>(ws), B, H, W);
@@ -652,7 +688,7 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
   a.out_a = out_a; a.out_b = out_b; a.rgb = rgb; a.H = H; a.W = W; a.bands = c.bands;
   a.cam_rays = nullptr; a.proj_rays = nullptr;
   a.tiles_x = (W + kEmitCols - 1) / kEmitCols;
-  a.total_tiles = (long long)a.tiles_x * a.bands * B;
+  a.total_tiles = (long long)a.tiles_x * a.bands * B;      // callers reject >= 2^31 (check_emit_size)
   return a;
 }
 
@@ -664,6 +700,7 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
   a.cal.proj_w = proj_w; a.cal.proj_h = proj_h;
   int rc = emit_configure();
   if (rc) return rc;
+  if ((rc = check_emit_size(a))) return rc;
   emit_kernel<kModePairs><<<grid_for(a.total_tiles, kEmitWarps), kEmitWarps * 32, kEmitSmem, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
@@ -693,11 +730,12 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   const int thr = kEmitWarps * 32;
   int rc = emit_configure();
   if (rc) return rc;
+  if ((rc = check_emit_size(a))) return rc;
   if (cam_rays) {
-    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmem, st>>>(a);
-    else emit_kernel<kModeTable32><<<g, thr, kEmitSmem, st>>>(a);
-  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmem, st>>>(a);
-  else emit_kernel<kModeCloud32><<<g, thr, kEmitSmem, st>>>(a);
+    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmemCloud, st>>>(a);
+    else emit_kernel<kModeTable32><<<g, thr, kEmitSmemCloud, st>>>(a);
+  } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmemCloud, st>>>(a);
+  else emit_kernel<kModeCloud32><<<g, thr, kEmitSmemCloud, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
