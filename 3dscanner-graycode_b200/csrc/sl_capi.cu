@@ -158,13 +158,14 @@ int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* co
 }
 
 int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, int B,
-                  int H, int W, int proj_w, int proj_h, const void* workspace, float* cam_pts,
-                  float* proj_pts, uint8_t* rgb, void* stream) {
-  if (!h_idx || !v_idx || !workspace || !cam_pts || !proj_pts) { set_error("null buffer"); return kErrBadArg; }
+                  int H, int W, int proj_w, int proj_h, const void* workspace, float* pairs,
+                  uint32_t* rgb32, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !pairs) { set_error("null buffer"); return kErrBadArg; }
+  if (rgb32 && !white_rgb) { set_error("rgb32 needs white_rgb"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1 || proj_w < 1 || proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
-  return launch_emit_pairs(h_idx, v_idx, white_rgb, B, H, W, proj_w, proj_h, workspace, cam_pts, proj_pts, rgb,
+  return launch_emit_pairs(h_idx, v_idx, white_rgb, B, H, W, proj_w, proj_h, workspace, pairs, rgb32,
                            (cudaStream_t)stream);
 }
 
@@ -179,15 +180,15 @@ int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, 
 
 int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
                   const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
-                  int B, int H, int W, const void* workspace, float* xyz, uint8_t* rgb, void* stream) {
-  if (!h_idx || !v_idx || !workspace || !xyz || !calib) { set_error("null buffer"); return kErrBadArg; }
+                  int B, int H, int W, const void* workspace, float* cloud, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !cloud || !calib) { set_error("null buffer"); return kErrBadArg; }
   if ((cam_rays == nullptr) != (proj_rays == nullptr)) { set_error("cam_rays and proj_rays go together"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
   return launch_emit_cloud(h_idx, v_idx, white_rgb, *calib, precision, cam_rays, proj_rays, B, H, W, workspace,
-                           xyz, rgb, (cudaStream_t)stream);
+                           cloud, (cudaStream_t)stream);
 }
 
 int sl_triangulate_points(const float* cam_pts, const float* proj_pts, int64_t N,
@@ -229,8 +230,7 @@ struct SlPipeline {
     void* ws = nullptr;
     long long* counts = nullptr;       // device [2]
     long long* counts_pinned = nullptr; // host pinned [2]
-    float* xyz = nullptr;
-    uint8_t* rgb = nullptr;
+    float* cloud = nullptr;      // [H*W][4] packed records
   } slot[kSlots];
   int8_t* h_codes = nullptr;   // lazily allocated for sl_decode_host with codes
   int8_t* v_codes = nullptr;
@@ -248,7 +248,7 @@ static void pipeline_free(SlPipeline* p) {
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.frames); cudaFree(s.white); cudaFree(s.h); cudaFree(s.v); cudaFree(s.ws);
-    cudaFree(s.counts); cudaFreeHost(s.counts_pinned); cudaFree(s.xyz); cudaFree(s.rgb);
+    cudaFree(s.counts); cudaFreeHost(s.counts_pinned); cudaFree(s.cloud);
     if (s.counted) cudaEventDestroy(s.counted);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
@@ -282,8 +282,7 @@ int sl_pipeline_create(SlPipeline** out, int device, int max_batch, int F, int H
     if (e == cudaSuccess) e = cudaMalloc(&s.ws, cloud_workspace_bytes(1, H, W));
     if (e == cudaSuccess) e = cudaMalloc(&s.counts, 2 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMallocHost(&s.counts_pinned, 2 * sizeof(long long));
-    if (e == cudaSuccess) e = cudaMalloc(&s.xyz, npix * 3 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&s.rgb, npix * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&s.cloud, npix * 4 * sizeof(float));
   }
   if (e != cudaSuccess) {
     pipeline_free(p);
@@ -301,12 +300,11 @@ void sl_pipeline_destroy(SlPipeline* p) { pipeline_free(p); }
 // `counted` event, while the next scans' copies and kernels are already queued on other streams.
 int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host,
                           int B, const SlCalib* calib, int precision, double eps,
-                          int16_t* h_idx_host, int16_t* v_idx_host, float* xyz_host,
-                          uint8_t* rgb_host, int64_t cap_points, int64_t* counts_host) {
-  if (!p || !frames_host || !calib || !xyz_host || !counts_host) { set_error("null argument"); return kErrBadArg; }
+                          int16_t* h_idx_host, int16_t* v_idx_host, float* cloud_host,
+                          int64_t cap_points, int64_t* counts_host) {
+  if (!p || !frames_host || !calib || !cloud_host || !counts_host) { set_error("null argument"); return kErrBadArg; }
   if (B < 1 || B > p->max_batch) { set_error("B=%d outside 1..max_batch=%d", B, p->max_batch); return kErrBadArg; }
   if ((h_idx_host == nullptr) != (v_idx_host == nullptr)) { set_error("h_idx_host and v_idx_host go together"); return kErrBadArg; }
-  if (rgb_host && !white_rgb_host) { set_error("rgb_host needs white_rgb_host"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
   SL_CUDA(cudaSetDevice(p->device));
   const size_t npix = (size_t)p->H * p->W;
@@ -339,11 +337,8 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     const long long n = s.counts_pinned[0];
     counts_host[i] = n;
     if (total + n > cap_points) overflow = true;
-    if (!overflow && n > 0) {
-      SL_CUDA(cudaMemcpyAsync(xyz_host + (size_t)total * 3, s.xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-      if (rgb_host)
-        SL_CUDA(cudaMemcpyAsync(rgb_host + (size_t)total * 3, s.rgb, (size_t)n * 3, cudaMemcpyDeviceToHost, s.stream));
-    }
+    if (!overflow && n > 0)
+      SL_CUDA(cudaMemcpyAsync(cloud_host + (size_t)total * 4, s.cloud, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     total += n;
     return kOk;
   };
@@ -371,7 +366,7 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
     rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
-                           1, p->H, p->W, s.ws, s.xyz, (white_rgb_host && rgb_host) ? s.rgb : nullptr, s.stream);
+                           1, p->H, p->W, s.ws, s.cloud, s.stream);
     if (rc) break;
     SL_CUDA(cudaEventRecord(s.counted, s.stream));
   }

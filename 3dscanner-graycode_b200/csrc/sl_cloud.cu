@@ -351,9 +351,8 @@ struct EmitArgs {
   const uint32_t* band_pre;
   const uint32_t* col_bits;
   const long long* col_base;
-  float* out_a;             // pairs: cam_pts (N,2)   cloud: xyz (N,3)
-  float* out_b;             // pairs: proj_pts (N,2)
-  uint8_t* rgb;             // nullable
+  float* out;               // (N,4) records, see emit_kernel
+  uint32_t* out_rgb32;      // pairs mode only, nullable: (N,) packed colour
   const float2* cam_rays;   // table modes: [H][W] undistorted camera rays (rotated by R)
   const float2* proj_rays;  // table modes: [proj_h][proj_w] undistorted projector rays
   int H, W, bands, tiles_x;
@@ -361,32 +360,33 @@ struct EmitArgs {
   CalibDev cal;
 };
 
-// Per-warp shared memory: for each of the tile's columns a run of up to 32 compacted points
-// (kPtWords payload words each, +1 word of padding per column against bank conflicts) and their colours.
-constexpr int kRgbRunPitch = kBandRows * 3 + 4;        // bytes per column
-template <int KW>                                      // payload words per point: 3 (cloud) or 4 (pairs)
+// Per-warp shared memory: for each of the tile's columns a run of up to 32 compacted 16-byte records
+// (+1 record of padding per column against bank conflicts).
+constexpr int kRunPitch = kBandRows + 1;               // uint4 records per column
+template <bool AUX>
 struct EmitTile {
-  static constexpr int kRunPitch = kBandRows * KW + 1; // words per column
-  uint32_t pts[kEmitCols * kRunPitch];
-  uint8_t rgb[kEmitCols * kRgbRunPitch];
+  uint4 rec[kEmitCols * kRunPitch];
+  uint32_t aux[AUX ? kEmitCols * kRunPitch : 1];       // pairs mode: the colour word of each point
 };
 
 // One warp per tile of 32 rows x kEmitCols columns.
 //  Phase A (row-major; a lane owns 4 neighbouring pixels of a row): vector loads of the indices, the
 //    colour and the camera rays, gathers of the projector rays (neighbouring pixels hit neighbouring
 //    projector pixels), the triangulation.  The rank of a valid pixel inside its column is
-//    popc(col_bits & rows-above), so every result goes straight to its slot of the column's run.
-//  Phase B: each column's run leaves shared memory as contiguous words.  Runs of successive bands /
-//    columns abut in the output, which is the reference's x-major order (triangulate.py:52-53).
+//    popc(col_bits & rows-above), so every 16-byte record goes straight to its slot of the column's run.
+//  Phase B: each column's run leaves shared memory as one contiguous, coalesced block of records.
+//    Runs of successive bands / columns abut in the output: the reference's x-major order
+//    (triangulate.py:52-53).
+// Record layouts (out, 4 words per point):
+//    cloud modes  {x, y, z, rgb}     rgb = R | G<<8 | B<<16 (0 without a colour image)
+//    kModePairs   {cam_x, cam_y, proj_x, proj_y}, colour word (same packing) to out_rgb32 when given
 template <int MODE>
-__global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a) {
   extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
   if (t >= a.total_tiles) return;
-  constexpr int kW = (MODE == kModePairs) ? 4 : 3;                    // payload words per point
-  using Tile = EmitTile<kW>;
-  constexpr int kRunPitch = Tile::kRunPitch;
+  using Tile = EmitTile<MODE == kModePairs>;
   Tile& tile = reinterpret_cast<Tile*>(emit_smem)[warp];
   // tile -> (scan, band, column block); 32-bit arithmetic (total_tiles < 2^31 is checked by the launcher)
   const uint32_t ti = (uint32_t)t;
@@ -396,10 +396,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs
   const int band = (int)(in_scan / (uint32_t)a.tiles_x);
   const int tx = (int)(in_scan - (uint32_t)band * (uint32_t)a.tiles_x);
   const int x0 = tx * kEmitCols, y0 = band * kBandRows;
-  const int rows = min(kBandRows, a.H - y0), cols = min(kEmitCols, a.W - x0);
+  const int cols = min(kEmitCols, a.W - x0);
   const size_t img = (size_t)b * a.H * a.W;
   const size_t cell = ((size_t)b * a.bands + band) * a.W + x0;       // (scan, band, column x0)
-  const bool has_rgb = a.white != nullptr && a.rgb != nullptr;
+  const bool has_rgb = a.white != nullptr;
   const bool vec = ((a.W & 3) == 0) && cols == kEmitCols;
   constexpr bool kTable = (MODE == kModeTable32 || MODE == kModeTable64);
 
@@ -416,55 +416,37 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs
   uint32_t cb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
-  // first-level loads of an iteration (vector path), issued one iteration ahead of their use
-  struct RowLoads { uint2 h2, v2; uint32_t w0, w1, w2; float4 r0, r1; };
-  auto fetch = [&](int r, RowLoads& L) {
-    const uint32_t any = ((cb[0] | cb[1] | cb[2] | cb[3]) >> r) & 1u;
-    if (!any) return;
-    const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
-    L.h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
-    L.v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
-    if (has_rgb) {
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);       // 12 bytes = 4 RGB pixels
-      L.w0 = __ldg(wp); L.w1 = __ldg(wp + 1); L.w2 = __ldg(wp + 2);
-    }
-    if (kTable) {
-      const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
-      L.r0 = __ldg(rp); L.r1 = __ldg(rp + 1);
-    }
-  };
-  RowLoads cur, nxt;
-  cur.h2 = cur.v2 = nxt.h2 = nxt.v2 = make_uint2(0, 0);
-  cur.w0 = cur.w1 = cur.w2 = nxt.w0 = nxt.w1 = nxt.w2 = 0;
-  cur.r0 = cur.r1 = nxt.r0 = nxt.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (vec) fetch(rr, cur);
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const int r = rr + 8 * it;
-    if (vec && it < 3) fetch(r + 8, nxt);
     const uint32_t below = (1u << r) - 1u;
     bool ok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) ok[k] = (cb[k] >> r) & 1u;            // == (h != -1 && v != -1), triangulate.py:56
-    if (!(ok[0] | ok[1] | ok[2] | ok[3])) { cur = nxt; continue; }
+    if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
     int hq[4], vq[4];
     uint32_t col[4] = {0, 0, 0, 0};
     float2 cray[4];
     const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
     if (vec) {
-      hq[0] = cur.h2.x & 0xffff; hq[1] = cur.h2.x >> 16; hq[2] = cur.h2.y & 0xffff; hq[3] = cur.h2.y >> 16;
-      vq[0] = cur.v2.x & 0xffff; vq[1] = cur.v2.x >> 16; vq[2] = cur.v2.y & 0xffff; vq[3] = cur.v2.y >> 16;
+      const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
+      const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
+      hq[0] = h2.x & 0xffff; hq[1] = h2.x >> 16; hq[2] = h2.y & 0xffff; hq[3] = h2.y >> 16;
+      vq[0] = v2.x & 0xffff; vq[1] = v2.x >> 16; vq[2] = v2.y & 0xffff; vq[3] = v2.y >> 16;
       if (has_rgb) {
-        col[0] = cur.w0 & 0xffffffu;
-        col[1] = (cur.w0 >> 24) | ((cur.w1 & 0xffffu) << 8);
-        col[2] = (cur.w1 >> 16) | ((cur.w2 & 0xffu) << 16);
-        col[3] = cur.w2 >> 8;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);   // 12 bytes = 4 RGB pixels
+        col[0] = w0 & 0xffffffu;
+        col[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+        col[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
+        col[3] = w2 >> 8;
       }
       if (kTable) {
-        cray[0] = make_float2(cur.r0.x, cur.r0.y); cray[1] = make_float2(cur.r0.z, cur.r0.w);
-        cray[2] = make_float2(cur.r1.x, cur.r1.y); cray[3] = make_float2(cur.r1.z, cur.r1.w);
+        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
+        cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
       }
-      cur = nxt;
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -473,7 +455,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs
           hq[k] = (uint16_t)a.h[g + k]; vq[k] = (uint16_t)a.v[g + k];
           if (has_rgb) {
             const uint8_t* wp = a.white + (g + k) * 3;
-            col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);
+            col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);      // triangulate.py:64
           }
           if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4 + k);
         }
@@ -489,10 +471,11 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!ok[k]) continue;
-      float X, Y, Z = 0.f, Q = 0.f;
+      float X, Y, Z = 0.f;
+      uint32_t wword = col[k];
       const float u = (float)(x0 + c4 + k), w = (float)(y0 + r);
       if (MODE == kModePairs) {
-        X = u; Y = w; Z = (float)hc[k]; Q = (float)vc[k];
+        X = u; Y = w; Z = (float)hc[k]; wword = __float_as_uint((float)vc[k]);
       } else if (MODE == kModeCloud32) {
         triangulate_fp32(u, w, (float)hc[k], (float)vc[k], a.cal, X, Y, Z);
       } else if (MODE == kModeCloud64) {
@@ -507,35 +490,20 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 6) emit_kernel(const EmitArgs
         X = (float)dx; Y = (float)dy; Z = (float)dz;
       }
       const int rank = __popc(cb[k] & below);
-      uint32_t* dst = tile.pts + (c4 + k) * kRunPitch + rank * kW;
-      dst[0] = __float_as_uint(X); dst[1] = __float_as_uint(Y); dst[2] = __float_as_uint(Z);
-      if (MODE == kModePairs) dst[3] = __float_as_uint(Q);
-      if (has_rgb) {
-        uint8_t* dc = tile.rgb + (c4 + k) * kRgbRunPitch + rank * 3;
-        dc[0] = (uint8_t)col[k]; dc[1] = (uint8_t)(col[k] >> 8); dc[2] = (uint8_t)(col[k] >> 16);    // triangulate.py:64
-      }
+      tile.rec[(c4 + k) * kRunPitch + rank] = make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), wword);
+      if (MODE == kModePairs) tile.aux[(c4 + k) * kRunPitch + rank] = col[k];
     }
   }
   __syncwarp();
 
   // ---- phase B
+  uint4* out = reinterpret_cast<uint4*>(a.out);
   for (int cidx = 0; cidx < cols; ++cidx) {
     const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, cidx));
     const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
-    if (cnt == 0) continue;
-    const uint32_t* run = tile.pts + cidx * kRunPitch;
-    if (MODE == kModePairs) {
-      for (int w = lane; w < 2 * cnt; w += 32) {           // point p, component j <- run[4p + j] / run[4p + 2 + j]
-        const int pt = w >> 1, j = w & 1;
-        a.out_a[base * 2 + w] = __uint_as_float(run[pt * 4 + j]);
-        a.out_b[base * 2 + w] = __uint_as_float(run[pt * 4 + 2 + j]);
-      }
-    } else {
-      for (int w = lane; w < 3 * cnt; w += 32) a.out_a[base * 3 + w] = __uint_as_float(run[w]);
-    }
-    if (has_rgb) {
-      const uint8_t* rc = tile.rgb + cidx * kRgbRunPitch;
-      for (int w = lane; w < 3 * cnt; w += 32) a.rgb[base * 3 + w] = rc[w];
+    if (lane < cnt) {
+      out[base + lane] = tile.rec[cidx * kRunPitch + lane];
+      if (MODE == kModePairs && a.out_rgb32) a.out_rgb32[base + lane] = tile.aux[cidx * kRunPitch + lane];
     }
   }
 }
@@ -657,8 +625,8 @@ uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_s
   return c.bitmap;
 }
 
-constexpr int kEmitSmem = (int)(sizeof(EmitTile<4>) * kEmitWarps);       // pairs mode
-constexpr int kEmitSmemCloud = (int)(sizeof(EmitTile<3>) * kEmitWarps);
+constexpr int kEmitSmem = (int)(sizeof(EmitTile<true>) * kEmitWarps);       // pairs mode
+constexpr int kEmitSmemCloud = (int)(sizeof(EmitTile<false>) * kEmitWarps);
 
 // > 48 KB of dynamic shared memory needs an opt-in per kernel, once per device
 static int emit_configure() {
@@ -681,11 +649,11 @@ static int check_emit_size(const EmitArgs& a) {
 }
 
 static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
-                          const void* ws, float* out_a, float* out_b, uint8_t* rgb) {
+                          const void* ws, float* out, uint32_t* out_rgb32) {
   const CloudWorkspace c = carve_workspace(const_cast<void*>(ws), B, H, W);
   EmitArgs a;
   a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_bits = c.col_bits; a.col_base = c.col_base;
-  a.out_a = out_a; a.out_b = out_b; a.rgb = rgb; a.H = H; a.W = W; a.bands = c.bands;
+  a.out = out; a.out_rgb32 = out_rgb32; a.H = H; a.W = W; a.bands = c.bands;
   a.cam_rays = nullptr; a.proj_rays = nullptr;
   a.tiles_x = (W + kEmitCols - 1) / kEmitCols;
   a.total_tiles = (long long)a.tiles_x * a.bands * B;      // callers reject >= 2^31 (check_emit_size)
@@ -693,9 +661,8 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
 }
 
 int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
-                      int proj_w, int proj_h, const void* ws, float* cam_pts, float* proj_pts,
-                      uint8_t* rgb, cudaStream_t st) {
-  EmitArgs a = make_emit(h, v, white, B, H, W, ws, cam_pts, proj_pts, rgb);
+                      int proj_w, int proj_h, const void* ws, float* pairs, uint32_t* rgb32, cudaStream_t st) {
+  EmitArgs a = make_emit(h, v, white, B, H, W, ws, pairs, rgb32);
   a.cal = CalibDev();
   a.cal.proj_w = proj_w; a.cal.proj_h = proj_h;
   int rc = emit_configure();
@@ -722,8 +689,8 @@ int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_ra
 
 int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
                       int precision, const float* cam_rays, const float* proj_rays, int B, int H, int W,
-                      const void* ws, float* xyz, uint8_t* rgb, cudaStream_t st) {
-  EmitArgs a = make_emit(h, v, white, B, H, W, ws, xyz, nullptr, rgb);
+                      const void* ws, float* cloud, cudaStream_t st) {
+  EmitArgs a = make_emit(h, v, white, B, H, W, ws, cloud, nullptr);
   a.cal = make_calib(calib);
   a.cam_rays = (const float2*)cam_rays; a.proj_rays = (const float2*)proj_rays;
   const int g = grid_for(a.total_tiles, kEmitWarps);

@@ -40,13 +40,12 @@ int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int
 int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts, cudaStream_t st);
 uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan);
 int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
-                      int proj_w, int proj_h, const void* ws, float* cam_pts, float* proj_pts,
-                      uint8_t* rgb, cudaStream_t st);
+                      int proj_w, int proj_h, const void* ws, float* pairs, uint32_t* rgb32, cudaStream_t st);
 int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
                        cudaStream_t st);
 int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
                       int precision, const float* cam_rays, const float* proj_rays, int B, int H, int W,
-                      const void* ws, float* xyz, uint8_t* rgb, cudaStream_t st);
+                      const void* ws, float* cloud, cudaStream_t st);
 int launch_triangulate_points(const float* cam_pts, const float* proj_pts, long long N,
                               const SlCalib& calib, int precision, double* out, cudaStream_t st);
 size_t filter_workspace_bytes(long long N);

@@ -111,8 +111,7 @@ class Triangulate(object):
             check(lib().sl_compact_offsets(_ptr(bufs.h_idx), _ptr(bufs.v_idx), 1, self.cam_h, self.cam_w,
                                            _ptr(bufs.ws), _ptr(bufs.counts), _stream()))
             check(lib().sl_emit_cloud(_ptr(bufs.h_idx), _ptr(bufs.v_idx), _ptr(white), C.byref(s), _PREC[precision],
-                                      None, None, 1, self.cam_h, self.cam_w, _ptr(bufs.ws), _ptr(bufs.xyz),
-                                      _ptr(bufs.rgb), _stream()))
+                                      None, None, 1, self.cam_h, self.cam_w, _ptr(bufs.ws), _ptr(bufs.cloud), _stream()))
         n = int(bufs.counts[1].item())
         pts = bufs.xyz[:n].to(torch.float64).t().contiguous().cpu().numpy()
         colors = bufs.rgb[:n].cpu().numpy().astype(np.float64) / 255.0

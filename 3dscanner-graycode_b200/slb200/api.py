@@ -287,16 +287,15 @@ def cam_proj_pairs(h_pixels, v_pixels, proj_size, img_white=None, device=None):
         white = white.to(dev).contiguous()
     off = _Offsets(h_idx, v_idx)
     n = int(off.counts[1].item())
-    cam = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    proj = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    rgb = torch.empty((n, 3), dtype=torch.uint8, device=dev) if white is not None else None
-    if n == 0:
-        return cam, proj, rgb
-    with torch.cuda.device(dev):
-        check(lib().sl_emit_pairs(_ptr(h_idx), _ptr(v_idx), _ptr(white), 1, off.h, off.w,
-                                  int(proj_size[0]), int(proj_size[1]), _ptr(off.ws), _ptr(cam),
-                                  _ptr(proj), _ptr(rgb), _stream()))
-    return cam, proj, rgb
+    pairs = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    rgb32 = torch.empty((n,), dtype=torch.int32, device=dev) if white is not None else None
+    if n:
+        with torch.cuda.device(dev):
+            check(lib().sl_emit_pairs(_ptr(h_idx), _ptr(v_idx), _ptr(white), 1, off.h, off.w,
+                                      int(proj_size[0]), int(proj_size[1]), _ptr(off.ws), _ptr(pairs),
+                                      _ptr(rgb32), _stream()))
+    rgb = unpack_rgb(rgb32) if rgb32 is not None else None
+    return pairs[:, :2].contiguous(), pairs[:, 2:].contiguous(), rgb
 
 
 def triangulate_points(cam_pts, proj_pts, calib: Calibration, precision="fp64", device=None) -> torch.Tensor:
@@ -343,15 +342,40 @@ def filter_box(pts: torch.Tensor, colors: Optional[torch.Tensor], threshold: flo
     return out_pts[:, :m], (out_col[:m] if out_col is not None else None)
 
 
+def unpack_rgb(word: torch.Tensor) -> torch.Tensor:
+    """Colour words (R | G<<8 | B<<16, int32 / float32 bit patterns) -> (N,3) uint8."""
+    return word.contiguous().view(torch.uint8).reshape(-1, 4)[:, :3]
+
+
 @dataclass
 class CloudBuffers:
-    """Pre-allocated device buffers so a scan_to_cloud call allocates nothing."""
+    """Pre-allocated device buffers so a scan_to_cloud call allocates nothing.
+
+    ``cloud`` holds one 16-byte XYZRGB record per point: ``[x, y, z, bits(R | G<<8 | B<<16)]``;
+    ``xyz`` / ``rgb`` give the two halves as (strided) views / unpacked copies."""
     h_idx: torch.Tensor
     v_idx: torch.Tensor
     ws: torch.Tensor
     counts: torch.Tensor
-    xyz: torch.Tensor
-    rgb: torch.Tensor
+    cloud: torch.Tensor
+
+    @property
+    def xyz(self) -> torch.Tensor:
+        return self.cloud[:, :3]
+
+    @property
+    def rgb(self) -> torch.Tensor:
+        return _RgbView(self.cloud)
+
+
+class _RgbView:
+    """Lazy ``rgb[:n]`` accessor over the colour word of the records (avoids unpacking the whole buffer)."""
+
+    def __init__(self, cloud):
+        self._cloud = cloud
+
+    def __getitem__(self, idx) -> torch.Tensor:
+        return unpack_rgb(self._cloud[idx][..., 3])
 
     @classmethod
     def allocate(cls, b: int, h: int, w: int, device, cap_points: Optional[int] = None) -> "CloudBuffers":
@@ -361,8 +385,7 @@ class CloudBuffers:
                    torch.empty(shape, dtype=torch.int16, device=device),
                    torch.empty(lib().sl_cloud_workspace_bytes(b, h, w), dtype=torch.uint8, device=device),
                    torch.empty(b + 1, dtype=torch.int64, device=device),
-                   torch.empty((cap, 3), dtype=torch.float32, device=device),
-                   torch.empty((cap, 3), dtype=torch.uint8, device=device))
+                   torch.empty((cap, 4), dtype=torch.float32, device=device))
 
 
 class LensTables:
@@ -389,8 +412,8 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     ``tables`` (LensTables of the same calibration / sizes) replaces the per-pixel undistortion
     iterations by look-ups of exact precomputed rays; without it the iterations run in the kernel.
 
-    Results are in the returned buffers: ``xyz[:counts[B]]`` / ``rgb[:counts[B]]`` packed scan
-    after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
+    Results are in the returned buffers: ``cloud[:counts[B]]`` (XYZRGB records; ``.xyz`` / ``.rgb``
+    views) packed scan after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
     Mirrors src/3-capture_decode.py:75-100 + src/4-triangulate.py:50-64.
     """
     _check_stack(frames)
@@ -415,8 +438,7 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
         check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
                               _PREC[precision], _ptr(tables.cam) if tables is not None else None,
                               _ptr(tables.proj) if tables is not None else None,
-                              b, h, w, _ptr(buffers.ws), _ptr(buffers.xyz),
-                              _ptr(buffers.rgb) if white_rgb is not None else None, st))
+                              b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
     return buffers
 
 
@@ -450,10 +472,11 @@ class Pipeline:
         return C.c_void_p(a.ctypes.data)
 
     def scan_to_cloud(self, frames, white_rgb, calib: Calibration, precision="fp32", eps: float = 1.0,
-                      xyz=None, rgb=None, counts=None, h_idx=None, v_idx=None):
-        """``frames`` host uint8 ``(B,F,H,W)`` (numpy or CPU torch, ideally pinned); outputs are
-        written into host buffers (allocated pinned when not supplied).  Returns
-        ``(xyz[:n], rgb[:n] | None, counts)``."""
+                      cloud=None, counts=None, h_idx=None, v_idx=None):
+        """``frames`` host uint8 ``(B,F,H,W)`` (numpy or CPU torch, ideally pinned); the XYZRGB records
+        are written into the host tensor ``cloud`` ``(cap,4)`` f32 (allocated pinned when not
+        supplied).  Returns ``(cloud[:n], counts)``; ``cloud[:, :3]`` is xyz, ``unpack_rgb(cloud[:, 3])``
+        the colours."""
         shape = tuple(frames.shape)
         if len(shape) == 3:
             shape = (1, *shape)
@@ -463,19 +486,17 @@ class Pipeline:
         if getattr(frames, "dtype", None) not in (np.uint8, torch.uint8):
             raise TypeError("frames must be uint8")
         cap = b * self.h * self.w
-        if xyz is None:
-            xyz = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
-        if rgb is None and white_rgb is not None:
-            rgb = torch.empty((cap, 3), dtype=torch.uint8).pin_memory()
+        if cloud is None:
+            cloud = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
         if counts is None:
             counts = torch.empty(b + 1, dtype=torch.int64)
         s = calib.struct()
         check(lib().sl_scan_to_cloud_host(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), b,
                                           C.byref(s), _PREC[precision], float(eps), self._host_ptr(h_idx),
-                                          self._host_ptr(v_idx), self._host_ptr(xyz), self._host_ptr(rgb),
-                                          int(xyz.shape[0]), self._host_ptr(counts)))
+                                          self._host_ptr(v_idx), self._host_ptr(cloud),
+                                          int(cloud.shape[0]), self._host_ptr(counts)))
         n = int(counts[b])
-        return xyz[:n], (rgb[:n] if rgb is not None else None), counts
+        return cloud[:n], counts
 
     def decode(self, frames, eps: float = 1.0, codes: bool = False):
         """Host uint8 ``(B,F,H,W)`` -> host int16 ``h_pixels, v_pixels`` [+ int8 tri-state codes]."""

@@ -31,52 +31,43 @@ def row_bands(height: int, world: int, align: int = 32) -> List[Tuple[int, int]]
     return out
 
 
-def gather_clouds(xyz: torch.Tensor, rgb: Optional[torch.Tensor], counts: torch.Tensor, group=None):
+def gather_clouds(cloud: torch.Tensor, counts: torch.Tensor, group=None):
     """All-gather-v of per-rank packed clouds.
 
-    xyz (n_r,3) f32, rgb (n_r,3) u8 (or None), counts (B_r+1,) int64 with counts[-1] == n_r.
-    Returns (xyz_all, rgb_all, counts_per_rank) where clouds are concatenated in rank order (scan
-    order is preserved because scans are block-partitioned) and counts_per_rank is a list of the
-    per-scan count tensors.  Two collectives: one for the counts, one per payload (padded to the
-    largest rank).
+    cloud (n_r, C) (XYZRGB records, C = 4 f32), counts (B_r+1,) int64 with counts[-1] == n_r.
+    Returns (cloud_all, counts_per_rank): clouds concatenated in rank order (scan order is preserved
+    because scans are block-partitioned); counts_per_rank is a list of the per-scan count tensors.
+    Three collectives: sizes, payload (padded to the largest rank), counts.
     """
     world = dist.get_world_size(group)
-    dev = xyz.device
-    n_local = torch.tensor([xyz.shape[0], counts.numel()], dtype=torch.int64, device=dev)
+    dev = cloud.device
+    n_local = torch.tensor([cloud.shape[0], counts.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.empty_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local, group=group)
     n_pts = [int(s[0]) for s in sizes]
     n_cnt = [int(s[1]) for s in sizes]
     cap, ccap = max(n_pts), max(n_cnt)
 
-    def padded(t, rows, width, dtype):
-        buf = torch.zeros((rows, width) if width else (rows,), dtype=dtype, device=dev)
-        buf[: t.shape[0]] = t
-        return buf
-
-    def allgather(t, rows, width, dtype):
-        mine = padded(t, rows, width, dtype)
-        out = torch.empty((world * rows, width) if width else (world * rows,), dtype=dtype, device=dev)
+    def allgather(t, rows):
+        shape = (rows,) + tuple(t.shape[1:])
+        mine = torch.zeros(shape, dtype=t.dtype, device=dev)
+        mine[: t.shape[0]] = t
+        out = torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
         dist.all_gather_into_tensor(out, mine, group=group)
         return out
 
-    xyz_all = allgather(xyz, cap, 3, torch.float32)
-    xyz_cat = torch.cat([xyz_all[r * cap: r * cap + n_pts[r]] for r in range(world)])
-    rgb_cat = None
-    if rgb is not None:
-        rgb_all = allgather(rgb, cap, 3, torch.uint8)
-        rgb_cat = torch.cat([rgb_all[r * cap: r * cap + n_pts[r]] for r in range(world)])
-    cnt_all = allgather(counts, ccap, 0, torch.int64)
+    all_pts = allgather(cloud, cap)
+    cloud_cat = torch.cat([all_pts[r * cap: r * cap + n_pts[r]] for r in range(world)])
+    cnt_all = allgather(counts, ccap)
     counts_per_rank = [cnt_all[r * ccap: r * ccap + n_cnt[r]] for r in range(world)]
-    return xyz_cat, rgb_cat, counts_per_rank
+    return cloud_cat, counts_per_rank
 
 
-def merge_row_bands(band_xyz: Sequence[torch.Tensor], band_rgb: Sequence[Optional[torch.Tensor]],
-                    band_cols: Sequence[torch.Tensor]):
+def merge_row_bands(band_clouds: Sequence[torch.Tensor], band_cols: Sequence[torch.Tensor]):
     """Merge the clouds of row bands (top to bottom) of ONE capture into the reference's x-major
     order (scanner/triangulation/triangulate.py:52-53): for every camera column, band 0's points,
     then band 1's, ...  band_cols[k] is the int64 (W,) per-column point count of band k (columns in
-    a band's cloud are already x-major).  Returns (xyz, rgb)."""
+    a band's cloud are already x-major).  Returns the merged (N, C) cloud."""
     cols = torch.stack(list(band_cols))                        # (K, W)
     k, w = cols.shape
     # destination of each (band, column) run: columns first, bands inside a column
@@ -84,17 +75,13 @@ def merge_row_bands(band_xyz: Sequence[torch.Tensor], band_rgb: Sequence[Optiona
     start = torch.cumsum(flat, 0) - flat
     start = start.reshape(w, k).t()                            # (K, W) start offset of each run
     total = int(flat.sum())
-    xyz = torch.empty((total, 3), dtype=band_xyz[0].dtype, device=band_xyz[0].device)
-    rgb = None
-    if band_rgb[0] is not None:
-        rgb = torch.empty((total, 3), dtype=band_rgb[0].dtype, device=band_rgb[0].device)
+    first = band_clouds[0]
+    out = torch.empty((total,) + tuple(first.shape[1:]), dtype=first.dtype, device=first.device)
     for b in range(k):
         n = int(cols[b].sum())
         src_start = torch.cumsum(cols[b], 0) - cols[b]          # (W,) start of each column run in the band cloud
         col_of_pt = torch.repeat_interleave(torch.arange(w, device=cols.device), cols[b])
         within = torch.arange(n, device=cols.device) - src_start[col_of_pt]
         dst = start[b][col_of_pt] + within
-        xyz[dst] = band_xyz[b][:n]
-        if rgb is not None:
-            rgb[dst] = band_rgb[b][:n]
-    return xyz, rgb
+        out[dst] = band_clouds[b][:n]
+    return out

@@ -314,15 +314,14 @@ def run_gpu(args):
         for i in range(eb):
             host_frames[i].copy_(ring_frames[i]); host_white[i].copy_(ring_white[i])
         pipe = slb200.Pipeline(N_FRAMES, H, W, max_batch=eb, device=local)
-        xyz_h = torch.empty((eb * H * W, 3), dtype=torch.float32).pin_memory()
-        rgb_h = torch.empty((eb * H * W, 3), dtype=torch.uint8).pin_memory()
+        cloud_h = torch.empty((eb * H * W, 4), dtype=torch.float32).pin_memory()
         cnt_h = torch.empty(eb + 1, dtype=torch.int64)
         calls = max(2, min(10, (K + eb - 1) // eb))
-        pipe.scan_to_cloud(host_frames, host_white, calib, xyz=xyz_h, rgb=rgb_h, counts=cnt_h)   # warm-up
+        pipe.scan_to_cloud(host_frames, host_white, calib, cloud=cloud_h, counts=cnt_h)   # warm-up
         barrier()
         t0 = time.perf_counter()
         for _ in range(calls):
-            pipe.scan_to_cloud(host_frames, host_white, calib, xyz=xyz_h, rgb=rgb_h, counts=cnt_h)
+            pipe.scan_to_cloud(host_frames, host_white, calib, cloud=cloud_h, counts=cnt_h)
         torch.cuda.synchronize()
         el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -330,7 +329,7 @@ def run_gpu(args):
         n_pts = int(cnt_h[eb])
         e2e = {"value": world * calls * eb * MPX / float(el.item()), "unit": "Mpx/s",
                "h2d_bytes_per_step": N_FRAMES * H * W + H * W * 3,
-               "d2h_bytes_per_step": int(n_pts / eb * 15 + 16),
+               "d2h_bytes_per_step": int(n_pts / eb * 16 + 16),
                "scans_per_call": eb, "steps": calls * eb, "ms_per_scan": float(el.item()) / (calls * eb) * 1e3,
                "api": "sl_scan_to_cloud_host (slb200.Pipeline.scan_to_cloud), pinned host buffers"}
         pipe.close()
@@ -339,20 +338,20 @@ def run_gpu(args):
     gather = None
     if world > 1:
         from slb200.dist import gather_clouds
-        xyz = bufs.xyz[:valid_pts]; rgb = bufs.rgb[:valid_pts]
-        gather_clouds(xyz, rgb, bufs.counts)
+        cloud = bufs.cloud[:valid_pts]
+        gather_clouds(cloud, bufs.counts)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         reps = 5
         for _ in range(reps):
-            out = gather_clouds(xyz, rgb, bufs.counts)
+            out = gather_clouds(cloud, bufs.counts)
         g1.record()
         torch.cuda.synchronize()
         gms = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gms.item()), "points_per_rank": valid_pts, "bytes_per_rank": valid_pts * 15,
-                  "what": "all-gather-v (NCCL) of one scan's compacted {xyz f32, rgb u8} cloud per rank"}
+        gather = {"ms": float(gms.item()), "points_per_rank": valid_pts, "bytes_per_rank": valid_pts * 16,
+                  "what": "all-gather-v (NCCL) of one scan's compacted XYZRGB cloud (16 B records) per rank"}
     clocks = sampler.stop()
 
     # ---- CPU baseline (rank 0, N=1 only)
@@ -373,7 +372,7 @@ def run_gpu(args):
                                 else "5 Brown-Conrady iterations per valid pixel in the emit kernel"),
                        "parallelism": f"scan-sharded x{world}",
                        "l2": f"inputs rotate over a ring of {RING} resident scans ({RING * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "CUDA graph per scan (decode, count, band-prefix, column-scan, emit)"},
+                       "launch": "CUDA graph per scan (decode, strip-prefix, column-scan, emit)"},
             "scans_per_s": world * K / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

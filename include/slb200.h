@@ -109,13 +109,13 @@ int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H,
 /* Same, for a workspace whose validity bitmap was already written by sl_decode_u8 (same B,H,W). */
 int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream);
 
-/* Triangulate.get_cam_proj_pts (triangulate.py:39-71): emits, x-major,
- * cam_pts (N,2) f32 = [x,y], proj_pts (N,2) f32 = [min(proj_w-1,h), min(proj_h-1,v)] and
- * rgb (N,3) u8 = white_rgb[y,x,:] (nullable together with white_rgb).
+/* Triangulate.get_cam_proj_pts (triangulate.py:39-71): emits, x-major, one 16-byte record per
+ * valid pixel: pairs (N,4) f32 = [x, y, min(proj_w-1,h), min(proj_h-1,v)] (cam_pts | proj_pts) and,
+ * when rgb32 and white_rgb are given, rgb32 (N,) u32 = R | G<<8 | B<<16 of white_rgb[y,x,:].
  * Requires sl_compact_offsets on the same workspace first. */
 int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, int B,
-                  int H, int W, int proj_w, int proj_h, const void* workspace, float* cam_pts,
-                  float* proj_pts, uint8_t* rgb, void* stream);
+                  int H, int W, int proj_w, int proj_h, const void* workspace, float* pairs,
+                  uint32_t* rgb32, void* stream);
 
 /* Lens tables: the undistorted normalised ray of every camera pixel (rotated by R) and of every
  * projector pixel -- cv2.undistortPoints (triangulate.py:84-85: 5 Brown-Conrady fixed-point
@@ -129,11 +129,13 @@ int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, 
  * law-of-sines depth, ordered compaction.  With cam_rays/proj_rays (from sl_lens_tables, same
  * calibration and sizes) the rays are looked up; with both NULL the 5 Brown-Conrady iterations
  * run in the kernel for every valid pixel (fp32 or fp64 per `precision`).
- * xyz (N,3) f32, rgb (N,3) u8 (nullable with white_rgb), packed over the batch.
- * Requires sl_compact_offsets on the same workspace first. */
+ * cloud (N,4) f32: one 16-byte XYZRGB record per point = [x, y, z, bits(R | G<<8 | B<<16)] (the
+ * layout PCL calls PointXYZRGB; colour word 0 when white_rgb is NULL), packed over the batch, each
+ * scan in the reference's x-major order.
+ * Requires sl_compact_offsets[_decoded] on the same workspace first. */
 int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
                   const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
-                  int B, int H, int W, const void* workspace, float* xyz, uint8_t* rgb, void* stream);
+                  int B, int H, int W, const void* workspace, float* cloud, void* stream);
 
 /* Triangulate.triangulate (triangulate.py:73-97) on caller-supplied point pairs.
  * cam_pts, proj_pts device f32 (N,2); out device f64 (3,N) like the reference's return. */
@@ -163,13 +165,13 @@ void sl_pipeline_destroy(SlPipeline* p);
  * H2D of the frame stacks and white images, decode, compaction, triangulation, D2H.
  *   frames_host     u8 [B][F][H][W]         white_rgb_host  u8 [B][H][W][3] (nullable)
  *   h_idx_host, v_idx_host   nullable int16 [B][H][W]
- *   xyz_host        f32, capacity cap_points*3      rgb_host  u8, capacity cap_points*3 (nullable)
+ *   cloud_host      f32, capacity cap_points*4: XYZRGB records as sl_emit_cloud writes them
  *   counts_host     int64 [B+1] (last = total)
  * Fails with SL_ERR_BAD_ARG if the total exceeds cap_points (counts_host is still written). */
 int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host,
                           int B, const SlCalib* calib, int precision, double eps,
-                          int16_t* h_idx_host, int16_t* v_idx_host, float* xyz_host,
-                          uint8_t* rgb_host, int64_t cap_points, int64_t* counts_host);
+                          int16_t* h_idx_host, int16_t* v_idx_host, float* cloud_host,
+                          int64_t cap_points, int64_t* counts_host);
 
 /* Decode only, HOST buffers (get_codes + gray_to_decimal loops for one or more scans). */
 int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,

@@ -25,14 +25,12 @@ def _worker(rank, world, port, q):
     n_scans = 5
     rng = np.random.default_rng(0)
     per_scan = [int(x) for x in rng.integers(0, 50, n_scans)]
-    clouds = [torch.from_numpy(rng.random((n, 3)).astype(np.float32)) for n in per_scan]
-    colors = [torch.from_numpy(rng.integers(0, 256, (n, 3)).astype(np.uint8)) for n in per_scan]
+    clouds = [torch.from_numpy(rng.random((n, 4)).astype(np.float32)) for n in per_scan]
     lo, hi = shard_range(n_scans, rank, world)
-    xyz = torch.cat(clouds[lo:hi]) if hi > lo else torch.zeros((0, 3))
-    rgb = torch.cat(colors[lo:hi]) if hi > lo else torch.zeros((0, 3), dtype=torch.uint8)
+    mine = torch.cat(clouds[lo:hi]) if hi > lo else torch.zeros((0, 4))
     counts = torch.tensor(per_scan[lo:hi] + [sum(per_scan[lo:hi])], dtype=torch.int64)
-    xyz_all, rgb_all, cnts = gather_clouds(xyz, rgb, counts)
-    ok = torch.equal(xyz_all, torch.cat(clouds)) and torch.equal(rgb_all, torch.cat(colors))
+    cloud_all, cnts = gather_clouds(mine, counts)
+    ok = torch.equal(cloud_all, torch.cat(clouds))
     got = [int(c) for r in cnts for c in r[:-1]]
     ok = ok and got == per_scan
     q.put((rank, bool(ok)))
@@ -80,15 +78,13 @@ def test_merge_row_bands_restores_x_major_order():
     hp = rng.integers(-1, 50, (h, w)); vp = rng.integers(-1, 50, (h, w))
     white = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
     cam, proj, col = O.cam_proj_pairs(hp, vp, (64, 64), white)
-    full = np.concatenate([cam, proj], axis=1)[:, :3]
-    bx, bc, bcols = [], [], []
+    full = np.concatenate([cam, proj, np.round(col * 255)], axis=1).astype(np.float32)
+    bx, bcols = [], []
     for (y0, y1) in row_bands(h, 3):
         c, p, cl = O.cam_proj_pairs(hp[y0:y1], vp[y0:y1], (64, 64), white[y0:y1])
         c = c + np.array([[0, y0]], dtype=np.float32)
-        bx.append(torch.from_numpy(np.concatenate([c, p], axis=1)[:, :3].copy()))
-        bc.append(torch.from_numpy(np.round(cl * 255).astype(np.uint8)))
+        bx.append(torch.from_numpy(np.concatenate([c, p, np.round(cl * 255)], axis=1).astype(np.float32)))
         valid = (hp[y0:y1] != -1) & (vp[y0:y1] != -1)
         bcols.append(torch.from_numpy(valid.sum(axis=0).astype(np.int64)))
-    xyz, rgb = merge_row_bands(bx, bc, bcols)
-    np.testing.assert_array_equal(xyz.numpy(), full)
-    np.testing.assert_array_equal(rgb.numpy(), np.round(col * 255).astype(np.uint8))
+    merged = merge_row_bands(bx, bcols)
+    np.testing.assert_array_equal(merged.numpy(), full)

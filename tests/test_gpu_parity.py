@@ -311,8 +311,7 @@ def test_batched_cloud_matches_single(T):
         one = slb200.scan_to_cloud(scans[b][0], scans[b][1], calib)
         n = int(one.counts[1])
         assert n == counts[b]
-        assert T.equal(one.xyz[:n], bufs.xyz[start:start + n])
-        assert T.equal(one.rgb[:n], bufs.rgb[start:start + n])
+        assert T.equal(one.cloud[:n].view(T.int32), bufs.cloud[start:start + n].view(T.int32))
         assert T.equal(one.h_idx[0], bufs.h_idx[b])
         start += n
 
@@ -349,7 +348,7 @@ def test_lens_tables_exact_and_table_modes(T):
     tb32 = slb200.scan_to_cloud(frames, white, calib, precision="fp32", tables=tab)
     n = int(it64.counts[1])
     assert n == int(tb64.counts[1]) == int(tb32.counts[1]) and n > 0
-    assert T.equal(it64.xyz[:n], tb64.xyz[:n])              # same rays, same fp64 formula -> identical
+    assert T.equal(it64.cloud[:n].view(T.int32), tb64.cloud[:n].view(T.int32))    # same rays, same fp64 formula -> identical
     assert T.equal(it64.rgb[:n], tb32.rgb[:n])
     hp, vp = O.decode_pixels(frames.cpu().numpy().astype(np.float64))
     cam, proj, _ = O.cam_proj_pairs(hp, vp, proj_size, white.cpu().numpy())
@@ -371,13 +370,14 @@ def test_pipeline_host_buffers(T):
     white = T.stack([s[1] for s in scans]).contiguous().pin_memory()
     pipe = slb200.Pipeline(frames.shape[1], 200, 320, max_batch=5)
     h_idx = np.empty((5, 200, 320), np.int16); v_idx = np.empty((5, 200, 320), np.int16)
-    xyz, rgb, counts = pipe.scan_to_cloud(frames, white, calib, h_idx=h_idx, v_idx=v_idx)
+    cloud, counts = pipe.scan_to_cloud(frames, white, calib, h_idx=h_idx, v_idx=v_idx)
     tables = slb200.LensTables(calib, cam_size, "cuda")      # the pipeline builds the same tables internally
     dev = slb200.scan_to_cloud(frames.cuda(), white.cuda(), calib, tables=tables)
     n = int(dev.counts[-1])
-    assert int(counts[-1]) == n and xyz.shape[0] == n
+    assert int(counts[-1]) == n and tuple(cloud.shape) == (n, 4)
     np.testing.assert_array_equal(counts.numpy(), dev.counts.cpu().numpy())
-    assert T.equal(xyz, dev.xyz[:n].cpu()) and T.equal(rgb, dev.rgb[:n].cpu())
+    assert T.equal(cloud.view(T.int32), dev.cloud[:n].cpu().view(T.int32))       # records identical, bit for bit
+    assert T.equal(slb200.unpack_rgb(cloud[:, 3]), dev.rgb[:n].cpu())
     np.testing.assert_array_equal(h_idx, dev.h_idx.cpu().numpy())
     np.testing.assert_array_equal(v_idx, dev.v_idx.cpu().numpy())
     hi, vi, hc, vc = pipe.decode(frames[:2].numpy(), codes=True)
@@ -386,7 +386,7 @@ def test_pipeline_host_buffers(T):
         np.testing.assert_array_equal(hi[b], hp); np.testing.assert_array_equal(vi[b], vp)
         np.testing.assert_array_equal(hc[b], h); np.testing.assert_array_equal(vc[b], v)
     with pytest.raises(slb200.SlError):
-        pipe.scan_to_cloud(frames, white, calib, xyz=T.empty((10, 3), dtype=T.float32))   # cap too small
+        pipe.scan_to_cloud(frames, white, calib, cloud=T.empty((10, 4), dtype=T.float32))   # cap too small
     pipe.close()
 
 
