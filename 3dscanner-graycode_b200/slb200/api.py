@@ -347,6 +347,16 @@ def unpack_rgb(word: torch.Tensor) -> torch.Tensor:
     return word.contiguous().view(torch.uint8).reshape(-1, 4)[:, :3]
 
 
+class _RgbView:
+    """Lazy ``rgb[:n]`` accessor over the colour word of the records (avoids unpacking the whole buffer)."""
+
+    def __init__(self, cloud):
+        self._cloud = cloud
+
+    def __getitem__(self, idx) -> torch.Tensor:
+        return unpack_rgb(self._cloud[idx][..., 3])
+
+
 @dataclass
 class CloudBuffers:
     """Pre-allocated device buffers so a scan_to_cloud call allocates nothing.
@@ -367,15 +377,6 @@ class CloudBuffers:
     def rgb(self) -> torch.Tensor:
         return _RgbView(self.cloud)
 
-
-class _RgbView:
-    """Lazy ``rgb[:n]`` accessor over the colour word of the records (avoids unpacking the whole buffer)."""
-
-    def __init__(self, cloud):
-        self._cloud = cloud
-
-    def __getitem__(self, idx) -> torch.Tensor:
-        return unpack_rgb(self._cloud[idx][..., 3])
 
     @classmethod
     def allocate(cls, b: int, h: int, w: int, device, cap_points: Optional[int] = None) -> "CloudBuffers":
