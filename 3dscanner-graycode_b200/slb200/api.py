@@ -344,7 +344,9 @@ def filter_box(pts: torch.Tensor, colors: Optional[torch.Tensor], threshold: flo
 
 def unpack_rgb(word: torch.Tensor) -> torch.Tensor:
     """Colour words (R | G<<8 | B<<16, int32 / float32 bit patterns) -> (N,3) uint8."""
-    return word.contiguous().view(torch.uint8).reshape(-1, 4)[:, :3]
+    flat = torch.empty(word.shape, dtype=word.dtype, device=word.device)      # fresh, unit-stride storage
+    flat.copy_(word)
+    return flat.view(torch.uint8).reshape(-1, 4)[:, :3]
 
 
 class _RgbView:
