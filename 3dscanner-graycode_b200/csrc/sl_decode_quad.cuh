@@ -45,6 +45,52 @@ SL_HD void finish_axis(uint32_t accA, uint32_t accB, uint32_t allv, int n,
   out23 = g23 | byte_perm(bad, 0u, 0xbbaau);
 }
 
+// Full evaluation of the four rules for both axes (decode_codes.py:172-182).  Kept out of line on the
+// device: it is the slow path of decode_quad and must not add to the fast path's register budget.
+template <int NB, bool CODES, class Load, class StoreCode>
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void full_rules(Load ld, StoreCode st, int n, const QuadThr& qt, uint32_t ek, QuadOut& out) {
+  // column bits: code bit i (LSB = 0) is reference index j = n-1-i
+  {
+    uint32_t accA = 0, accB = 0, allv = kMsb4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < n; ++i) {
+      const int j = n - 1 - i;
+      uint32_t one, valid;
+      classify4(ld(2 + 2 * j), ld(2 + 2 * n + 2 * j), qt, ek, one, valid);
+      allv &= valid;
+      if (i < 8) accA = ((accA >> 1) & kLow4) | (one & kMsb4);
+      else       accB = ((accB >> 1) & kLow4) | (one & kMsb4);
+      if (CODES) st(0, j, tristate4(one, valid));
+    }
+    finish_axis(accA, accB, allv, n, out.h01, out.h23);
+    out.valid = allv;
+  }
+  // row bits: stored LSB first (flipped by the caller at src/3-capture_decode.py:100)
+  {
+    uint32_t accA = 0, accB = 0, allv = kMsb4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < n; ++i) {
+      uint32_t one, valid;
+      classify4(ld(3 + 2 * i), ld(3 + 2 * n + 2 * i), qt, ek, one, valid);
+      allv &= valid;
+      if (i < 8) accA = ((accA >> 1) & kLow4) | (one & kMsb4);
+      else       accB = ((accB >> 1) & kLow4) | (one & kMsb4);
+      if (CODES) st(1, i, tristate4(one, valid));
+    }
+    finish_axis(accA, accB, allv, n, out.v01, out.v23);
+    out.valid &= allv;
+  }
+}
+
 // NB > 0: compile-time bit count (fully unrolled); NB == 0: run-time n.
 // ld(f) returns the 4 bytes of frame f for this quad.  st(axis, bit, tri) stores the
 // tri-state bytes of one bit when CODES (axis 0 = h with bit = j MSB-first index,
@@ -77,7 +123,7 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
   }
 
   QuadThr qt;
-  qt.lo = 0; qt.hi1 = 0; qt.a = 0;
+  qt.lo = 0; qt.hi1 = 0; qt.a = 0; qt.hard = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -89,47 +135,42 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
     qt.lo |= (uint32_t)t.lo << (8 * k);
     qt.hi1 |= (uint32_t)t.hi1 << (8 * k);
     qt.a |= (uint32_t)(t.a << 7) << (8 * k);
+    qt.hard |= (uint32_t)((t.easy ^ 1) << 7) << (8 * k);
   }
   qt.loL = qt.lo & kLow4;
   qt.hi1L = qt.hi1 & kLow4;
   const uint32_t ek = 0x01010101u * (uint32_t)(0x80 - (e + 1));
 
   QuadOut out;
-  // ---- column bits: code bit i (LSB = 0) is reference index j = n-1-i --------------
-  {
-    uint32_t accA = 0, accB = 0, allv = kMsb4;
+  // ---- fast pass (both axes): single-threshold shortcut, 2 byte compares per bit.  If every bit of
+  // the 4 pixels is decided by it the result is final (all bits known => all indices valid).
+  bool need_full = CODES;
+  if (!CODES) {
+    uint32_t hA = 0, hB = 0, vA = 0, vB = 0, undecided = qt.hard;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < n; ++i) {
       const int j = n - 1 - i;
-      uint32_t one, valid;
-      classify4(ld(2 + 2 * j), ld(2 + 2 * n + 2 * j), qt, ek, one, valid);
-      allv &= valid;
-      if (i < 8) accA = ((accA >> 1) & kLow4) | (one & kMsb4);
-      else       accB = ((accB >> 1) & kLow4) | (one & kMsb4);
-      if (CODES) st(0, j, tristate4(one, valid));
+      uint32_t gp, same;
+      classify4_easy(ld(2 + 2 * j), ld(2 + 2 * n + 2 * j), qt, gp, same);
+      undecided |= same;
+      if (i < 8) hA = ((hA >> 1) & kLow4) | (gp & kMsb4);
+      else       hB = ((hB >> 1) & kLow4) | (gp & kMsb4);
+      classify4_easy(ld(3 + 2 * i), ld(3 + 2 * n + 2 * i), qt, gp, same);
+      undecided |= same;
+      if (i < 8) vA = ((vA >> 1) & kLow4) | (gp & kMsb4);
+      else       vB = ((vB >> 1) & kLow4) | (gp & kMsb4);
     }
-    finish_axis(accA, accB, allv, n, out.h01, out.h23);
-    out.valid = allv;
-  }
-  // ---- row bits: stored LSB first (flipped by the caller at src/3-capture_decode.py:100)
-  {
-    uint32_t accA = 0, accB = 0, allv = kMsb4;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < n; ++i) {
-      uint32_t one, valid;
-      classify4(ld(3 + 2 * i), ld(3 + 2 * n + 2 * i), qt, ek, one, valid);
-      allv &= valid;
-      if (i < 8) accA = ((accA >> 1) & kLow4) | (one & kMsb4);
-      else       accB = ((accB >> 1) & kLow4) | (one & kMsb4);
-      if (CODES) st(1, i, tristate4(one, valid));
+    need_full = (undecided & kMsb4) != 0;
+    if (!need_full) {
+      finish_axis(hA, hB, kMsb4, n, out.h01, out.h23);
+      finish_axis(vA, vB, kMsb4, n, out.v01, out.v23);
+      out.valid = kMsb4;
+      return out;
     }
-    finish_axis(accA, accB, allv, n, out.v01, out.v23);
-    out.valid &= allv;
   }
+  full_rules<NB, CODES>(ld, st, n, qt, ek, out);
   return out;
 }
 

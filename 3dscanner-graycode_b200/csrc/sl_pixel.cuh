@@ -120,6 +120,7 @@ struct PixelThr {
   int lo;    // 0..255
   int hi1;   // 0..255
   int a;     // 0/1
+  int easy;  // hi1 <= lo: the single-threshold shortcut of classify4_easy applies
 };
 
 SL_HD PixelThr pixel_thresholds(int white, int black, int lmax, int lmin, int e) {
@@ -139,6 +140,7 @@ SL_HD PixelThr pixel_thresholds(int white, int black, int lmax, int lmin, int e)
   if (lo < 0) lo = 0;
   if (lo > 255) lo = 255;                               // unreachable (Ld <= 255); defensive
   t.lo = lo; t.hi1 = hi1;
+  t.easy = (hi1 <= lo) ? 1 : 0;
   return t;
 }
 
@@ -154,7 +156,19 @@ struct QuadThr {           // thresholds of 4 neighbouring pixels, one per byte 
   uint32_t lo, loL;        // lo and lo & 0x7f
   uint32_t hi1, hi1L;
   uint32_t a;              // 0x80 in lanes where A holds
+  uint32_t hard;           // 0x80 in lanes where hi1 > lo (no shortcut)
 };
+
+// Shortcut for a pixel with hi1 <= lo.  If the normal and inverse samples lie on opposite sides of
+// hi1 the bit is decided by rules 3/4 alone, which outrank rules 1/2 (decode_codes.py:178-182):
+//   p >= hi1 and q < hi1 (<= lo)  =>  rule 4 fires                      => 1
+//   p <  hi1 (<= lo) and q >= hi1 =>  rule 3 fires and rule 4 cannot    => 0
+// gp = (p >= hi1) is then the bit; ~(gp ^ gq) marks bits this test cannot decide (msb flags).
+SL_HD void classify4_easy(uint32_t p, uint32_t q, const QuadThr& t, uint32_t& gp, uint32_t& same) {
+  gp = ge4(p, p | kMsb4, t.hi1, t.hi1L);
+  const uint32_t gq = ge4(q, q | kMsb4, t.hi1, t.hi1L);
+  same = ~(gp ^ gq);
+}
 
 // Classify one bit of 4 pixels.  p = normal pattern bytes, q = inverse pattern bytes.
 // ek = per-lane constant (0x80 - (e+1)) replicated, requires 0 <= e <= 127.
