@@ -1,6 +1,7 @@
 // Stage 1: fused Gray-code decode kernels (sm_100a).
 //
-// K1  decode_tma_kernel     persistent, one CTA per SM.  A producer thread streams [F x 1024 px]
+// K1  decode_tma_kernel     persistent, one CTA per SM (1 producer + 16 consumer warps that claim
+//                           128-px sub-tiles dynamically).  The producer thread streams [F x 1024 px]
 //                           tiles into a ring of shared-memory stages, ONE TMA tensor load per
 //                           tile (cp.async.bulk.tensor.3d + mbarrier complete_tx; the stack is
 //                           described as a (pixels/4 x F x B) uint32 tensor); consumer warps read them as
@@ -19,9 +20,8 @@ namespace sl {
 
 // ------------------------------------------------------------------ K1 configuration
 constexpr int kTilePx = 1024;                 // pixels per stage row (bytes per frame per stage)
-constexpr int kGroups = 2;                    // consumer groups, alternate tiles
-constexpr int kWarpsPerGroup = kTilePx / 4 / 32;   // 8 warps * 32 lanes * 4 px = 1024 px
-constexpr int kConsumerWarps = kGroups * kWarpsPerGroup;
+constexpr int kSubTiles = kTilePx / 128;      // a warp handles 128 px (32 lanes * 4 px) at a time
+constexpr int kConsumerWarps = 16;
 constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;   // + 1 producer warp
 constexpr int kMaxStages = 4;
 constexpr int kSmemBudget = 227 * 1024;
@@ -51,14 +51,16 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __g
   const int stages = a.stages;
   const uint32_t stage_bytes = (uint32_t)F * kTilePx;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-  // bars[0..stages) = full, bars[stages..2*stages) = empty
+  // bars[0..stages) = full, bars[stages..2*stages) = empty; then the sub-tile claim counter
+  unsigned int* next_sub = reinterpret_cast<unsigned int*>(bars + 2 * stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[stages + s]), kWarpsPerGroup);
+      mbar_init(smem_u32(&bars[stages + s]), kSubTiles);
     }
+    *next_sub = 0;
     mbar_init_fence();
   }
   __syncthreads();
@@ -84,11 +86,18 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __g
   }
 
   // -------------------------------------------------------------- consumers
-  const int group = warp / kWarpsPerGroup;
-  const int off = ((warp - group * kWarpsPerGroup) * 32 + lane) * 4;   // pixel offset in tile
-  long long it = group;
-  for (long long t = (long long)blockIdx.x + (long long)group * gridDim.x; t < a.total_tiles;
-       t += (long long)kGroups * gridDim.x, it += kGroups) {
+  // All consumer warps draw 128-pixel sub-tiles from one counter, in ring order.  A warp that hits the
+  // slow path (full rule evaluation) therefore delays nobody: the others keep claiming work up to
+  // `stages - 1` tiles ahead of it.
+  const int off_lane = lane * 4;
+  for (;;) {
+    unsigned int sub = 0;
+    if (lane == 0) sub = atomicAdd(next_sub, 1u);
+    sub = __shfl_sync(0xffffffffu, sub, 0);
+    const long long it = sub / kSubTiles;
+    const int part = (int)(sub % kSubTiles);
+    const long long t = (long long)blockIdx.x + it * gridDim.x;
+    if (t >= a.total_tiles) break;
     const int s = (int)(it % stages);
     const uint32_t ph = (uint32_t)((it / stages) & 1);
     mbar_wait(smem_u32(&bars[s]), ph);
@@ -97,6 +106,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __g
     const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
     const long long rem = a.npix4 - px0;
     const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
+    const int off = part * 128 + off_lane;                                 // pixel offset in tile
     uint32_t nib = 0;
     if (off < cnt) {
       const uint32_t* base = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + (off >> 2);
@@ -328,11 +338,10 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     const size_t stage_bytes = (size_t)F * kTilePx;
     int stages = (int)((kSmemBudget - 256) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
-    stages -= stages % kGroups;
-    if (stages < kGroups) { tma_px = 0; }
+    if (stages < 2) { tma_px = 0; }
     else {
       a.stages = stages;
-      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16;
       const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
       CUtensorMap tmap;
       int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch);
