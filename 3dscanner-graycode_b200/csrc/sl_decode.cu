@@ -21,7 +21,7 @@ namespace sl {
 // ------------------------------------------------------------------ K1 configuration
 constexpr int kTilePx = 1024;                 // pixels per stage row (bytes per frame per stage)
 constexpr int kSubTiles = kTilePx / 128;      // a warp handles 128 px (32 lanes * 4 px) at a time
-constexpr int kConsumerWarps = 24;
+constexpr int kConsumerWarps = 16;
 constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;   // + 1 producer warp
 constexpr int kMaxStages = 4;
 constexpr int kSmemBudget = 227 * 1024;
