@@ -165,7 +165,6 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
       undecided |= same;
       if (i < 8) vA = ((vA >> 1) & kLow4) | (gp & kMsb4);
       else       vB = ((vB >> 1) & kLow4) | (gp & kMsb4);
-      if ((i & 3) == 3 && (undecided & kMsb4) != 0) break;      // no point finishing the shortcut
     }
     need_full = (undecided & kMsb4) != 0;
     if (!need_full) {
