@@ -19,11 +19,20 @@
 namespace sl {
 
 // ------------------------------------------------------------------ K1 configuration
-constexpr int kTilePx = 1024;                 // pixels per stage row (bytes per frame per stage)
+#ifndef SL_TILE_PX
+#define SL_TILE_PX 1024
+#endif
+#ifndef SL_CONSUMER_WARPS
+#define SL_CONSUMER_WARPS 16
+#endif
+#ifndef SL_MAX_STAGES
+#define SL_MAX_STAGES 4
+#endif
+constexpr int kTilePx = SL_TILE_PX;           // pixels per stage row (bytes per frame per stage)
 constexpr int kSubTiles = kTilePx / 128;      // a warp handles 128 px (32 lanes * 4 px) at a time
-constexpr int kConsumerWarps = 16;
+constexpr int kConsumerWarps = SL_CONSUMER_WARPS;
 constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;   // + 1 producer warp
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = SL_MAX_STAGES;
 constexpr int kSmemBudget = 227 * 1024;
 
 struct DecodeArgs {

@@ -68,9 +68,6 @@ void full_rules(Load ld, StoreCode st, int n, const QuadThr& qt, uint32_t ek, Qu
       if (i < 8) accA = ((accA >> 1) & kLow4) | (one & kMsb4);
       else       accB = ((accB >> 1) & kLow4) | (one & kMsb4);
       if (CODES) st(0, j, tristate4(one, valid));
-      // Only the indices are wanted: once each of the 4 pixels has a -1 bit on this axis its index is
-      // -1 whatever the remaining bits are (decode_codes.py:225-226) -- typical for shadow / noise.
-      if (!CODES && (allv & kMsb4) == 0) break;
     }
     finish_axis(accA, accB, allv, n, out.h01, out.h23);
     out.valid = allv;
@@ -88,7 +85,6 @@ void full_rules(Load ld, StoreCode st, int n, const QuadThr& qt, uint32_t ek, Qu
       if (i < 8) accA = ((accA >> 1) & kLow4) | (one & kMsb4);
       else       accB = ((accB >> 1) & kLow4) | (one & kMsb4);
       if (CODES) st(1, i, tristate4(one, valid));
-      if (!CODES && (allv & kMsb4) == 0) break;
     }
     finish_axis(accA, accB, allv, n, out.v01, out.v23);
     out.valid &= allv;

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libslb200.so")
+# SLB200_LIB selects another build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("SLB200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libslb200.so")
 
 SL_PREC_FP32 = 0
 SL_PREC_FP64 = 1
