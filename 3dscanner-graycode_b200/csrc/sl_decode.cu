@@ -20,13 +20,13 @@ namespace sl {
 
 // ------------------------------------------------------------------ K1 configuration
 #ifndef SL_TILE_PX
-#define SL_TILE_PX 1024
+#define SL_TILE_PX 512
 #endif
 #ifndef SL_CONSUMER_WARPS
 #define SL_CONSUMER_WARPS 16
 #endif
 #ifndef SL_MAX_STAGES
-#define SL_MAX_STAGES 4
+#define SL_MAX_STAGES 8
 #endif
 constexpr int kTilePx = SL_TILE_PX;           // pixels per stage row (bytes per frame per stage)
 constexpr int kSubTiles = kTilePx / 128;      // a warp handles 128 px (32 lanes * 4 px) at a time
