@@ -40,7 +40,8 @@ N_FRAMES = 4 * N_BITS + 2
 MPX = CAM_SIZE[0] * CAM_SIZE[1] / 1e6
 METRIC = "Mpx/s decoded+triangulated"
 WORKLOAD = "config[1]: single 1920x1080 camera scan of a 1920x1080 projector Gray sequence (11+11 bits + inverses + white/black)"
-RING = 8          # resident scans per rank: 8 x 95.4 MB = 763 MB > 126 MB L2
+RING = 9          # resident scans per rank: 9 x 95.4 MB = 859 MB > 126 MB L2
+STREAMS = 3       # independent scans are pipelined over 3 CUDA streams (own buffers each)
 
 
 def load_peaks():
@@ -228,28 +229,54 @@ def run_gpu(args):
         fr, wh = synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=rank * RING + i, device=dev, patterns=pats, calib=calib)
         ring_frames.append(fr); ring_white.append(wh)
     del pats
-    bufs = CloudBuffers.allocate(1, H, W, dev)
+    S = max(1, min(args.streams, RING))
+    bufsets = [CloudBuffers.allocate(1, H, W, dev) for _ in range(S)]
+    bufs = bufsets[0]
     tables = None if args.lens == "iterate" else slb200.LensTables(calib, CAM_SIZE, dev)   # once per calibration
     torch.cuda.synchronize()
 
-    def step(i):
+    def step(i, k):
         slb200.scan_to_cloud(ring_frames[i % RING], ring_white[i % RING], calib, precision="fp32",
-                             buffers=bufs, calib_struct=cstruct, tables=tables)
+                             buffers=bufsets[k], calib_struct=cstruct, tables=tables)
 
-    # one CUDA graph per ring slot: the 5 launches of a step replay without host launch latency
+    # One CUDA graph per ring slot (the 4 launches of a step replay without host launch latency); slot i
+    # always runs on stream i % S with that stream's buffers, so consecutive scans overlap: the small
+    # compaction / emit kernels of one scan run beside the decode of the next.
     before = slb200.launch_count()
-    step(0)
+    step(0, 0)
     kernels_per_step = slb200.launch_count() - before
     torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
     graphs = []
-    side = torch.cuda.Stream(dev)
-    with torch.cuda.stream(side):
-        for i in range(RING):
+    for i in range(RING):
+        with torch.cuda.stream(streams[i % S]):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                step(i)
+            with torch.cuda.graph(g, stream=streams[i % S]):
+                step(i, i % S)
             graphs.append(g)
     torch.cuda.synchronize()
+    main = torch.cuda.current_stream()
+
+    def replay(graph_list, n):
+        for i in range(n):
+            k = i % RING
+            with torch.cuda.stream(streams[k % S]):
+                graph_list[k].replay()
+
+    def timed(graph_list, n):
+        """n replays bracketed by CUDA events: the start event gates every stream, the end event waits for all."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
+        replay(graph_list, n)
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        e1.record(main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -260,50 +287,50 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY K steps
-    for i in range(Wm):
-        graphs[i % RING].replay()
+    replay(graphs, Wm)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        graphs[i % RING].replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    ms = torch.tensor([timed(graphs, K)], dtype=torch.float64, device=dev)
     barrier()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     valid_pts = int(bufs.counts[1].item())
 
-    # ---- roofline of the dominant kernel (fused decode): decode-only launches, CUDA events on the
-    # launching (current) stream, rotating over the ring
-    h_idx, v_idx = bufs.h_idx, bufs.v_idx
-    kr = max(50, min(K, 400))
-    for i in range(10):
-        slb200.decode_pixels(ring_frames[i % RING], out=(h_idx[0], v_idx[0]))
-    torch.cuda.synchronize()
+    # ---- roofline of the dominant kernel (fused decode): decode-only launches over the same ring, timed
+    # with CUDA events (a) in the configuration the step uses (pipelined over the S streams) and
+    # (b) isolated: back to back on one stream, every launch waiting for the previous one.
+    kr = max(60, min(K, 600))
     dgraphs = []
-    with torch.cuda.stream(side):
-        for i in range(RING):
+    for i in range(RING):
+        with torch.cuda.stream(streams[i % S]):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                slb200.decode_pixels(ring_frames[i], out=(h_idx[0], v_idx[0]))
+            with torch.cuda.graph(g, stream=streams[i % S]):
+                slb200.decode_pixels(ring_frames[i], out=(bufsets[i % S].h_idx[0], bufsets[i % S].v_idx[0]))
             dgraphs.append(g)
     torch.cuda.synchronize()
-    for i in range(5):
-        dgraphs[i % RING].replay()
+    replay(dgraphs, 10)
     torch.cuda.synchronize()
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d0.record()
-    for i in range(kr):
-        dgraphs[i % RING].replay()
-    d1.record()
+    decode_ms = timed(dgraphs, kr) / kr
+    with torch.cuda.stream(streams[0]):
+        solo = []
+        for i in range(RING):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=streams[0]):
+                slb200.decode_pixels(ring_frames[i], out=(bufs.h_idx[0], bufs.v_idx[0]))
+            solo.append(g)
+        for i in range(10):
+            solo[i % RING].replay()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(streams[0])
+        for i in range(kr):
+            solo[i % RING].replay()
+        d1.record(streams[0])
     torch.cuda.synchronize()
-    decode_ms = d0.elapsed_time(d1) / kr
+    decode_solo_ms = d0.elapsed_time(d1) / kr
     peak, peak_src = load_peaks()
     algo_bytes = (N_FRAMES + 4) * W * H                      # F u8 reads + two int16 writes per pixel
     achieved = algo_bytes / (decode_ms * 1e-3) / 1e9
+    achieved_solo = algo_bytes / (decode_solo_ms * 1e-3) / 1e9
 
     # ---- e2e through the host-buffer C-ABI call: pinned host frames in, host cloud out
     e2e = None
@@ -372,12 +399,16 @@ def run_gpu(args):
                                 else "5 Brown-Conrady iterations per valid pixel in the emit kernel"),
                        "parallelism": f"scan-sharded x{world}",
                        "l2": f"inputs rotate over a ring of {RING} resident scans ({RING * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "CUDA graph per scan (decode, strip-prefix, column-scan, emit)"},
+                       "launch": f"CUDA graph per scan (decode, strip-prefix, column-scan, emit); independent scans pipelined over {S} CUDA streams"},
             "scans_per_s": world * K / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": decode_ms * 1e3,
-                         "frac_of_nominal_8000": achieved / 8000.0},
+                         "frac_of_nominal_8000": achieved / 8000.0,
+                         "timing": f"{kr} decode-only launches over the ring, CUDA events, pipelined over {S} streams like the step",
+                         "isolated": {"us_per_launch": decode_solo_ms * 1e3, "achieved": achieved_solo,
+                                      "frac": achieved_solo / peak,
+                                      "timing": "same launches back to back on one stream (includes the launch gap)"}},
             "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "clocks": clocks,
             "gpu_launches": int(K * kernels_per_step),
         }
@@ -394,6 +425,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lens", default="tables", choices=["tables", "iterate"])
+    ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
