@@ -157,6 +157,11 @@ int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* co
   return launch_offsets_from_bitmap(B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
 }
 
+const uint32_t* sl_workspace_col_totals(const void* workspace, int B, int H, int W) {
+  if (!workspace || B < 1 || H < 1 || W < 1) return nullptr;
+  return carve_workspace(const_cast<void*>(workspace), B, H, W).col_tot;
+}
+
 int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, int B,
                   int H, int W, int proj_w, int proj_h, const void* workspace, float* pairs,
                   uint32_t* rgb32, void* stream) {

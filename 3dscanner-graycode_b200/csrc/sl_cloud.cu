@@ -188,6 +188,7 @@ struct CalibDev {
   double T[3], t_len;
   float Tf[3], t_len2f;
   int proj_w, proj_h;
+  int row0;     // first image row of the band being processed (row-band sharding), 0 for whole images
 };
 
 template <class T>
@@ -212,6 +213,7 @@ static CalibDev make_calib(const SlCalib& c) {
   d.t_len = sqrt(s);
   d.t_len2f = (float)s;
   d.proj_w = c.proj_w; d.proj_h = c.proj_h;
+  d.row0 = c.cam_row0;
   return d;
 }
 
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
         col[3] = w2 >> 8;
       }
       if (kTable) {
-        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4);
+        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
         const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
         cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
             const uint8_t* wp = a.white + (g + k) * 3;
             col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);      // triangulate.py:64
           }
-          if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(y0 + r) * a.W + x0 + c4 + k);
+          if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4 + k);
         }
       }
     }
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
       if (!ok[k]) continue;
       float X, Y, Z = 0.f;
       uint32_t wword = col[k];
-      const float u = (float)(x0 + c4 + k), w = (float)(y0 + r);
+      const float u = (float)(x0 + c4 + k), w = (float)(a.cal.row0 + y0 + r);
       if (MODE == kModePairs) {
         X = u; Y = w; Z = (float)hc[k]; wword = __float_as_uint((float)vc[k]);
       } else if (MODE == kModeCloud32) {
@@ -664,7 +666,7 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
                       int proj_w, int proj_h, const void* ws, float* pairs, uint32_t* rgb32, cudaStream_t st) {
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, pairs, rgb32);
   a.cal = CalibDev();
-  a.cal.proj_w = proj_w; a.cal.proj_h = proj_h;
+  a.cal.proj_w = proj_w; a.cal.proj_h = proj_h; a.cal.row0 = 0;
   int rc = emit_configure();
   if (rc) return rc;
   if ((rc = check_emit_size(a))) return rc;

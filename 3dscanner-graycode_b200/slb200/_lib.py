@@ -21,7 +21,7 @@ class SlCalib(C.Structure):
         ("cam_K", C.c_double * 9), ("cam_dist", C.c_double * 8),
         ("proj_K", C.c_double * 9), ("proj_dist", C.c_double * 8),
         ("R", C.c_double * 9), ("T", C.c_double * 3),
-        ("proj_w", C.c_int32), ("proj_h", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("proj_w", C.c_int32), ("proj_h", C.c_int32), ("cam_row0", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "sl_cloud_workspace_bytes": (_sz, [_i, _i, _i]),
     "sl_compact_offsets": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sl_compact_offsets_decoded": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "sl_workspace_col_totals": (_vp, [_vp, _i, _i, _i]),
     "sl_emit_pairs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _vp, _vp, _vp]),
     "sl_emit_cloud": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

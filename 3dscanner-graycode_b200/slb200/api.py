@@ -59,8 +59,9 @@ class Calibration:
                    np.asarray(proj_dist, np.float64), np.asarray(proj_R, np.float64),
                    np.asarray(proj_T, np.float64), (int(proj_size[0]), int(proj_size[1])))
 
-    def struct(self) -> SlCalib:
+    def struct(self, row0: int = 0) -> SlCalib:
         s = SlCalib()
+        s.cam_row0 = int(row0)
 
         def fill(dst, src, n, what):
             a = np.asarray(src, dtype=np.float64).ravel()
@@ -130,11 +131,25 @@ def _stack_dims(frames: torch.Tensor):
     raise ValueError("frames must be (F,H,W) or (B,F,H,W)")
 
 
+def _pitches(frames: torch.Tensor):
+    """(frame_pitch, scan_pitch) in bytes.  Row bands of a resident stack (``stack[:, y0:y1]``) are
+    accepted as they are: rows must be dense, frames / scans may be strided."""
+    b, f, h, w, batched = _stack_dims(frames)
+    st = frames.stride()
+    frame_pitch = st[-3] if f > 1 else h * w
+    scan_pitch = (st[0] if b > 1 else f * frame_pitch) if batched else f * frame_pitch
+    return int(frame_pitch), int(scan_pitch)
+
+
 def _check_stack(frames: torch.Tensor):
     if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8):
         raise TypeError("frames must be a CUDA uint8 tensor (use as_u8_stack)")
-    if not frames.is_contiguous():
-        raise ValueError("frames must be contiguous")
+    b, f, h, w, batched = _stack_dims(frames)
+    st = frames.stride()
+    rows_dense = (st[-1] == 1 or w == 1) and (st[-2] == w or h == 1)
+    fp, sp = _pitches(frames)
+    if not rows_dense or fp < h * w or (batched and b > 1 and sp < f * fp):
+        raise ValueError("frames must be contiguous, or a row band of a contiguous stack")
 
 
 # --------------------------------------------------------------------------- stage 1
@@ -153,7 +168,8 @@ def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[to
     else:
         h_idx, v_idx = out
     with torch.cuda.device(frames.device):
-        check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
+        fp, sp = _pitches(frames)
+        check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
                                  _ptr(h_idx), _ptr(v_idx), None, None, None, _stream()))
     return h_idx, v_idx
 
@@ -172,7 +188,8 @@ def decode_codes(frames: torch.Tensor, eps: float = 1.0):
     h_idx = torch.empty(ishape, dtype=torch.int16, device=dev)
     v_idx = torch.empty(ishape, dtype=torch.int16, device=dev)
     with torch.cuda.device(dev):
-        check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
+        fp, sp = _pitches(frames)
+        check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
                                  _ptr(h_idx), _ptr(v_idx), _ptr(h_codes), _ptr(v_codes), None, _stream()))
     return h_codes, v_codes, h_idx, v_idx
 
@@ -380,6 +397,13 @@ class CloudBuffers:
         return _RgbView(self.cloud)
 
 
+    def column_counts(self) -> torch.Tensor:
+        """Per-column point counts ``(B, W)`` int32 of the last compaction (view into the workspace)."""
+        b, h, w = self.h_idx.shape
+        ptr = lib().sl_workspace_col_totals(_ptr(self.ws), b, h, w)
+        off = int(ptr) - self.ws.data_ptr()
+        return self.ws[off: off + 4 * b * w].view(torch.int32).view(b, w)
+
     @classmethod
     def allocate(cls, b: int, h: int, w: int, device, cap_points: Optional[int] = None) -> "CloudBuffers":
         cap = b * h * w if cap_points is None else int(cap_points)
@@ -408,12 +432,15 @@ class LensTables:
 
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
                   precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
-                  calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None) -> CloudBuffers:
+                  calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None,
+                  row0: int = 0) -> CloudBuffers:
     """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
     decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
 
     ``tables`` (LensTables of the same calibration / sizes) replaces the per-pixel undistortion
     iterations by look-ups of exact precomputed rays; without it the iterations run in the kernel.
+    ``row0``: the stack is the row band ``[row0, row0 + H)`` of a larger capture (row-band sharding);
+    camera coordinates and ray look-ups use absolute rows, ``tables`` must cover the whole image.
 
     Results are in the returned buffers: ``cloud[:counts[B]]`` (XYZRGB records; ``.xyz`` / ``.rgb``
     views) packed scan after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
@@ -429,13 +456,15 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
             raise TypeError("white_rgb must be a contiguous CUDA uint8 tensor")
         if white_rgb.numel() != b * h * w * 3:
             raise ValueError("white_rgb must be ([B,]H,W,3)")
-    s = calib_struct if calib_struct is not None else calib.struct()
-    if tables is not None and (tables.cam_size != (w, h) or tables.proj_size != tuple(calib.proj_size)):
+    s = calib_struct if calib_struct is not None else calib.struct(row0)
+    if tables is not None and (tables.cam_size[0] != w or tables.cam_size[1] < row0 + h
+                               or tables.proj_size != tuple(calib.proj_size)):
         raise ValueError("lens tables were built for another image / panel size")
     L = lib()
     st = _stream()
     with torch.cuda.device(dev):
-        check(L.sl_decode_u8(_ptr(frames), b, f, h, w, h * w, f * h * w, float(eps),
+        fp, sp = _pitches(frames)
+        check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
                              _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, _ptr(buffers.ws), st))
         check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
         check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),

@@ -85,3 +85,29 @@ def merge_row_bands(band_clouds: Sequence[torch.Tensor], band_cols: Sequence[tor
         dst = start[b][col_of_pt] + within
         out[dst] = band_clouds[b][:n]
     return out
+
+
+def scan_to_cloud_row_bands(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib, tables,
+                            bands: Sequence[Tuple[int, int]], precision="fp32", eps: float = 1.0):
+    """One capture cut into row bands, each decoded + triangulated on its own (this is what every rank
+    of a row-band-sharded job does for its band), then merged back into x-major order.
+
+    On a multi-GPU job call it with the single band of this rank and all-gather the per-band results
+    (`gather_clouds` for the records, `all_gather` for the (W,) column counts) before `merge_row_bands`;
+    with a list of bands on one GPU it is the reference implementation of that flow (tests).
+    Returns (merged cloud (N,4), list of per-band clouds, list of per-band column counts).
+    """
+    import slb200
+    clouds, cols = [], []
+    for (y0, y1) in bands:
+        if y1 <= y0:
+            clouds.append(torch.zeros((0, 4), dtype=torch.float32, device=frames.device))
+            cols.append(torch.zeros((frames.shape[-1],), dtype=torch.int64, device=frames.device))
+            continue
+        band = frames[:, y0:y1]
+        white = white_rgb[y0:y1].contiguous() if white_rgb is not None else None
+        bufs = slb200.scan_to_cloud(band, white, calib, precision=precision, eps=eps, tables=tables, row0=y0)
+        n = int(bufs.counts[1])
+        clouds.append(bufs.cloud[:n].clone())
+        cols.append(bufs.column_counts()[0].to(torch.int64).clone())
+    return merge_row_bands(clouds, cols), clouds, cols

@@ -49,7 +49,9 @@ typedef struct SlCalib {
   double T[3];         /* proj_T[:,0] (triangulate.py:86) */
   int32_t proj_w;      /* clamp of decoded indices (triangulate.py:60-61) */
   int32_t proj_h;
-  int32_t reserved[2];
+  int32_t cam_row0;    /* row-band sharding: image row of the first row of the h/v/white buffers passed to
+                          sl_emit_cloud (camera coordinates and cam_rays look-ups use cam_row0 + y); else 0 */
+  int32_t reserved;
 } SlCalib;
 
 const char* sl_last_error(void);
@@ -108,6 +110,10 @@ int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H,
 
 /* Same, for a workspace whose validity bitmap was already written by sl_decode_u8 (same B,H,W). */
 int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream);
+
+/* Per-column point counts left in the workspace by sl_compact_offsets[_decoded]: device u32 [B][W]
+ * (needed to merge the clouds of row bands back into x-major order).  Returns NULL on bad arguments. */
+const uint32_t* sl_workspace_col_totals(const void* workspace, int B, int H, int W);
 
 /* Triangulate.get_cam_proj_pts (triangulate.py:39-71): emits, x-major, one 16-byte record per
  * valid pixel: pairs (N,4) f32 = [x, y, min(proj_w-1,h), min(proj_h-1,v)] (cam_pts | proj_pts) and,

@@ -293,6 +293,26 @@ def test_cloud_ragged_shapes(T, shape):
     np.testing.assert_array_equal(proj_g.cpu().numpy(), proj)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_band_sharding_matches_whole_image(T, world):
+    """Config 3 (one capture split by row bands over `world` GPUs), emulated band by band on one GPU: the
+    merged cloud is bit-identical to the whole-image result, in the reference's x-major order."""
+    import slb200
+    from slb200 import synth
+    from slb200.dist import row_bands, scan_to_cloud_row_bands
+    cam_size, proj_size = (256, 200), (1024, 768)
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    frames, white = synth.render_scan(cam_size, proj_size, seed=8, device="cuda")
+    tables = slb200.LensTables(calib, cam_size, "cuda")
+    for tab in (tables, None):
+        whole = slb200.scan_to_cloud(frames, white, calib, tables=tab)
+        n = int(whole.counts[1])
+        merged, clouds, cols = scan_to_cloud_row_bands(frames, white, calib, tab, row_bands(200, world))
+        assert merged.shape[0] == n == sum(c.shape[0] for c in clouds)
+        assert T.equal(merged.view(T.int32), whole.cloud[:n].view(T.int32))
+        np.testing.assert_array_equal(sum(c.cpu().numpy() for c in cols), whole.column_counts()[0].cpu().numpy())
+
+
 def test_batched_cloud_matches_single(T):
     """Packed batch output == the scans done one by one (order inside a scan, counts, bytes)."""
     import slb200
