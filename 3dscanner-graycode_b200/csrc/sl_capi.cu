@@ -93,10 +93,11 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
   int sms = 0;
   if ((rc = device_gate(&sms))) return rc;
   uint32_t* bitmap = nullptr;
+  unsigned int* ticket = nullptr;
   long long words = 0;
-  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words);
+  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &ticket);
   return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, h_codes, v_codes,
-                       bitmap, words, sms, (cudaStream_t)stream);
+                       bitmap, words, ticket, sms, (cudaStream_t)stream);
 }
 
 int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
@@ -359,9 +360,10 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     if (white_rgb_host)
       SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host + (size_t)i * npix * 3, npix * 3, cudaMemcpyHostToDevice, s.stream));
     long long bm_words = 0;
-    uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words);
+    unsigned int* ticket = nullptr;
+    uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &ticket);
     rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
-                       p->sms, s.stream);
+                       ticket, p->sms, s.stream);
     if (rc) break;
     if (h_idx_host) {
       SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, s.h, npix * 2, cudaMemcpyDeviceToHost, s.stream));
@@ -414,7 +416,8 @@ int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
     auto& u = h_codes_host ? p->slot[0] : s;
     SL_CUDA(cudaMemcpyAsync(u.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, st));
     rc = launch_decode(u.frames, 1, p->F, (long long)npix, npix, stack, eps, u.h, u.v,
-                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, nullptr, 0, p->sms, st);
+                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, nullptr, 0, nullptr,
+                       p->sms, st);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, u.h, npix * 2, cudaMemcpyDeviceToHost, st));
     SL_CUDA(cudaMemcpyAsync(v_idx_host + (size_t)i * npix, u.v, npix * 2, cudaMemcpyDeviceToHost, st));

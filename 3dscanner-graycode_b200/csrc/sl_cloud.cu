@@ -6,7 +6,8 @@
 //   (K1 writes a flat validity bitmap, 1 bit per pixel; K3a builds it from caller-supplied indices)
 //   K3b strip_prefix_kernel  one warp per 32-column strip: 32x32 ballot transposes of the bitmap give
 //                            per-(band, column) counts, prefixed down each column + column totals
-//   K3c colscan_kernel       exclusive scan of the column totals in (scan, x) order -> packed bases
+//   K3c (inside K3b)         the last strip CTA to finish scans the column totals in (scan, x) order
+//                            -> packed bases + per-scan counts (colscan_kernel is the standalone form)
 //   K2  emit_kernel          one warp per 32-row x 16-column tile; compute phase has lane = row, so a
 //                            warp ballot gives the rank inside the band and the warp writes a
 //                            contiguous run of points per column.
@@ -18,6 +19,9 @@
 
 namespace sl {
 
+#ifndef SL_EMIT_UNROLL
+#define SL_EMIT_UNROLL 1
+#endif
 constexpr int kBandRows = 32;       // rows per band = lanes per warp
 constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
 constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
@@ -34,7 +38,8 @@ size_t cloud_workspace_bytes(int B, int H, int W) {
          align_up((size_t)B * bands * W * 4, 256) +                            // band_pre
          align_up((size_t)B * bands * W * 4, 256) +                            // col_bits
          align_up((size_t)B * W * 4, 256) +                                    // col_tot
-         align_up((size_t)B * W * 8, 256);                                     // col_base
+         align_up((size_t)B * W * 8, 256) +                                    // col_base
+         256;                                                                  // ticket of the strip kernel
 }
 
 CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
@@ -51,6 +56,8 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
   c.col_tot = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)B * W * 4, 256);
   c.col_base = reinterpret_cast<long long*>(p);
+  p += align_up((size_t)B * W * 8, 256);
+  c.ticket = reinterpret_cast<unsigned int*>(p);
   return c;
 }
 
@@ -60,7 +67,9 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
 __global__ void __launch_bounds__(256) bitmap_from_idx_kernel(const int16_t* __restrict__ h,
                                                                const int16_t* __restrict__ v, long long npix,
                                                                long long words_per_scan, int B,
-                                                               uint32_t* __restrict__ bitmap) {
+                                                               uint32_t* __restrict__ bitmap,
+                                                               unsigned int* __restrict__ ticket) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0;      // arms the strip kernel's last-CTA election
   const long long padded = (npix + 31) & ~31LL;
   const long long total = padded * B;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -73,7 +82,63 @@ __global__ void __launch_bounds__(256) bitmap_from_idx_kernel(const int16_t* __r
   }
 }
 
-// K3b: one CTA per strip of 32 columns, one warp per band (round-robin).  Lane r fetches the 32
+// Exclusive scan of m uint32 values into int64 by ONE thread block of NT threads, plus per-scan totals
+// (counts[b] = points of scan b, counts[B] = total).
+template <int NT>
+__device__ __forceinline__ void block_scan_columns(const uint32_t* __restrict__ vals, long long* __restrict__ out,
+                                                   long long m, int B, int W, long long* __restrict__ counts) {
+  __shared__ long long warp_sum[32];
+  __shared__ long long carry_s;
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (long long base = 0; base < m; base += NT) {
+    const long long i = base + tid;
+    const long long x = i < m ? (long long)vals[i] : 0;
+    long long inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += y;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = lane < NW ? warp_sum[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sum[lane] = w;     // inclusive over warps
+    }
+    __syncthreads();
+    const long long carry = carry_s;
+    const long long before = carry + (warp ? warp_sum[warp - 1] : 0) + inc - x;
+    if (i < m) out[i] = before;
+    __syncthreads();
+    if (tid == NT - 1) carry_s = carry + warp_sum[NW - 1];
+    __syncthreads();
+  }
+  if (counts) {
+    const long long total = carry_s;
+    for (int b = tid; b < B; b += NT) {
+      const long long lo = out[(long long)b * W];
+      const long long hi = (b + 1 < B) ? out[(long long)(b + 1) * W] : total;
+      counts[b] = hi - lo;
+    }
+    if (tid == 0) counts[B] = total;
+  }
+}
+
+__global__ void __launch_bounds__(1024) colscan_kernel(const uint32_t* __restrict__ vals,
+                                                        long long* __restrict__ out, long long m,
+                                                        int B, int W, long long* __restrict__ counts) {
+  block_scan_columns<1024>(vals, out, m, B, W, counts);
+}
+
+// K3b (+K3c): one CTA per strip of 32 columns, one warp per band (round-robin).  Lane r fetches the 32
 // validity bits of row (band*32 + r) in the strip (funnel shift out of the flat bitmap); 32 ballots
 // transpose the 32x32 bit block so lane c holds the column word of column x0+c, whose popcount is
 // the number of valid pixels of that column in the band.  The counts meet in shared memory, are
@@ -87,7 +152,10 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
                                                                          int bands, int strips,
                                                                          uint32_t* __restrict__ band_pre,
                                                                          uint32_t* __restrict__ col_bits,
-                                                                         uint32_t* __restrict__ col_tot) {
+                                                                         uint32_t* __restrict__ col_tot,
+                                                                         long long* __restrict__ col_base, int B,
+                                                                         long long* __restrict__ counts,
+                                                                         unsigned int* __restrict__ ticket) {
   extern __shared__ uint32_t cnt[];            // [bands][32] counts, then exclusive prefixes
   const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,54 +192,18 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
   if (x < W)
     for (int band = warp; band < bands; band += kStripWarps)
       band_pre[((size_t)b * bands + band) * W + x] = cnt[band * 32 + lane];
-}
 
-// single block: exclusive scan of m uint32 values into int64, plus per-scan totals
-__global__ void __launch_bounds__(1024) colscan_kernel(const uint32_t* __restrict__ vals,
-                                                        long long* __restrict__ out, long long m,
-                                                        int B, int W, long long* __restrict__ counts) {
-  __shared__ long long warp_sum[32];
-  __shared__ long long carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  // K3c folded in: the CTA that finishes last scans the column totals of the whole batch
+  // (threadfence + ticket: every other CTA's col_tot is visible to it) and re-arms the ticket.
+  __shared__ bool last;
+  __threadfence();
   __syncthreads();
-  for (long long base = 0; base < m; base += 1024) {
-    const long long i = base + tid;
-    const long long x = i < m ? (long long)vals[i] : 0;
-    long long inc = x;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const long long y = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += y;
-    }
-    if (lane == 31) warp_sum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      long long w = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      warp_sum[lane] = w;     // inclusive over warps
-    }
-    __syncthreads();
-    const long long carry = carry_s;
-    const long long before = carry + (warp ? warp_sum[warp - 1] : 0) + inc - x;
-    if (i < m) out[i] = before;
-    __syncthreads();
-    if (tid == 1023) carry_s = carry + warp_sum[31];
-    __syncthreads();
-  }
-  if (counts) {
-    const long long total = carry_s;
-    for (int b = tid; b < B; b += 1024) {
-      const long long lo = out[(long long)b * W];
-      const long long hi = (b + 1 < B) ? out[(long long)(b + 1) * W] : total;
-      counts[b] = hi - lo;
-    }
-    if (tid == 0) counts[B] = total;
-  }
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  block_scan_columns<kStripWarps * 32>(col_tot, col_base, (long long)B * W, B, W, counts);
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
 // ------------------------------------------------------------------ camera models
@@ -418,7 +450,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   uint32_t cb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
-#pragma unroll 1
+#pragma unroll SL_EMIT_UNROLL
   for (int it = 0; it < 4; ++it) {
     const int r = rr + 8 * it;
     const uint32_t below = (1u << r) - 1u;
@@ -603,9 +635,8 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   (void)warps;
   if (c.bands > kMaxBands) { set_error("image too tall (%d rows)", H); return kErrBadArg; }
   strip_prefix_kernel<<<B * strips, kStripWarps * 32, (size_t)c.bands * 32 * sizeof(uint32_t), st>>>(
-      c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot);
-  count_launch();
-  colscan_kernel<<<1, 1024, 0, st>>>(c.col_tot, c.col_base, (long long)B * W, B, W, counts);
+      c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot, c.col_base, B, counts,
+      c.ticket);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
@@ -616,14 +647,15 @@ int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int
   const CloudWorkspace c = carve_workspace(ws, B, H, W);
   const long long npix = (long long)H * W;
   const long long padded = ((npix + 31) & ~31LL) * B;
-  bitmap_from_idx_kernel<<<grid_for(padded, 256, 148 * 16), 256, 0, st>>>(h, v, npix, c.bitmap_words, B, c.bitmap);
+  bitmap_from_idx_kernel<<<grid_for(padded, 256, 148 * 16), 256, 0, st>>>(h, v, npix, c.bitmap_words, B, c.bitmap, c.ticket);
   count_launch();
   return launch_offsets_from_bitmap(B, H, W, ws, counts, st);
 }
 
-uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan) {
+uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned int** ticket) {
   const CloudWorkspace c = carve_workspace(ws, B, H, W);
   *words_per_scan = c.bitmap_words;
+  *ticket = c.ticket;
   return c.bitmap;
 }
 

@@ -44,6 +44,7 @@ struct DecodeArgs {
   int8_t* v_codes;
   uint32_t* bitmap;      // nullable: flat validity bits, scan b at bitmap + b*bitmap_words
   long long bitmap_words;
+  unsigned int* ticket;  // nullable: compaction workspace ticket, zeroed here (see strip_prefix_kernel)
   long long npix;        // pixels per scan
   long long npix4;       // npix rounded down to a multiple of 4 (part handled by this kernel)
   long long total_tiles; // B * tiles_per_scan
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && a.ticket) *a.ticket = 0;
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
       mbar_init(smem_u32(&bars[stages + s]), kSubTiles);
@@ -156,6 +158,7 @@ struct GenericArgs {
   double eps;
   uint32_t* bitmap;       // nullable: validity bits are OR-ed in (the launcher zeroes the words first)
   long long bitmap_words;
+  unsigned int* ticket;   // nullable, zeroed (see DecodeArgs)
   const double* ld_in;    // nullable: caller-supplied L_d / L_g (get_is_lit, decode_codes.py:125)
   const double* lg_in;
   double* ld_out;         // nullable: get_direct_indirect outputs (decode_codes.py:90-122)
@@ -174,6 +177,7 @@ __device__ __forceinline__ int classify_fp64(double p, double q, double ld, doub
 }
 
 __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericArgs a) {
+  if (a.ticket && blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0;
   const long long span = a.px_end - a.px_begin;
   const long long total = span * a.B;
   const int n = a.n;
@@ -321,8 +325,8 @@ static int dispatch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, 
 
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, int num_sms,
-                  cudaStream_t st) {
+                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
+                  int num_sms, cudaStream_t st) {
   const int n = (F - 2) / 4;
   const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
   const bool aligned = ((uintptr_t)frames % 16 == 0) && (frame_pitch % 16 == 0) &&
@@ -339,7 +343,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
-    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket;
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
@@ -364,7 +368,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = scan_pitch;
     g.h_idx = h_idx; g.v_idx = v_idx; g.h_codes = h_codes; g.v_codes = v_codes;
     g.npix = npix; g.px_begin = tma_px; g.px_end = npix; g.n = n; g.B = B; g.eps = eps;
-    g.bitmap = valid_bitmap; g.bitmap_words = bitmap_words;
+    g.bitmap = valid_bitmap; g.bitmap_words = bitmap_words; g.ticket = ticket;
     g.ld_in = g.lg_in = nullptr; g.ld_out = g.lg_out = nullptr;
     const long long total = (npix - tma_px) * B;
     long long blocks = (total + 255) / 256;
@@ -385,7 +389,7 @@ int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t fra
   g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = 0;
   g.h_idx = nullptr; g.v_idx = nullptr; g.h_codes = h_codes; g.v_codes = v_codes;
   g.npix = npix; g.px_begin = 0; g.px_end = npix; g.n = (F - 2) / 4; g.B = 1; g.eps = eps;
-  g.bitmap = nullptr; g.bitmap_words = 0;
+  g.bitmap = nullptr; g.bitmap_words = 0; g.ticket = nullptr;
   g.ld_in = ld_in; g.lg_in = lg_in; g.ld_out = ld_out; g.lg_out = lg_out;
   long long blocks = (npix + 255) / 256;
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
