@@ -22,6 +22,7 @@ namespace sl {
 #ifndef SL_EMIT_UNROLL
 #define SL_EMIT_UNROLL 1
 #endif
+constexpr int kEmitUnroll = SL_EMIT_UNROLL;
 constexpr int kBandRows = 32;       // rows per band = lanes per warp
 constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
 constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   uint32_t cb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
-#pragma unroll SL_EMIT_UNROLL
+#pragma unroll kEmitUnroll
   for (int it = 0; it < 4; ++it) {
     const int r = rr + 8 * it;
     const uint32_t below = (1u << r) - 1u;
