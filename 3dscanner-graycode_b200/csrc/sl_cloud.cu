@@ -26,7 +26,10 @@ constexpr int kEmitUnroll = SL_EMIT_UNROLL;
 constexpr int kBandRows = 32;       // rows per band = lanes per warp
 constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
 constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
-constexpr int kEmitWarps = 4;
+#ifndef SL_EMIT_WARPS
+#define SL_EMIT_WARPS 4
+#endif
+constexpr int kEmitWarps = SL_EMIT_WARPS;
 
 // ------------------------------------------------------------------ workspace
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

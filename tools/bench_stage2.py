@@ -1,0 +1,39 @@
+"""Stage-2-only timing (offsets + emit) on decoded 1080p scans; honours SLB200_LIB."""
+import argparse, ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3dscanner-graycode_b200")); sys.path.insert(0, ROOT)
+import torch, slb200
+from slb200 import synth
+from slb200.api import _ptr, _stream, check, lib, CloudBuffers
+ap = argparse.ArgumentParser(); ap.add_argument("--iters", type=int, default=300); ap.add_argument("--ring", type=int, default=6)
+a = ap.parse_args()
+cam, proj = (1920, 1080), (1920, 1080); dev = torch.device("cuda", 0)
+calib = synth.synthetic_calibration(cam, proj); pats = synth.pattern_stack(proj, dev)
+tables = slb200.LensTables(calib, cam, dev)
+sets = []
+for i in range(a.ring):
+    fr, wh = synth.render_scan(cam, proj, seed=i, device=dev, patterns=pats, calib=calib)
+    b = CloudBuffers.allocate(1, cam[1], cam[0], dev)
+    slb200.scan_to_cloud(fr, wh, calib, buffers=b, tables=tables)       # leaves h/v + bitmap in b
+    sets.append((b, wh)); del fr
+torch.cuda.synchronize()
+s = calib.struct(); L = lib(); H, W = cam[1], cam[0]
+def offsets(b): check(L.sl_compact_offsets_decoded(1, H, W, _ptr(b.ws), _ptr(b.counts), _stream()))
+def emit(b, wh): check(L.sl_emit_cloud(_ptr(b.h_idx), _ptr(b.v_idx), _ptr(wh), C.byref(s), 0, _ptr(tables.cam), _ptr(tables.proj), 1, H, W, _ptr(b.ws), _ptr(b.cloud), _stream()))
+def timeit(fn, name):
+    side = torch.cuda.Stream(dev); graphs = []
+    with torch.cuda.stream(side):
+        for (b, wh) in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side): fn(b, wh)
+            graphs.append(g)
+        for i in range(10): graphs[i % len(graphs)].replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for i in range(a.iters): graphs[i % len(graphs)].replay()
+        e1.record(side)
+    torch.cuda.synchronize()
+    print(f"{os.environ.get('SLB200_LIB','default').split('/')[-1]:45s} {name:14s} {e0.elapsed_time(e1) / a.iters * 1e3:8.2f} us")
+timeit(lambda b, wh: offsets(b), "offsets")
+timeit(lambda b, wh: emit(b, wh), "emit")
+timeit(lambda b, wh: (offsets(b), emit(b, wh)), "offsets+emit")
