@@ -22,7 +22,6 @@ namespace sl {
 #ifndef SL_EMIT_UNROLL
 #define SL_EMIT_UNROLL 1
 #endif
-constexpr int kEmitUnroll = SL_EMIT_UNROLL;
 constexpr int kBandRows = 32;       // rows per band = lanes per warp
 constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
 constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
@@ -451,85 +450,111 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
 
   // ---- phase A
   const int rr = lane >> 2, c4 = (lane & 3) * 4;
-  uint32_t cb[4];
+  const int rows = min(kBandRows, a.H - y0);
+  // result of one pixel -> its slot in the column's run
+  auto store_point = [&](int k, int r, uint32_t bits, int hc, int vc, float2 cray, float2 pray, uint32_t colour) {
+    float X, Y, Z = 0.f;
+    uint32_t wword = colour;
+    const float u = (float)(x0 + c4 + k), w = (float)(a.cal.row0 + y0 + r);
+    if (MODE == kModePairs) {
+      X = u; Y = w; Z = (float)hc; wword = __float_as_uint((float)vc);
+    } else if (MODE == kModeCloud32) {
+      triangulate_fp32(u, w, (float)hc, (float)vc, a.cal, X, Y, Z);
+    } else if (MODE == kModeCloud64) {
+      double dx, dy, dz;
+      triangulate_fp64(u, w, (float)hc, (float)vc, a.cal, dx, dy, dz);
+      X = (float)dx; Y = (float)dy; Z = (float)dz;
+    } else if (MODE == kModeTable32) {
+      rays_to_point_fp32(cray.x, cray.y, pray.x, pray.y, a.cal, X, Y, Z);
+    } else {
+      double dx, dy, dz;
+      rays_to_point_fp64(cray.x, cray.y, pray.x, pray.y, a.cal, dx, dy, dz);
+      X = (float)dx; Y = (float)dy; Z = (float)dz;
+    }
+    const int rank = __popc(bits & ((1u << r) - 1u));
+    tile.rec[(c4 + k) * kRunPitch + rank] = make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), wword);
+    if (MODE == kModePairs) tile.aux[(c4 + k) * kRunPitch + rank] = colour;
+  };
+
+  if (vec) {
+    // (1) every load that depends on nothing, for all 4 row groups of the tile, back to back
+    uint2 h2[4], v2[4];
+    uint32_t w0[4], w1[4], w2[4];
+    float4 r0[4], r1[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
-#pragma unroll kEmitUnroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = rr + 8 * it;
-    const uint32_t below = (1u << r) - 1u;
-    bool ok[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ok[k] = (cb[k] >> r) & 1u;            // == (h != -1 && v != -1), triangulate.py:56
-    if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
-    int hq[4], vq[4];
-    uint32_t col[4] = {0, 0, 0, 0};
-    float2 cray[4];
-    const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
-    if (vec) {
-      const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(a.h + g));
-      const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(a.v + g));
-      hq[0] = h2.x & 0xffff; hq[1] = h2.x >> 16; hq[2] = h2.y & 0xffff; hq[3] = h2.y >> 16;
-      vq[0] = v2.x & 0xffff; vq[1] = v2.x >> 16; vq[2] = v2.y & 0xffff; vq[3] = v2.y >> 16;
+    for (int it = 0; it < 4; ++it) {
+      const int r = min(rr + 8 * it, rows - 1);               // rows past the image repeat the last one (never valid)
+      const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+      h2[it] = __ldg(reinterpret_cast<const uint2*>(a.h + g));
+      v2[it] = __ldg(reinterpret_cast<const uint2*>(a.v + g));
       if (has_rgb) {
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);
-        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);   // 12 bytes = 4 RGB pixels
-        col[0] = w0 & 0xffffffu;
-        col[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
-        col[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
-        col[3] = w2 >> 8;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);      // 12 bytes = 4 RGB pixels
+        w0[it] = __ldg(wp); w1[it] = __ldg(wp + 1); w2[it] = __ldg(wp + 2);
+      } else {
+        w0[it] = w1[it] = w2[it] = 0;
       }
       if (kTable) {
         const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
-        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-        cray[0] = make_float2(r0.x, r0.y); cray[1] = make_float2(r0.z, r0.w);
-        cray[2] = make_float2(r1.x, r1.y); cray[3] = make_float2(r1.z, r1.w);
+        r0[it] = __ldg(rp); r1[it] = __ldg(rp + 1);
       }
-    } else {
+    }
+    uint32_t cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
+    // (2) the 16 projector-ray gathers (neighbouring pixels hit neighbouring table entries)
+    float2 pray[4][4];
+    int hc[4][4], vc[4][4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = rr + 8 * it;
+      const uint32_t hw[2] = {h2[it].x, h2[it].y}, vw[2] = {v2[it].x, v2[it].y};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        hq[k] = vq[k] = 0;
-        if (ok[k]) {                                    // ok implies the pixel is inside the image
-          hq[k] = (uint16_t)a.h[g + k]; vq[k] = (uint16_t)a.v[g + k];
-          if (has_rgb) {
-            const uint8_t* wp = a.white + (g + k) * 3;
-            col[k] = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);      // triangulate.py:64
-          }
-          if (kTable) cray[k] = __ldg(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4 + k);
+        const int hq = (hw[k >> 1] >> (16 * (k & 1))) & 0xffff, vq = (vw[k >> 1] >> (16 * (k & 1))) & 0xffff;
+        hc[it][k] = min(a.cal.proj_w - 1, hq); vc[it][k] = min(a.cal.proj_h - 1, vq);     // triangulate.py:60-61
+        pray[it][k] = make_float2(0.f, 0.f);
+        if (kTable && ((cb[k] >> r) & 1u))                                                // triangulate.py:56
+          pray[it][k] = __ldg(a.proj_rays + (size_t)vc[it][k] * a.cal.proj_w + hc[it][k]);
+      }
+    }
+    // (3) arithmetic + store
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = rr + 8 * it;
+      const uint32_t col[4] = {w0[it] & 0xffffffu, (w0[it] >> 24) | ((w1[it] & 0xffffu) << 8),
+                               (w1[it] >> 16) | ((w2[it] & 0xffu) << 16), w2[it] >> 8};   // triangulate.py:64
+      const float2 cray[4] = {make_float2(r0[it].x, r0[it].y), make_float2(r0[it].z, r0[it].w),
+                              make_float2(r1[it].x, r1[it].y), make_float2(r1[it].z, r1[it].w)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((cb[k] >> r) & 1u) store_point(k, r, cb[k], hc[it][k], vc[it][k], cray[k], pray[it][k], col[k]);
+    }
+  } else {
+    // ragged tiles / row pitches that are not a multiple of 4 pixels: scalar loads, one row group at a time
+    uint32_t cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const int r = rr + 8 * it;
+      const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!((cb[k] >> r) & 1u)) continue;             // a set bit implies the pixel is inside the image
+        const int hq = (uint16_t)a.h[g + k], vq = (uint16_t)a.v[g + k];
+        uint32_t colour = 0;
+        if (has_rgb) {
+          const uint8_t* wp = a.white + (g + k) * 3;
+          colour = (uint32_t)wp[0] | ((uint32_t)wp[1] << 8) | ((uint32_t)wp[2] << 16);
         }
+        const int hcl = min(a.cal.proj_w - 1, hq), vcl = min(a.cal.proj_h - 1, vq);
+        float2 cray = make_float2(0.f, 0.f), pray = cray;
+        if (kTable) {
+          cray = __ldg(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4 + k);
+          pray = __ldg(a.proj_rays + (size_t)vcl * a.cal.proj_w + hcl);
+        }
+        store_point(k, r, cb[k], hcl, vcl, cray, pray, colour);
       }
-    }
-    float2 pray[4];
-    int hc[4], vc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      hc[k] = min(a.cal.proj_w - 1, hq[k]); vc[k] = min(a.cal.proj_h - 1, vq[k]);     // triangulate.py:60-61
-      if (kTable && ok[k]) pray[k] = __ldg(a.proj_rays + (size_t)vc[k] * a.cal.proj_w + hc[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!ok[k]) continue;
-      float X, Y, Z = 0.f;
-      uint32_t wword = col[k];
-      const float u = (float)(x0 + c4 + k), w = (float)(a.cal.row0 + y0 + r);
-      if (MODE == kModePairs) {
-        X = u; Y = w; Z = (float)hc[k]; wword = __float_as_uint((float)vc[k]);
-      } else if (MODE == kModeCloud32) {
-        triangulate_fp32(u, w, (float)hc[k], (float)vc[k], a.cal, X, Y, Z);
-      } else if (MODE == kModeCloud64) {
-        double dx, dy, dz;
-        triangulate_fp64(u, w, (float)hc[k], (float)vc[k], a.cal, dx, dy, dz);
-        X = (float)dx; Y = (float)dy; Z = (float)dz;
-      } else if (MODE == kModeTable32) {
-        rays_to_point_fp32(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, X, Y, Z);
-      } else {
-        double dx, dy, dz;
-        rays_to_point_fp64(cray[k].x, cray[k].y, pray[k].x, pray[k].y, a.cal, dx, dy, dz);
-        X = (float)dx; Y = (float)dy; Z = (float)dz;
-      }
-      const int rank = __popc(cb[k] & below);
-      tile.rec[(c4 + k) * kRunPitch + rank] = make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), wword);
-      if (MODE == kModePairs) tile.aux[(c4 + k) * kRunPitch + rank] = col[k];
     }
   }
   __syncwarp();
