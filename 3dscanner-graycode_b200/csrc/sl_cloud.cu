@@ -199,12 +199,14 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
   // K3c folded in: the CTA that finishes last scans the column totals of the whole batch
   // (threadfence + ticket: every other CTA's col_tot is visible to it) and re-arms the ticket.
   __shared__ bool last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();                      // this CTA's col_tot writes happen-before thread 0's fence
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (last) __threadfence();          // acquire side: the other CTAs' col_tot
+  }
   __syncthreads();
   if (!last) return;
-  __threadfence();
   block_scan_columns<kStripWarps * 32>(col_tot, col_base, (long long)B * W, B, W, counts);
   if (threadIdx.x == 0) *ticket = 0;
 }
@@ -476,6 +478,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
     if (MODE == kModePairs) tile.aux[(c4 + k) * kRunPitch + rank] = colour;
   };
 
+  // L2 policy: the lens tables are re-read by every scan (keep them: evict_last); indices, colours and
+  // the cloud stream through once (evict_first)
+  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
   if (vec) {
     // (1) every load that depends on nothing, for all 4 row groups of the tile, back to back
     uint2 h2[4], v2[4];
@@ -485,17 +490,17 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
     for (int it = 0; it < 4; ++it) {
       const int r = min(rr + 8 * it, rows - 1);               // rows past the image repeat the last one (never valid)
       const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
-      h2[it] = __ldg(reinterpret_cast<const uint2*>(a.h + g));
-      v2[it] = __ldg(reinterpret_cast<const uint2*>(a.v + g));
+      h2[it] = ldg_u2_hint(a.h + g, stream);
+      v2[it] = ldg_u2_hint(a.v + g, stream);
       if (has_rgb) {
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);      // 12 bytes = 4 RGB pixels
-        w0[it] = __ldg(wp); w1[it] = __ldg(wp + 1); w2[it] = __ldg(wp + 2);
+        w0[it] = ldg_u32_hint(wp, stream); w1[it] = ldg_u32_hint(wp + 1, stream); w2[it] = ldg_u32_hint(wp + 2, stream);
       } else {
         w0[it] = w1[it] = w2[it] = 0;
       }
       if (kTable) {
         const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
-        r0[it] = __ldg(rp); r1[it] = __ldg(rp + 1);
+        r0[it] = ldg_f4_hint(rp, keep); r1[it] = ldg_f4_hint(rp + 1, keep);
       }
     }
     uint32_t cb[4];
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
         hc[it][k] = min(a.cal.proj_w - 1, hq); vc[it][k] = min(a.cal.proj_h - 1, vq);     // triangulate.py:60-61
         pray[it][k] = make_float2(0.f, 0.f);
         if (kTable && ((cb[k] >> r) & 1u))                                                // triangulate.py:56
-          pray[it][k] = __ldg(a.proj_rays + (size_t)vc[it][k] * a.cal.proj_w + hc[it][k]);
+          pray[it][k] = ldg_f2_hint(a.proj_rays + (size_t)vc[it][k] * a.cal.proj_w + hc[it][k], keep);
       }
     }
     // (3) arithmetic + store
@@ -565,7 +570,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
     const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, cidx));
     const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
     if (lane < cnt) {
-      out[base + lane] = tile.rec[cidx * kRunPitch + lane];
+      stg_u4_hint(out + base + lane, tile.rec[cidx * kRunPitch + lane], stream);
       if (MODE == kModePairs && a.out_rgb32) a.out_rgb32[base + lane] = tile.aux[cidx * kRunPitch + lane];
     }
   }

@@ -72,6 +72,38 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// read-only loads / stores with an explicit L2 eviction policy
+__device__ __forceinline__ float4 ldg_f4_hint(const void* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_f2_hint(const void* p, uint64_t pol) {
+  float2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_u2_hint(const void* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const void* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void stg_u4_hint(void* p, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // TMA tiled load (SASS: UTMALDG): one instruction moves a whole [rows][cols] box described by a
 // CUtensorMap into shared memory; out-of-bounds elements are zero-filled and still counted in
 // the mbarrier transaction bytes.
