@@ -119,7 +119,27 @@ def _oracle_band(args):
     return int(pts.shape[1])
 
 
-def cpu_baseline_single_core(frames_np, white_np, calib, budget_s=20.0):
+def ncu_traffic_per_launch():
+    """dram__bytes_read + dram__bytes_write of the decode kernel per launch, from the committed ncu launch
+    list of the same workload (profiles/r01_launches.csv); None if the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_launches.csv")
+    try:
+        rd = wr = None
+        with open(path) as f:
+            for line in f:
+                if "decode_tma_kernel" not in line:
+                    continue
+                parts = line.strip().split(",")
+                if "dram__bytes_read.sum" in line:
+                    rd = float(parts[-2])
+                elif "dram__bytes_write.sum" in line:
+                    wr = float(parts[-2])
+        return None if rd is None or wr is None else rd + wr
+    except Exception:
+        return None
+
+
+def cpu_baseline_single_core(frames_np, white_np, calib, budget_s=15.0):
     """Oracle port, one thread, on a bounded sample of the 1080p scan (whole rows)."""
     import numpy as np
     cal = _oracle_calib(calib)
@@ -134,7 +154,7 @@ def cpu_baseline_single_core(frames_np, white_np, calib, budget_s=20.0):
         calls += 1
         y = (y + rows) % (CAM_SIZE[1] - rows + 1)
         el = time.perf_counter() - t0
-        if el > budget_s or calls >= 16:
+        if el > budget_s or calls >= 96:
             break
     return {"value": done_px / 1e6 / el, "unit": "Mpx/s", "cores": 1, "kind": "port",
             "sample": f"{calls} bands of {rows} rows x 1920 px of the 1080p scan ({done_px / 1e6:.2f} Mpx, {el:.1f} s), "
@@ -402,7 +422,9 @@ def run_gpu(args):
                        "launch": f"CUDA graph per scan (decode, strip-prefix, column-scan, emit); independent scans pipelined over {S} CUDA streams"},
             "scans_per_s": world * K / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_launches.csv",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": decode_ms * 1e3,
                          "frac_of_nominal_8000": achieved / 8000.0,
                          "timing": f"{kr} decode-only launches over the ring, CUDA events, pipelined over {S} streams like the step",
