@@ -136,6 +136,24 @@ int sl_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int 
   return launch_codes_to_pixels(h_codes, v_codes, R, n, npix, run_pitch, h_idx, v_idx, sms, (cudaStream_t)stream);
 }
 
+int sl_bgr_to_gray_u8(const uint8_t* bgr, int64_t npix, uint8_t* gray, void* stream) {
+  if (npix < 0 || (npix > 0 && (!bgr || !gray))) { set_error("bad argument"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_bgr_to_gray(bgr, npix, gray, sms, (cudaStream_t)stream);
+}
+
+int sl_pair_diff_counts(const uint8_t* frames, int n_frames, int64_t elems_per_frame, size_t frame_pitch,
+                        int thresh, uint64_t* counts, void* stream) {
+  if (n_frames < 1 || elems_per_frame < 0 || (n_frames > 1 && (!frames || !counts))) { set_error("bad argument"); return kErrBadArg; }
+  if (frame_pitch < (size_t)elems_per_frame) { set_error("frame_pitch smaller than the frame"); return kErrBadArg; }
+  if (n_frames > 65536) { set_error("too many frames"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_pair_diff(frames, n_frames, elems_per_frame, frame_pitch, thresh, (unsigned long long*)counts, sms,
+                          (cudaStream_t)stream);
+}
+
 size_t sl_cloud_workspace_bytes(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
   return cloud_workspace_bytes(B, H, W);

@@ -22,6 +22,11 @@ int launch_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, 
                            long long npix, size_t run_pitch, int16_t* h_idx, int16_t* v_idx,
                            int num_sms, cudaStream_t st);
 
+// ---- capture front end (sl_frames.cu)
+int launch_bgr_to_gray(const uint8_t* bgr, long long npix, uint8_t* gray, int num_sms, cudaStream_t st);
+int launch_pair_diff(const uint8_t* frames, int n_frames, long long elems, size_t frame_pitch, int thresh,
+                     unsigned long long* counts, int num_sms, cudaStream_t st);
+
 // ---- stage 2 (sl_cloud.cu)
 struct CloudWorkspace {      // views into the caller's workspace buffer
   uint32_t* bitmap;          // [B][bitmap_words] flat validity bits (bit i of word i/32 = pixel i)

@@ -18,6 +18,64 @@ def _stack(images):
     return slb200.as_u8_stack(images)
 
 
+# ---- capture front end (reference decode_codes.py:6-87) ------------------------------------
+def read_images(folder):
+    """All images of a folder, sorted by name length like the reference (decode_codes.py:6-32).
+    Host file I/O (cv2.imread); returns ``(images float64 (N,H,W,3), file_names)``."""
+    import os
+    import cv2
+    files = sorted(os.listdir(folder), key=len)
+    images = None
+    for i, name in enumerate(files):
+        im = cv2.imread(os.path.join(folder, name))
+        if images is None:
+            images = np.empty((len(files),) + im.shape)
+        images[i] = im
+    return images, np.array(files)
+
+
+def _selection_from_counts(d):
+    """The reference's transition-frame state machine (decode_codes.py:49-68) on the consecutive-pair
+    difference counts d[k] = count(|images[k+1] - images[k]| > 50)."""
+    n_images = len(d) + 1
+    if n_images < 3:
+        raise IndexError("remove_bad_images needs at least 3 images")   # the reference indexes images[2]
+    diff1, diff2 = int(d[0]), int(d[1])
+    keep = []
+    for i in range(max(n_images - 3, 0)):            # `for i, image in enumerate(images[2:-1])`
+        diff3 = int(d[i + 2])                        # absdiff(images[i+3], images[i+2])
+        if diff1 < diff2 and diff1 < diff3 and diff2 < diff3 and i + 1 not in keep:
+            if len(keep) == 0 or (keep[-1] != i and keep[-1] != i + 2):
+                keep.append(i + 1)
+        elif diff2 <= diff1 and diff2 <= diff3 and i + 2 not in keep:
+            if len(keep) == 0 or (keep[-1] != i + 1 and keep[-1] != i + 3):
+                keep.append(i + 2)
+                diff3 = -1
+                diff2 = -1
+        diff1 = diff2
+        diff2 = diff3
+    return keep
+
+
+def remove_bad_images(images):
+    """Indexes of the frames to keep from a captured video sequence (transition frames dropped);
+    reference decode_codes.py:34-68.  The per-pair difference counts run on the GPU."""
+    d = slb200.pair_diff_counts(slb200.as_u8_stack(images)).cpu().numpy()
+    return _selection_from_counts(d)
+
+
+def to_gray(images):
+    """``(N,H,W,3)`` BGR frames -> ``(N,H,W)`` float64 grey levels (reference decode_codes.py:70-87:
+    ``astype(uint8)`` then cv2 BGR2GRAY).  Float input is truncated to uint8 like the reference does."""
+    a = np.asarray(images)
+    u8 = a if a.dtype == np.uint8 else a.astype(np.uint8)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if dev is None:
+        raise RuntimeError("slb200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    gray = slb200.bgr_to_gray(torch.from_numpy(np.ascontiguousarray(u8)).to(dev))
+    return gray.cpu().numpy().astype(np.float64)
+
+
 def get_direct_indirect(images):
     """L_d, L_g float64 ``(H,W)``; reference decode_codes.py:90-122."""
     l_d, l_g = slb200.direct_indirect(_stack(images))

@@ -152,6 +152,34 @@ def _check_stack(frames: torch.Tensor):
         raise ValueError("frames must be contiguous, or a row band of a contiguous stack")
 
 
+# --------------------------------------------------------------------------- capture front end
+def bgr_to_gray(bgr: torch.Tensor) -> torch.Tensor:
+    """cv2.cvtColor(BGR2GRAY) of uint8 CUDA frames ``(..., 3)`` -> ``(...)`` uint8
+    (src/3-capture_decode.py:66, decode_codes.py:86)."""
+    if not (bgr.is_cuda and bgr.dtype == torch.uint8 and bgr.shape[-1] == 3):
+        raise TypeError("bgr must be a CUDA uint8 tensor with a trailing dimension of 3")
+    bgr = bgr.contiguous()
+    gray = torch.empty(bgr.shape[:-1], dtype=torch.uint8, device=bgr.device)
+    with torch.cuda.device(bgr.device):
+        check(lib().sl_bgr_to_gray_u8(_ptr(bgr), gray.numel(), _ptr(gray), _stream()))
+    return gray
+
+
+def pair_diff_counts(frames: torch.Tensor, thresh: int = 50) -> torch.Tensor:
+    """Number of elements with ``|frames[k+1] - frames[k]| > thresh`` for every consecutive pair
+    (decode_codes.py:49-54).  frames: CUDA uint8 ``(N, ...)``; returns int64 ``(N-1,)`` (CUDA)."""
+    if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() >= 2):
+        raise TypeError("frames must be a CUDA uint8 tensor (N, ...)")
+    frames = frames.contiguous()
+    n = frames.shape[0]
+    elems = frames[0].numel()
+    counts = torch.zeros(max(n - 1, 0), dtype=torch.int64, device=frames.device)
+    if n >= 2:
+        with torch.cuda.device(frames.device):
+            check(lib().sl_pair_diff_counts(_ptr(frames), n, elems, elems, int(thresh), _ptr(counts), _stream()))
+    return counts
+
+
 # --------------------------------------------------------------------------- stage 1
 def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
     """Fused decode: ``(F,H,W)`` / ``(B,F,H,W)`` uint8 -> ``h_pixels, v_pixels`` int16, -1 invalid.

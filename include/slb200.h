@@ -96,6 +96,19 @@ int sl_is_lit(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, co
 int sl_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int n, int64_t npix,
                        size_t run_pitch, int16_t* h_idx, int16_t* v_idx, void* stream);
 
+/* ------------------------------------------------------------- capture front end */
+
+/* cv2.cvtColor(frame, COLOR_BGR2GRAY) on 8-bit frames, as src/3-capture_decode.py:66 and to_gray
+ * (scanner/grayCode/decode_codes.py:70-87) apply it before the decode:
+ * gray = (3735*B + 19235*G + 9798*R + 16384) >> 15.  bgr device u8 [npix][3], gray device u8 [npix]. */
+int sl_bgr_to_gray_u8(const uint8_t* bgr, int64_t npix, uint8_t* gray, void* stream);
+
+/* remove_bad_images' measurements (decode_codes.py:49-54): counts[k] = number of elements with
+ * |frames[k+1] - frames[k]| > thresh, k = 0..n_frames-2 (the reference counts per channel element).
+ * frames device u8, frame k at frames + k*frame_pitch; counts device u64 [n_frames-1]. */
+int sl_pair_diff_counts(const uint8_t* frames, int n_frames, int64_t elems_per_frame, size_t frame_pitch,
+                        int thresh, uint64_t* counts, void* stream);
+
 /* ---------------------------------------------------------- triangulation (stage 2) */
 
 /* Bytes of device scratch the compaction needs for B scans of H x W. */

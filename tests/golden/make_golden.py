@@ -119,7 +119,36 @@ def main():
                      f"{name}_filt_pts": fp, f"{name}_filt_colors": fc, f"{name}_filt125_pts": fp2,
                      f"{name}_filt125_colors": fc2, f"{name}_und_cam": und_cam, f"{name}_und_proj": und_proj})
     np.savez_compressed(os.path.join(HERE, "triangulate_golden.npz"), **tout)
-    for f in ("decode_golden.npz", "triangulate_golden.npz"):
+    # ---- capture front end: to_gray (decode_codes.py:70-87) and remove_bad_images (:34-68)
+    rng = np.random.default_rng(41)
+    fout = {}
+    bgr = rng.integers(0, 256, (3, 20, 36, 3)).astype(np.uint8)
+    bgr[0, 0, :6] = [[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 2, 3]]
+    fout["gray_bgr"] = bgr
+    fout["gray_out"] = dec.to_gray(bgr.astype(np.float64))                  # float64 (N,H,W)
+    fout["gray_float_in"] = bgr.astype(np.float64) + 0.75                   # astype(uint8) truncates
+    fout["gray_float_out"] = dec.to_gray(fout["gray_float_in"])
+    # a "video": stable pattern frames separated by blended transition frames, with sensor noise
+    def video(seed, n_patterns, holds):
+        r = np.random.default_rng(seed)
+        pats = [r.integers(0, 256, (12, 18, 3)).astype(np.float64) for _ in range(n_patterns)]
+        frames = []
+        for k, pat in enumerate(pats):
+            for _ in range(holds[k % len(holds)]):
+                frames.append(np.clip(pat + r.integers(-3, 4, pat.shape), 0, 255))
+            if k + 1 < n_patterns:
+                alpha = r.uniform(0.3, 0.7)
+                frames.append(np.clip(alpha * pat + (1 - alpha) * pats[k + 1], 0, 255))
+        return np.floor(np.array(frames))
+    for name, (seed, n_p, holds) in {"v1": (51, 6, [2]), "v2": (52, 7, [2, 3]), "v3": (53, 5, [1, 2])}.items():
+        frames = video(seed, n_p, holds)
+        fout[f"video_{name}"] = frames.astype(np.uint8)
+        fout[f"video_{name}_keep"] = np.array(dec.remove_bad_images(frames), dtype=np.int64)
+        fout[f"video_{name}_counts"] = np.array(
+            [len(np.argwhere(cv2.absdiff(frames[k + 1], frames[k]) > 50)) for k in range(len(frames) - 1)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "frames_golden.npz"), **fout)
+
+    for f in ("decode_golden.npz", "triangulate_golden.npz", "frames_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -113,3 +113,25 @@ def test_synthetic_scene_is_deterministic_and_decodable():
     hp, vp = O.decode_pixels(a[0].numpy().astype(np.float64))
     valid = (hp >= 0) & (vp >= 0)
     assert valid[:, 20:].mean() > 0.99 and valid[:, :20].mean() < 0.1
+
+
+def test_remove_bad_images_state_machine_golden(golden_dir):
+    """Host half of remove_bad_images (the selection logic over per-pair difference counts) against the
+    reference's own output on synthetic videos; the counts here come from NumPy, the GPU test checks the kernel."""
+    from scanner.grayCode.decode_codes import _selection_from_counts
+    g = np.load(os.path.join(golden_dir, "frames_golden.npz"))
+    for name in ("v1", "v2", "v3"):
+        frames = g[f"video_{name}"].astype(np.int16)
+        d = [(np.abs(frames[k + 1] - frames[k]) > 50).sum() for k in range(len(frames) - 1)]
+        np.testing.assert_array_equal(d, g[f"video_{name}_counts"])
+        assert _selection_from_counts(d) == g[f"video_{name}_keep"].tolist()
+    with pytest.raises(IndexError):
+        _selection_from_counts([3])
+
+
+def test_gray_formula_matches_cv2_golden(golden_dir):
+    """The fixed-point BGR2GRAY formula the kernel implements, checked on the CPU against cv2's output."""
+    g = np.load(os.path.join(golden_dir, "frames_golden.npz"))
+    bgr = g["gray_bgr"].astype(np.uint32)
+    gray = (3735 * bgr[..., 0] + 19235 * bgr[..., 1] + 9798 * bgr[..., 2] + 16384) >> 15
+    np.testing.assert_array_equal(gray.astype(np.float64), g["gray_out"])

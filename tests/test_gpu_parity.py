@@ -473,6 +473,34 @@ def test_dropin_scripts_flow(T):
     Triangulate()                                                 # all-default constructor (src/4-triangulate.py:24)
 
 
+def test_front_end_to_gray_and_remove_bad_images(T, golden_dir):
+    """cv2 BGR2GRAY (to_gray) and the transition-frame rejection (remove_bad_images)."""
+    import slb200
+    from scanner.grayCode import decode_codes as dc
+    g = np.load(os.path.join(golden_dir, "frames_golden.npz"))
+    out = dc.to_gray(g["gray_bgr"].astype(np.float64))
+    assert out.dtype == np.float64
+    np.testing.assert_array_equal(out, g["gray_out"])
+    np.testing.assert_array_equal(dc.to_gray(g["gray_float_in"]), g["gray_float_out"])
+    # exhaustive over all 2^24 colours against the closed form (pinned to cv2 by the golden test on the CPU)
+    idx = T.arange(1 << 24, dtype=T.int32, device="cuda")
+    bgr = T.stack([idx & 255, (idx >> 8) & 255, (idx >> 16) & 255], dim=1).to(T.uint8)
+    gray = slb200.bgr_to_gray(bgr).to(T.int32)
+    ref = (3735 * (idx & 255) + 19235 * ((idx >> 8) & 255) + 9798 * ((idx >> 16) & 255) + 16384) >> 15
+    assert T.equal(gray, ref)
+    odd = slb200.bgr_to_gray(bgr[1:1 + 1003].clone())            # unaligned start / ragged tail
+    assert T.equal(odd.to(T.int32), ref[1:1 + 1003])
+    for name in ("v1", "v2", "v3"):
+        frames = g[f"video_{name}"]
+        counts = slb200.pair_diff_counts(T.from_numpy(frames).cuda()).cpu().numpy()
+        np.testing.assert_array_equal(counts, g[f"video_{name}_counts"])
+        assert dc.remove_bad_images(frames.astype(np.float64)) == g[f"video_{name}_keep"].tolist()
+    big = T.randint(0, 256, (5, 333, 517, 3), dtype=T.uint8, device="cuda")
+    c = slb200.pair_diff_counts(big, thresh=50).cpu().numpy()
+    b16 = big.cpu().numpy().astype(np.int16)
+    np.testing.assert_array_equal(c, [(np.abs(b16[k + 1] - b16[k]) > 50).sum() for k in range(4)])
+
+
 def test_error_codes(T):
     import slb200
     with pytest.raises(slb200.SlError):
