@@ -668,7 +668,10 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   const long long warps = (long long)B * strips;
   (void)warps;
   if (c.bands > kMaxBands) { set_error("image too tall (%d rows)", H); return kErrBadArg; }
-  strip_prefix_kernel<<<B * strips, kStripWarps * 32, (size_t)c.bands * 32 * sizeof(uint32_t), st>>>(
+  const size_t strip_smem = (size_t)c.bands * 32 * sizeof(uint32_t);
+  if (strip_smem > 48 * 1024)     // rare (more than 12288 rows): opt in to the larger carve-out
+    SL_CUDA(cudaFuncSetAttribute(strip_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem));
+  strip_prefix_kernel<<<B * strips, kStripWarps * 32, strip_smem, st>>>(
       c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot, c.col_base, B, counts,
       c.ticket);
   count_launch();

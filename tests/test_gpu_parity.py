@@ -155,6 +155,26 @@ def test_ideal_sequence_identity_full_size(T):
     assert bool((hi == xs).all()) and bool((vi == ys).all())
 
 
+def test_ideal_sequence_identity_4k_and_tall(T):
+    """Largest configured size (3840x2160, n = 12, F = 50) and a very tall, narrow image (many bands)."""
+    import slb200
+    from scanner.grayCode.generate_codes import get_gray_codes, get_image_sequence
+    pw, ph = 3840, 2160
+    seq = T.from_numpy(get_image_sequence(get_gray_codes(pw, ph), pw, ph)).cuda()
+    hi, vi = slb200.decode_pixels(seq)
+    xs = T.arange(pw, dtype=T.int16, device="cuda")[None, :].expand(ph, pw)
+    ys = T.arange(ph, dtype=T.int16, device="cuda")[:, None].expand(ph, pw)
+    assert bool((hi == xs).all()) and bool((vi == ys).all())
+    del seq, hi, vi
+    # tall: 13000 rows x 8 columns (407 bands -> the strip kernel's large shared-memory carve-out)
+    hp = np.full((13000, 8), 3, dtype=np.int64); vp = hp.copy()
+    hp[::7, 3] = -1
+    cam, proj, _ = slb200.cam_proj_pairs(hp, vp, (16, 16), None)
+    co, po, _ = O.cam_proj_pairs(hp, vp, (16, 16), None)
+    np.testing.assert_array_equal(cam.cpu().numpy(), co)
+    np.testing.assert_array_equal(proj.cpu().numpy(), po)
+
+
 def test_full_size_synthetic_scan_vs_oracle(T):
     """Config 1 (1280x720 camera, 1024x768 projector) end to end against the oracle."""
     import slb200
