@@ -18,6 +18,30 @@
 
 namespace sl {
 
+__device__ double g_binv_table[65536];
+
+__global__ void binv_table_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // i = white << 8 | black
+  if (i < 65536) g_binv_table[i] = __ddiv_rn((double)(i >> 8), (double)((i >> 8) + (i & 255)));
+}
+
+static int ensure_binv_table(cudaStream_t st) {
+#if defined(SL_BINV_TABLE)
+  static bool ready[64] = {false};
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (!ready[dev & 63]) {
+    binv_table_kernel<<<256, 256, 0, st>>>();
+    count_launch();
+    SL_CUDA(cudaGetLastError());
+    ready[dev & 63] = true;
+  }
+#else
+  (void)st;
+#endif
+  return kOk;
+}
+
 // ------------------------------------------------------------------ K1 configuration
 #ifndef SL_TILE_PX
 #define SL_TILE_PX 512
@@ -328,6 +352,10 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
                   int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
                   int num_sms, cudaStream_t st) {
   const int n = (F - 2) / 4;
+  {
+    const int trc = ensure_binv_table(st);
+    if (trc) return trc;
+  }
   const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
   const bool aligned = ((uintptr_t)frames % 16 == 0) && (frame_pitch % 16 == 0) &&
                        (scan_pitch % 16 == 0) && ((uintptr_t)h_idx % 8 == 0) &&
