@@ -12,18 +12,25 @@
 //                           scanner/grayCode/decode_codes.py:172-182 writes them.
 // K1m codes_to_pixels_kernel run merge (src/3-capture_decode.py:95-96) + Gray->decimal (:99-100).
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
+#include <cuda_runtime.h>
+#if defined(SL_BINV_TABLE)
+// b_inv = white / (white + black) for every pair of 8-bit samples, filled once per device by
+// binv_table_kernel with the same correctly rounded fp64 division (NaN for 0/0); 512 KB, L2-resident.
+namespace sl { __device__ double g_binv_table[65536]; }
+#define SL_BINV_LOOKUP(w, b) __ldg(&::sl::g_binv_table[((w) << 8) | (b)])
+#endif
 #include "sl_common.cuh"
 #include "sl_decode_quad.cuh"
 #include "sl_kernels.h"
 
 namespace sl {
 
-__device__ double g_binv_table[65536];
-
+#if defined(SL_BINV_TABLE)
 __global__ void binv_table_kernel() {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;     // i = white << 8 | black
   if (i < 65536) g_binv_table[i] = __ddiv_rn((double)(i >> 8), (double)((i >> 8) + (i & 255)));
 }
+#endif
 
 static int ensure_binv_table(cudaStream_t st) {
 #if defined(SL_BINV_TABLE)

@@ -123,15 +123,10 @@ struct PixelThr {
   int easy;  // hi1 <= lo: the single-threshold shortcut of classify4_easy applies
 };
 
-#if defined(__CUDACC__)
-// b_inv = white / (white + black) for every pair of 8-bit samples, filled once per device by
-// binv_table_kernel with the same correctly rounded fp64 division (NaN for 0/0); 512 KB, L2-resident.
-extern __device__ double g_binv_table[65536];
-#endif
-
 SL_HD PixelThr pixel_thresholds(int white, int black, int lmax, int lmin, int e) {
-#if defined(__CUDA_ARCH__) && defined(SL_BINV_TABLE)
-  const double b_inv = __ldg(&g_binv_table[(white << 8) | black]);     // decode_codes.py:113
+#if defined(__CUDA_ARCH__) && defined(SL_BINV_LOOKUP)
+  // tuning option of sl_decode.cu: b_inv from a 256x256 table filled with the same rounded division
+  const double b_inv = SL_BINV_LOOKUP(white, black);   // decode_codes.py:113
 #else
   const double w = (double)white;
   const double s = (double)(white + black);           // exact
