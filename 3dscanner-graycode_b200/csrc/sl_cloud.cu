@@ -25,6 +25,10 @@ namespace sl {
 constexpr int kBandRows = 32;       // rows per band = lanes per warp
 constexpr int kStripCols = 32;      // columns per strip in the offsets kernel
 constexpr int kEmitCols = 16;       // columns per warp tile in the emit kernel
+#ifndef SL_EMIT_GROUP
+#define SL_EMIT_GROUP 4
+#endif
+constexpr int kEmitGroup = SL_EMIT_GROUP;     // row groups (of 8 rows) loaded per pass: 1, 2 or 4
 #ifndef SL_EMIT_WARPS
 #define SL_EMIT_WARPS 4
 #endif
@@ -482,57 +486,62 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a)
   // the cloud stream through once (evict_first)
   const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
   if (vec) {
-    // (1) every load that depends on nothing, for all 4 row groups of the tile, back to back
-    uint2 h2[4], v2[4];
-    uint32_t w0[4], w1[4], w2[4];
-    float4 r0[4], r1[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = min(rr + 8 * it, rows - 1);               // rows past the image repeat the last one (never valid)
-      const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
-      h2[it] = ldg_u2_hint(a.h + g, stream);
-      v2[it] = ldg_u2_hint(a.v + g, stream);
-      if (has_rgb) {
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);      // 12 bytes = 4 RGB pixels
-        w0[it] = ldg_u32_hint(wp, stream); w1[it] = ldg_u32_hint(wp + 1, stream); w2[it] = ldg_u32_hint(wp + 2, stream);
-      } else {
-        w0[it] = w1[it] = w2[it] = 0;
-      }
-      if (kTable) {
-        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
-        r0[it] = ldg_f4_hint(rp, keep); r1[it] = ldg_f4_hint(rp + 1, keep);
-      }
-    }
     uint32_t cb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
-    // (2) the 16 projector-ray gathers (neighbouring pixels hit neighbouring table entries)
-    float2 pray[4][4];
-    int hc[4][4], vc[4][4];
+    // The tile's 4 row groups are processed kEmitGroup at a time: more groups per pass = more loads
+    // in flight per warp, fewer = fewer registers (more resident warps).
+#pragma unroll 1
+    for (int it0 = 0; it0 < 4; it0 += kEmitGroup) {
+      // (1) every load that depends on nothing, back to back
+      uint2 h2[kEmitGroup], v2[kEmitGroup];
+      uint32_t w0[kEmitGroup], w1[kEmitGroup], w2[kEmitGroup];
+      float4 r0[kEmitGroup], r1[kEmitGroup];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = rr + 8 * it;
-      const uint32_t hw[2] = {h2[it].x, h2[it].y}, vw[2] = {v2[it].x, v2[it].y};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int hq = (hw[k >> 1] >> (16 * (k & 1))) & 0xffff, vq = (vw[k >> 1] >> (16 * (k & 1))) & 0xffff;
-        hc[it][k] = min(a.cal.proj_w - 1, hq); vc[it][k] = min(a.cal.proj_h - 1, vq);     // triangulate.py:60-61
-        pray[it][k] = make_float2(0.f, 0.f);
-        if (kTable && ((cb[k] >> r) & 1u))                                                // triangulate.py:56
-          pray[it][k] = ldg_f2_hint(a.proj_rays + (size_t)vc[it][k] * a.cal.proj_w + hc[it][k], keep);
+      for (int j = 0; j < kEmitGroup; ++j) {
+        const int r = min(rr + 8 * (it0 + j), rows - 1);        // rows past the image repeat the last one (never valid)
+        const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+        h2[j] = ldg_u2_hint(a.h + g, stream);
+        v2[j] = ldg_u2_hint(a.v + g, stream);
+        if (has_rgb) {
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);      // 12 bytes = 4 RGB pixels
+          w0[j] = ldg_u32_hint(wp, stream); w1[j] = ldg_u32_hint(wp + 1, stream); w2[j] = ldg_u32_hint(wp + 2, stream);
+        } else {
+          w0[j] = w1[j] = w2[j] = 0;
+        }
+        if (kTable) {
+          const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
+          r0[j] = ldg_f4_hint(rp, keep); r1[j] = ldg_f4_hint(rp + 1, keep);
+        }
       }
-    }
-    // (3) arithmetic + store
+      // (2) the projector-ray gathers (neighbouring pixels hit neighbouring table entries)
+      float2 pray[kEmitGroup][4];
+      int hc[kEmitGroup][4], vc[kEmitGroup][4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = rr + 8 * it;
-      const uint32_t col[4] = {w0[it] & 0xffffffu, (w0[it] >> 24) | ((w1[it] & 0xffffu) << 8),
-                               (w1[it] >> 16) | ((w2[it] & 0xffu) << 16), w2[it] >> 8};   // triangulate.py:64
-      const float2 cray[4] = {make_float2(r0[it].x, r0[it].y), make_float2(r0[it].z, r0[it].w),
-                              make_float2(r1[it].x, r1[it].y), make_float2(r1[it].z, r1[it].w)};
+      for (int j = 0; j < kEmitGroup; ++j) {
+        const int r = rr + 8 * (it0 + j);
+        const uint32_t hw[2] = {h2[j].x, h2[j].y}, vw[2] = {v2[j].x, v2[j].y};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if ((cb[k] >> r) & 1u) store_point(k, r, cb[k], hc[it][k], vc[it][k], cray[k], pray[it][k], col[k]);
+        for (int k = 0; k < 4; ++k) {
+          const int hq = (hw[k >> 1] >> (16 * (k & 1))) & 0xffff, vq = (vw[k >> 1] >> (16 * (k & 1))) & 0xffff;
+          hc[j][k] = min(a.cal.proj_w - 1, hq); vc[j][k] = min(a.cal.proj_h - 1, vq);     // triangulate.py:60-61
+          pray[j][k] = make_float2(0.f, 0.f);
+          if (kTable && ((cb[k] >> r) & 1u))                                              // triangulate.py:56
+            pray[j][k] = ldg_f2_hint(a.proj_rays + (size_t)vc[j][k] * a.cal.proj_w + hc[j][k], keep);
+        }
+      }
+      // (3) arithmetic + store
+#pragma unroll
+      for (int j = 0; j < kEmitGroup; ++j) {
+        const int r = rr + 8 * (it0 + j);
+        const uint32_t col[4] = {w0[j] & 0xffffffu, (w0[j] >> 24) | ((w1[j] & 0xffffu) << 8),
+                                 (w1[j] >> 16) | ((w2[j] & 0xffu) << 16), w2[j] >> 8};   // triangulate.py:64
+        const float2 cray[4] = {make_float2(r0[j].x, r0[j].y), make_float2(r0[j].z, r0[j].w),
+                                make_float2(r1[j].x, r1[j].y), make_float2(r1[j].z, r1[j].w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((cb[k] >> r) & 1u) store_point(k, r, cb[k], hc[j][k], vc[j][k], cray[k], pray[j][k], col[k]);
+      }
     }
   } else {
     // ragged tiles / row pitches that are not a multiple of 4 pixels: scalar loads, one row group at a time
