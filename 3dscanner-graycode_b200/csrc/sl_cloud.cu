@@ -423,8 +423,11 @@ struct EmitTile {
 // Record layouts (out, 4 words per point):
 //    cloud modes  {x, y, z, rgb}     rgb = R | G<<8 | B<<16 (0 without a colour image)
 //    kModePairs   {cam_x, cam_y, proj_x, proj_y}, colour word (same packing) to out_rgb32 when given
+#ifndef SL_EMIT_MIN_CTAS
+#define SL_EMIT_MIN_CTAS 1
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs a) {
+__global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel(const EmitArgs a) {
   extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
