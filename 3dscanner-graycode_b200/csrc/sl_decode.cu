@@ -86,8 +86,13 @@ struct DecodeArgs {
   int n, F, e, stages;
 };
 
+#ifdef SL_DECODE_MAXREG
+#define SL_DECODE_REG_ATTR __maxnreg__(SL_DECODE_MAXREG)
+#else
+#define SL_DECODE_REG_ATTR __launch_bounds__(kDecodeThreads, 1)
+#endif
 template <int NB, bool CODES>
-__global__ void __launch_bounds__(kDecodeThreads, 1) decode_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                         const DecodeArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int n = NB ? NB : a.n;
