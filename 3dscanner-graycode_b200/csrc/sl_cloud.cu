@@ -424,7 +424,7 @@ struct EmitTile {
 //    cloud modes  {x, y, z, rgb}     rgb = R | G<<8 | B<<16 (0 without a colour image)
 //    kModePairs   {cam_x, cam_y, proj_x, proj_y}, colour word (same packing) to out_rgb32 when given
 #ifndef SL_EMIT_MIN_CTAS
-#define SL_EMIT_MIN_CTAS 1
+#define SL_EMIT_MIN_CTAS 5      // <= 102 registers: an emit CTA fits beside a resident decode CTA (see sl_decode.cu)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel(const EmitArgs a) {
