@@ -219,6 +219,8 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
+    global RING
+    RING = max(2, args.ring)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -448,6 +450,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lens", default="tables", choices=["tables", "iterate"])
     ap.add_argument("--streams", type=int, default=STREAMS)
+    ap.add_argument("--ring", type=int, default=RING)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
