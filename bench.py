@@ -40,8 +40,8 @@ N_FRAMES = 4 * N_BITS + 2
 MPX = CAM_SIZE[0] * CAM_SIZE[1] / 1e6
 METRIC = "Mpx/s decoded+triangulated"
 WORKLOAD = "config[1]: single 1920x1080 camera scan of a 1920x1080 projector Gray sequence (11+11 bits + inverses + white/black)"
-RING = 9          # resident scans per rank: 9 x 95.4 MB = 859 MB > 126 MB L2
-STREAMS = 3       # independent scans are pipelined over 3 CUDA streams (own buffers each)
+RING = 12         # resident scans per rank: 12 x 95.4 MB = 1.14 GB > 126 MB L2
+STREAMS = 4       # independent scans are pipelined over 4 CUDA streams (own buffers each)
 
 
 def load_peaks():
