@@ -722,47 +722,7 @@ static int emit_configure() {
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
-#if defined(SL_L2_PERSIST)
-  // reserve part of L2 for the lens tables (see launch_emit_cloud)
-  int max_persist = 0;
-  SL_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-  size_t want = (size_t)SL_L2_PERSIST << 20;
-  if ((size_t)max_persist < want) want = (size_t)max_persist;
-  if (want) SL_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-#endif
   done[dev & 63] = true;
-  return kOk;
-}
-
-template <int MODE>
-static int launch_emit_table(const EmitArgs& a, int g, int thr, const float* cam_rays, const float* proj_rays,
-                             size_t cam_bytes, size_t proj_bytes, cudaStream_t st) {
-#if defined(SL_L2_PERSIST)
-  // The tables are re-read by every scan: ask L2 to keep them (persisting access window over both when they
-  // sit in one allocation, else over the camera table) while everything else streams.
-  const char* lo = reinterpret_cast<const char*>(cam_rays);
-  size_t span = cam_bytes;
-  const char* plo = reinterpret_cast<const char*>(proj_rays);
-  if (plo >= lo && (size_t)(plo - lo) <= cam_bytes + 4096) span = (size_t)(plo - lo) + proj_bytes;
-  int dev = 0, max_win = 0;
-  SL_CUDA(cudaGetDevice(&dev));
-  SL_CUDA(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-  if (span > (size_t)max_win) span = (size_t)max_win;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-  attr[0].val.accessPolicyWindow.base_ptr = const_cast<char*>(lo);
-  attr[0].val.accessPolicyWindow.num_bytes = span;
-  attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-  attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g); cfg.blockDim = dim3(thr); cfg.dynamicSmemBytes = kEmitSmemCloud; cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  SL_CUDA(cudaLaunchKernelEx(&cfg, emit_kernel<MODE>, a));
-#else
-  (void)cam_rays; (void)proj_rays; (void)cam_bytes; (void)proj_bytes;
-  emit_kernel<MODE><<<g, thr, kEmitSmemCloud, st>>>(a);
-#endif
   return kOk;
 }
 
@@ -822,12 +782,8 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   if (rc) return rc;
   if ((rc = check_emit_size(a))) return rc;
   if (cam_rays) {
-    // NOTE: the camera table may cover more rows than this band (row-band sharding); H + row0 rows are touched
-    const size_t cam_bytes = (size_t)(H + calib.cam_row0) * W * sizeof(float2);
-    const size_t proj_bytes = (size_t)calib.proj_w * calib.proj_h * sizeof(float2);
-    if (precision == SL_PREC_FP64) rc = launch_emit_table<kModeTable64>(a, g, thr, cam_rays, proj_rays, cam_bytes, proj_bytes, st);
-    else rc = launch_emit_table<kModeTable32>(a, g, thr, cam_rays, proj_rays, cam_bytes, proj_bytes, st);
-    if (rc) return rc;
+    if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmemCloud, st>>>(a);
+    else emit_kernel<kModeTable32><<<g, thr, kEmitSmemCloud, st>>>(a);
   } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmemCloud, st>>>(a);
   else emit_kernel<kModeCloud32><<<g, thr, kEmitSmemCloud, st>>>(a);
   count_launch();

@@ -451,10 +451,8 @@ class LensTables:
         w, h = int(cam_size[0]), int(cam_size[1])
         pw, ph = calib.proj_size
         self.cam_size, self.proj_size = (w, h), (pw, ph)
-        # one allocation (camera table, then projector table) so a single L2 access window can cover both
-        self._buf = torch.empty(2 * (h * w + ph * pw), dtype=torch.float32, device=device)
-        self.cam = self._buf[: 2 * h * w].view(h, w, 2)
-        self.proj = self._buf[2 * h * w:].view(ph, pw, 2)
+        self.cam = torch.empty((h, w, 2), dtype=torch.float32, device=device)
+        self.proj = torch.empty((ph, pw, 2), dtype=torch.float32, device=device)
         s = calib.struct()
         with torch.cuda.device(device):
             check(lib().sl_lens_tables(C.byref(s), w, h, _ptr(self.cam), _ptr(self.proj), _stream()))
