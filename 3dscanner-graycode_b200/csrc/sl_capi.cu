@@ -240,6 +240,16 @@ int sl_filter_box(const double* pts, const double* colors, int64_t N, double thr
                            (cudaStream_t)stream);
 }
 
+int sl_filter_cloud_box(const float* cloud, int64_t N, double threshold, float* out_cloud,
+                        int64_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N < 0 || !out_count || !workspace) { set_error("bad argument"); return kErrBadArg; }
+  if (N > 0 && (!cloud || !out_cloud)) { set_error("null buffer"); return kErrBadArg; }
+  if (workspace_bytes < filter_workspace_bytes(N)) { set_error("workspace too small"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_filter_cloud(cloud, N, threshold, out_cloud, (long long*)out_count, workspace, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ host-buffer pipeline
 struct SlPipeline {
   int device = 0, max_batch = 0, F = 0, H = 0, W = 0, sms = 0;

@@ -611,18 +611,30 @@ __global__ void __launch_bounds__(256) points_kernel(const float2* __restrict__ 
 // ------------------------------------------------------------------ box filter (triangulate.py:99-122)
 constexpr int kFilterBlock = 1024;   // points per block (256 threads x 4)
 
-__device__ __forceinline__ bool keep_pt(const double* pts, long long N, long long i, double thr) {
-  const double x = pts[i], y = pts[N + i], z = pts[2 * N + i];
-  return (z < thr) && (z > -thr) && (y < thr) && (y > -thr) && (x < thr) && (x > -thr);
+__device__ __forceinline__ bool inside_box(double x, double y, double z, double thr) {
+  return (z < thr) && (z > -thr) && (y < thr) && (y > -thr) && (x < thr) && (x > -thr);     // triangulate.py:119
 }
 
-__global__ void __launch_bounds__(256) filter_count_kernel(const double* __restrict__ pts, long long N,
+// REC = false: pts is the reference's (3,N) float64 array (+ optional (N,3) colours);
+// REC = true : pts is the packed (N,4) float32 XYZRGB cloud of sl_emit_cloud.
+template <bool REC>
+__device__ __forceinline__ bool keep_pt(const void* pts, long long N, long long i, double thr) {
+  if (REC) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + i);
+    return inside_box((double)q.x, (double)q.y, (double)q.z, thr);
+  }
+  const double* p = reinterpret_cast<const double*>(pts);
+  return inside_box(p[i], p[N + i], p[2 * N + i], thr);
+}
+
+template <bool REC>
+__global__ void __launch_bounds__(256) filter_count_kernel(const void* __restrict__ pts, long long N,
                                                             double thr, uint32_t* __restrict__ blk_cnt) {
   const long long base = (long long)blockIdx.x * kFilterBlock;
   uint32_t c = 0;
   for (int k = 0; k < 4; ++k) {
     const long long i = base + k * 256 + threadIdx.x;
-    if (i < N && keep_pt(pts, N, i, thr)) ++c;
+    if (i < N && keep_pt<REC>(pts, N, i, thr)) ++c;
   }
   c = __reduce_add_sync(0xffffffffu, c);
   __shared__ uint32_t ws[8];
@@ -635,10 +647,11 @@ __global__ void __launch_bounds__(256) filter_count_kernel(const double* __restr
   }
 }
 
-__global__ void __launch_bounds__(256) filter_emit_kernel(const double* __restrict__ pts,
+template <bool REC>
+__global__ void __launch_bounds__(256) filter_emit_kernel(const void* __restrict__ pts,
                                                            const double* __restrict__ colors, long long N,
                                                            double thr, const long long* __restrict__ blk_base,
-                                                           double* __restrict__ out_pts,
+                                                           void* __restrict__ out_pts,
                                                            double* __restrict__ out_colors) {
   __shared__ uint32_t ws[8];
   const long long base = (long long)blockIdx.x * kFilterBlock;
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(256) filter_emit_kernel(const double* __restri
   long long run = blk_base[blockIdx.x];
   for (int k = 0; k < 4; ++k) {          // chunks of 256 consecutive points keep the order
     const long long i = base + k * 256 + threadIdx.x;
-    const bool keep = i < N && keep_pt(pts, N, i, thr);
+    const bool keep = i < N && keep_pt<REC>(pts, N, i, thr);
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) ws[warp] = __popc(m);
     __syncthreads();
@@ -654,11 +667,17 @@ __global__ void __launch_bounds__(256) filter_emit_kernel(const double* __restri
     for (int w = 0; w < 8; ++w) { const uint32_t c = ws[w]; if (w < warp) before += c; total += c; }
     if (keep) {
       const long long o = run + before + __popc(m & ((1u << lane) - 1u));
-      out_pts[o] = pts[i]; out_pts[N + o] = pts[N + i]; out_pts[2 * N + o] = pts[2 * N + i];
-      if (colors) {
-        out_colors[o * 3 + 0] = colors[i * 3 + 0];
-        out_colors[o * 3 + 1] = colors[i * 3 + 1];
-        out_colors[o * 3 + 2] = colors[i * 3 + 2];
+      if (REC) {
+        reinterpret_cast<float4*>(out_pts)[o] = __ldg(reinterpret_cast<const float4*>(pts) + i);
+      } else {
+        const double* p = reinterpret_cast<const double*>(pts);
+        double* q = reinterpret_cast<double*>(out_pts);
+        q[o] = p[i]; q[N + o] = p[N + i]; q[2 * N + o] = p[2 * N + i];
+        if (colors) {
+          out_colors[o * 3 + 0] = colors[i * 3 + 0];
+          out_colors[o * 3 + 1] = colors[i * 3 + 1];
+          out_colors[o * 3 + 2] = colors[i * 3 + 2];
+        }
       }
     }
     run += total;
@@ -811,25 +830,36 @@ size_t filter_workspace_bytes(long long N) {
   return align_up(blocks * 4, 256) + align_up(blocks * 8, 256);
 }
 
-int launch_filter_box(const double* pts, const double* colors, long long N, double threshold,
-                      double* out_pts, double* out_colors, long long* out_count, void* ws,
-                      cudaStream_t st) {
+template <bool REC>
+static int filter_impl(const void* pts, const double* colors, long long N, double threshold, void* out_pts,
+                       double* out_colors, long long* out_count, void* ws, cudaStream_t st) {
   const long long blocks = (N + kFilterBlock - 1) / kFilterBlock;
   uint32_t* blk_cnt = static_cast<uint32_t*>(ws);
   long long* blk_base = reinterpret_cast<long long*>(static_cast<uint8_t*>(ws) + align_up((size_t)(blocks + 1) * 4, 256));
   if (blocks > 0) {
-    filter_count_kernel<<<(int)blocks, 256, 0, st>>>(pts, N, threshold, blk_cnt);
+    filter_count_kernel<REC><<<(int)blocks, 256, 0, st>>>(pts, N, threshold, blk_cnt);
     count_launch();
   }
   // B = 0: the scan writes only counts[0] = total kept
   colscan_kernel<<<1, 1024, 0, st>>>(blk_cnt, blk_base, blocks, 0, 1, out_count);
   count_launch();
   if (blocks > 0) {
-    filter_emit_kernel<<<(int)blocks, 256, 0, st>>>(pts, colors, N, threshold, blk_base, out_pts, out_colors);
+    filter_emit_kernel<REC><<<(int)blocks, 256, 0, st>>>(pts, colors, N, threshold, blk_base, out_pts, out_colors);
     count_launch();
   }
   SL_CUDA(cudaGetLastError());
   return kOk;
+}
+
+int launch_filter_box(const double* pts, const double* colors, long long N, double threshold,
+                      double* out_pts, double* out_colors, long long* out_count, void* ws,
+                      cudaStream_t st) {
+  return filter_impl<false>(pts, colors, N, threshold, out_pts, out_colors, out_count, ws, st);
+}
+
+int launch_filter_cloud(const float* cloud, long long N, double threshold, float* out_cloud,
+                        long long* out_count, void* ws, cudaStream_t st) {
+  return filter_impl<true>(cloud, nullptr, N, threshold, out_cloud, nullptr, out_count, ws, st);
 }
 
 }  // namespace sl

@@ -59,4 +59,7 @@ int launch_filter_box(const double* pts, const double* colors, long long N, doub
                       double* out_pts, double* out_colors, long long* out_count, void* ws,
                       cudaStream_t st);
 
+int launch_filter_cloud(const float* cloud, long long N, double threshold, float* out_cloud,
+                        long long* out_count, void* ws, cudaStream_t st);
+
 }  // namespace sl

@@ -387,6 +387,22 @@ def filter_box(pts: torch.Tensor, colors: Optional[torch.Tensor], threshold: flo
     return out_pts[:, :m], (out_col[:m] if out_col is not None else None)
 
 
+def filter_cloud_box(cloud: torch.Tensor, threshold: float = .5) -> torch.Tensor:
+    """Triangulate.filter_3d_pts (triangulate.py:99-122) on a packed XYZRGB cloud ``(N,4)`` f32 (CUDA):
+    keeps records with |x|,|y|,|z| < threshold, order preserved."""
+    if not (cloud.is_cuda and cloud.dtype == torch.float32 and cloud.dim() == 2 and cloud.shape[1] == 4):
+        raise TypeError("cloud must be a CUDA float32 (N,4) tensor")
+    cloud = cloud.contiguous()
+    n = cloud.shape[0]
+    out = torch.empty_like(cloud)
+    cnt = torch.empty(1, dtype=torch.int64, device=cloud.device)
+    nbytes = lib().sl_filter_workspace_bytes(n)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=cloud.device)
+    with torch.cuda.device(cloud.device):
+        check(lib().sl_filter_cloud_box(_ptr(cloud), n, float(threshold), _ptr(out), _ptr(cnt), _ptr(ws), nbytes, _stream()))
+    return out[: int(cnt.item())]
+
+
 def unpack_rgb(word: torch.Tensor) -> torch.Tensor:
     """Colour words (R | G<<8 | B<<16, int32 / float32 bit patterns) -> (N,3) uint8."""
     flat = torch.empty(word.shape, dtype=word.dtype, device=word.device)      # fresh, unit-stride storage

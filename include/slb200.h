@@ -171,6 +171,12 @@ int sl_filter_box(const double* pts, const double* colors, int64_t N, double thr
                   size_t workspace_bytes, void* stream);
 size_t sl_filter_workspace_bytes(int64_t N);
 
+/* The same filter on the packed XYZRGB cloud of sl_emit_cloud (src/4-triangulate.py:71 applied to the
+ * fast path's output): cloud device f32 (N,4) -> out_cloud (first M records), out_count device int64[1] = M.
+ * Coordinates are compared as doubles against `threshold`, like the reference compares its float64 points. */
+int sl_filter_cloud_box(const float* cloud, int64_t N, double threshold, float* out_cloud,
+                        int64_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* -------------------------------------------------------------- host-buffer pipeline */
 
 typedef struct SlPipeline SlPipeline;

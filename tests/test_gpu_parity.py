@@ -260,6 +260,21 @@ def test_filter_box_large_and_empty(T):
     assert fp.shape == (3, 0) and fc.shape == (0, 3)
 
 
+def test_filter_cloud_records(T):
+    """Box filter on the packed XYZRGB cloud == the reference filter applied to the same points."""
+    import slb200
+    rng = np.random.default_rng(6)
+    n = 70001
+    cloud = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    cloud[::11, 1] = np.nan
+    cloud[:, 3] = rng.integers(0, 1 << 24, n).astype(np.int32).view(np.float32)
+    kept = slb200.filter_cloud_box(T.from_numpy(cloud).cuda(), 0.5).cpu().numpy()
+    pts = cloud[:, :3].T.astype(np.float64)
+    ref_p, ref_idx = O.filter_3d_pts(pts, np.arange(n), 0.5)
+    np.testing.assert_array_equal(kept.view(np.int32), cloud[ref_idx].view(np.int32))
+    assert slb200.filter_cloud_box(T.zeros((0, 4), device="cuda"), 0.5).shape == (0, 4)
+
+
 def test_pairs_edge_cases(T):
     import slb200
     # nothing valid / everything valid / single column / ragged sizes
