@@ -124,13 +124,16 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
       const uint64_t pol = policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
-      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      // 32-bit tile bookkeeping (total_tiles < 2^31 is checked by the launcher); (b, tile) advance
+      // incrementally, a division only when a scan boundary is crossed
+      const uint32_t total = (uint32_t)a.total_tiles, tps = (uint32_t)a.tiles_per_scan, grid = gridDim.x;
+      uint32_t tile = blockIdx.x, b = 0;
+      for (uint32_t t = blockIdx.x; t < total; t += grid, tile += grid) {
+        if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
         mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
-        const int b = (int)(t / a.tiles_per_scan);
-        const int tile = (int)(t - (long long)b * a.tiles_per_scan);
         const uint32_t full = smem_u32(&bars[s]);
         mbar_arrive_expect_tx(full, stage_bytes);          // the box is always written in full
-        tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, tile * (kTilePx / 4), 0, b, full, pol);
+        tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)(tile * (kTilePx / 4)), 0, (int)b, full, pol);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -142,20 +145,27 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   // slow path (full rule evaluation) therefore delays nobody: the others keep claiming work up to
   // `stages - 1` tiles ahead of it.
   const int off_lane = lane * 4;
+  // 32-bit bookkeeping, advanced incrementally from claim to claim (claims of a warp are monotonic):
+  // ring slot s / phase ph of iteration `it`, and (scan b, tile in scan) of tile t = blockIdx.x + it * grid
+  const uint32_t total = (uint32_t)a.total_tiles, tps = (uint32_t)a.tiles_per_scan, grid = gridDim.x;
+  uint32_t it_prev = 0, s = 0, ph = 0, tile = blockIdx.x, b = 0;
   for (;;) {
     unsigned int sub = 0;
     if (lane == 0) sub = atomicAdd(next_sub, 1u);
     sub = __shfl_sync(0xffffffffu, sub, 0);
-    const long long it = sub / kSubTiles;
+    const uint32_t it = sub / kSubTiles;                 // kSubTiles is a power of two
     const int part = (int)(sub % kSubTiles);
-    const long long t = (long long)blockIdx.x + it * gridDim.x;
-    if (t >= a.total_tiles) break;
-    const int s = (int)(it % stages);
-    const uint32_t ph = (uint32_t)((it / stages) & 1);
+    const uint32_t t = blockIdx.x + it * grid;
+    if (t >= total) break;
+    const uint32_t delta = it - it_prev;
+    it_prev = it;
+    s += delta;
+    while (s >= (uint32_t)stages) { s -= (uint32_t)stages; ph ^= 1u; }
+    tile += delta * grid;
+    if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
     mbar_wait(smem_u32(&bars[s]), ph);
 
-    const long long b = t / a.tiles_per_scan;
-    const long long px0 = (t - b * a.tiles_per_scan) * (long long)kTilePx;
+    const long long px0 = (long long)tile * kTilePx;
     const long long rem = a.npix4 - px0;
     const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
     const int off = part * 128 + off_lane;                                 // pixel offset in tile
@@ -398,6 +408,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { tma_px = 0; }
     else {
+      if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
       a.stages = stages;
       const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16;
       const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
