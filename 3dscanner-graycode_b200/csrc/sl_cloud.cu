@@ -349,6 +349,12 @@ __device__ __forceinline__ void rays_to_point_fp64(float cx, float cy, float px,
   Z = dmul((double)lz, p_len);
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -364,7 +370,7 @@ __device__ __forceinline__ void rays_to_point_fp32(float cx, float cy, float px,
   const float bn = sqrt_approx(bx * bx + by * by + bz * bz);
   const float tc = t0 * cx + t1 * cy + t2;
   const float tp = t0 * px + t1 * py + t2;
-  const float s = __fdividef(c.t_len2f * bn, an * tp - tc * bn);
+  const float s = c.t_len2f * bn * rcp_approx(an * tp - tc * bn);     // 2 instructions; __fdividef adds range scaling
   X = cx * s; Y = cy * s; Z = s;
 }
 
@@ -399,6 +405,7 @@ struct EmitArgs {
   const float2* cam_rays;   // table modes: [H][W] undistorted camera rays (rotated by R)
   const float2* proj_rays;  // table modes: [proj_h][proj_w] undistorted projector rays
   int H, W, bands, tiles_x;
+  int off32;                // every packed offset fits 32 bits (B*H*W < 2^32): cheaper warp shuffles
   long long total_tiles;
   CalibDev cal;
 };
@@ -580,7 +587,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
   uint4* out = reinterpret_cast<uint4*>(a.out);
   for (int cidx = 0; cidx < cols; ++cidx) {
     const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, cidx));
-    const long long base = __shfl_sync(0xffffffffu, my_base, cidx);
+    const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, cidx)
+                                   : __shfl_sync(0xffffffffu, my_base, cidx);
     if (lane < cnt) {
       stg_u4_hint(out + base + lane, tile.rec[cidx * kRunPitch + lane], stream);
       if (MODE == kModePairs && a.out_rgb32) a.out_rgb32[base + lane] = tile.aux[cidx * kRunPitch + lane];
@@ -757,6 +765,7 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
   a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_bits = c.col_bits; a.col_base = c.col_base;
   a.out = out; a.out_rgb32 = out_rgb32; a.H = H; a.W = W; a.bands = c.bands;
   a.cam_rays = nullptr; a.proj_rays = nullptr;
+  a.off32 = ((long long)B * H * W < (1LL << 32)) ? 1 : 0;
   a.tiles_x = (W + kEmitCols - 1) / kEmitCols;
   a.total_tiles = (long long)a.tiles_x * a.bands * B;      // callers reject >= 2^31 (check_emit_size)
   return a;
