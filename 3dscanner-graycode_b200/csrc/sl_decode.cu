@@ -356,28 +356,7 @@ static int launch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, si
     SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured[dev & 63] = true;
   }
-#if defined(SL_DECODE_PRIORITY)
-  // Launch priority above the stage-2 kernels of other streams: when an SM frees up, the pending decode CTA
-  // (which needs most of the SM) is placed first and emit CTAs fill what is left, instead of five emit CTAs
-  // keeping the decode CTA out.
-  static int prio_hi[64];
-  static bool prio_known[64] = {false};
-  if (!prio_known[dev & 63]) {
-    int lo = 0, hi = 0;
-    SL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    prio_hi[dev & 63] = hi;
-    prio_known[dev & 63] = true;
-  }
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributePriority;
-  attr[0].val.priority = prio_hi[dev & 63];
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kDecodeThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  SL_CUDA(cudaLaunchKernelEx(&cfg, k, tmap, a));
-#else
   k<<<grid, kDecodeThreads, smem, st>>>(tmap, a);
-#endif
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
