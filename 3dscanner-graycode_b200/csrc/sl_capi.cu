@@ -47,6 +47,7 @@ static int device_gate(int* sms) {
     SL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     d.checked = 1; d.ok = (major == 10 && minor == 0); d.sms = n;
     if (!d.ok) { d.sms = -(major * 10 + minor); }
+    else { const int trc = init_device_tables(); if (trc) return trc; }
   }
   if (!d.ok) {
     set_error("slb200 is built for sm_100a only; device %d is sm_%d (no fallback path exists)", dev, -d.sms);

@@ -35,16 +35,41 @@ __global__ void binv_table_kernel() {
 }
 #endif
 
-static int ensure_binv_table(cudaStream_t st) {
 #if defined(SL_BINV_TABLE)
-  static bool ready[64] = {false};
+static bool g_binv_ready[64] = {false};
+#endif
+
+// Called once per device from the first C-ABI entry (sl_capi.cu: device_gate): fill the table on the
+// legacy default stream and wait, so that no later launch on any stream can race with the fill.  If the
+// calling thread is capturing a CUDA graph this is not possible; ensure_binv_table() then fills it in
+// stream order on first use.
+int init_device_tables() {
+#if defined(SL_BINV_TABLE)
   int dev = 0;
   SL_CUDA(cudaGetDevice(&dev));
-  if (!ready[dev & 63]) {
+  if (g_binv_ready[dev & 63]) return kOk;
+  binv_table_kernel<<<256, 256, 0, 0>>>();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  if (e == cudaSuccess) {
+    count_launch();
+    g_binv_ready[dev & 63] = true;
+  } else {
+    (void)cudaGetLastError();       // capture in progress: leave it to the stream-ordered path
+  }
+#endif
+  return kOk;
+}
+
+static int ensure_binv_table(cudaStream_t st) {
+#if defined(SL_BINV_TABLE)
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (!g_binv_ready[dev & 63]) {
     binv_table_kernel<<<256, 256, 0, st>>>();
     count_launch();
     SL_CUDA(cudaGetLastError());
-    ready[dev & 63] = true;
+    g_binv_ready[dev & 63] = true;
   }
 #else
   (void)st;

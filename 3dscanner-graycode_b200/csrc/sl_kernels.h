@@ -10,6 +10,7 @@ namespace sl {
 void count_launch();   // bumps the process-wide kernel launch counter
 
 // ---- stage 1 (sl_decode.cu)
+int init_device_tables();   // once per device: constant look-up tables of the decode kernel
 // valid_bitmap (nullable): flat validity bits, scan b at valid_bitmap + b*bitmap_words
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
