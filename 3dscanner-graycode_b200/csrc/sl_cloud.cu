@@ -100,10 +100,18 @@ __device__ __forceinline__ void block_scan_columns(const uint32_t* __restrict__ 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (long long base = 0; base < m; base += NT) {
-    const long long i = base + tid;
-    const long long x = i < m ? (long long)vals[i] : 0;
-    long long inc = x;
+  for (long long base = 0; base < m; base += NT * 4) {       // 4 consecutive values per thread and round
+    const long long i0 = base + (long long)tid * 4;
+    uint32_t x[4] = {0, 0, 0, 0};
+    if (i0 + 3 < m) {
+      const uint4 q = *reinterpret_cast<const uint4*>(vals + i0);        // vals is 256-byte aligned, i0 % 4 == 0
+      x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (i0 + k < m) x[k] = vals[i0 + k];
+    }
+    const long long p1 = (long long)x[0], p2 = p1 + x[1], p3 = p2 + x[2], sum = p3 + x[3];
+    long long inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const long long y = __shfl_up_sync(0xffffffffu, inc, d);
@@ -122,8 +130,10 @@ __device__ __forceinline__ void block_scan_columns(const uint32_t* __restrict__ 
     }
     __syncthreads();
     const long long carry = carry_s;
-    const long long before = carry + (warp ? warp_sum[warp - 1] : 0) + inc - x;
-    if (i < m) out[i] = before;
+    const long long before = carry + (warp ? warp_sum[warp - 1] : 0) + inc - sum;
+    const long long o[4] = {before, before + p1, before + p2, before + p3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i0 + k < m) out[i0 + k] = o[k];
     __syncthreads();
     if (tid == NT - 1) carry_s = carry + warp_sum[NW - 1];
     __syncthreads();
@@ -169,21 +179,33 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
   const int x0 = strip * kStripCols, x = x0 + lane;
   const uint32_t* bm = bitmap + (size_t)b * words_per_scan;
   const uint32_t colmask = (W - x0 >= 32) ? 0xffffffffu : ((1u << (W - x0)) - 1u);
-  for (int band = warp; band < bands; band += kStripWarps) {
-    const int y = band * kBandRows + lane;
-    uint32_t rowword = 0;
-    if (y < H) {
-      const long long i = (long long)y * W + x0;
-      rowword = __funnelshift_r(bm[i >> 5], bm[(i >> 5) + 1], (uint32_t)(i & 31)) & colmask;
-    }
-    uint32_t colword = 0;
+  constexpr int kPrefetch = 4;                  // bands whose row words are fetched before any is transposed
+  for (int band0 = warp; band0 < bands; band0 += kStripWarps * kPrefetch) {
+    uint32_t rw[kPrefetch];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const uint32_t bits = __ballot_sync(0xffffffffu, (rowword >> c) & 1u);
-      if (lane == c) colword = bits;
+    for (int j = 0; j < kPrefetch; ++j) {
+      const int band = band0 + j * kStripWarps;
+      const int y = band * kBandRows + lane;
+      rw[j] = 0;
+      if (band < bands && y < H) {
+        const long long i = (long long)y * W + x0;
+        rw[j] = __funnelshift_r(__ldg(bm + (i >> 5)), __ldg(bm + (i >> 5) + 1), (uint32_t)(i & 31)) & colmask;
+      }
     }
-    cnt[band * 32 + lane] = __popc(colword);
-    if (x < W) col_bits[((size_t)b * bands + band) * W + x] = colword;    // bit r = pixel (band*32+r, x) valid
+#pragma unroll
+    for (int j = 0; j < kPrefetch; ++j) {
+      const int band = band0 + j * kStripWarps;
+      if (band >= bands) break;                 // warp-uniform
+      const uint32_t rowword = rw[j];
+      uint32_t colword = 0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, (rowword >> c) & 1u);
+        if (lane == c) colword = bits;
+      }
+      cnt[band * 32 + lane] = __popc(colword);
+      if (x < W) col_bits[((size_t)b * bands + band) * W + x] = colword;    // bit r = pixel (band*32+r, x) valid
+    }
   }
   __syncthreads();
   if (warp == 0) {                              // prefix down the column (bands <= ~70 in practice)
