@@ -1,5 +1,5 @@
-// sm_100a plumbing shared by the kernels: mbarrier + cp.async.bulk (TMA bulk copy)
-// PTX wrappers, error codes, launch helpers.
+// sm_100a plumbing shared by the kernels: mbarrier + TMA tensor-load PTX wrappers, L2 cache-policy
+// loads/stores, error codes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,15 +63,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted on an mbarrier.
-// dst/src 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
-                                         uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
-}
-
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -123,7 +114,5 @@ __device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) {
 }
 
 #endif  // __CUDACC__
-
-inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace sl

@@ -104,7 +104,7 @@ class Triangulate(object):
         bufs = slb200.api.CloudBuffers.allocate(1, self.cam_h, self.cam_w, dev)
         bufs.h_idx.copy_(h_idx.view(1, self.cam_h, self.cam_w))
         bufs.v_idx.copy_(v_idx.view(1, self.cam_h, self.cam_w))
-        from slb200.api import _Offsets, _ptr, _stream, _PREC, check, lib  # noqa
+        from slb200.api import _ptr, _stream, _PREC, check, lib
         import ctypes as C
         s = self._calibration().struct()
         with torch.cuda.device(dev):

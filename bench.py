@@ -21,7 +21,6 @@ host cores for the driver's ratio.
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import sys
