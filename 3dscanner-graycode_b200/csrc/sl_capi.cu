@@ -137,6 +137,16 @@ int sl_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int 
   return launch_codes_to_pixels(h_codes, v_codes, R, n, npix, run_pitch, h_idx, v_idx, sms, (cudaStream_t)stream);
 }
 
+int sl_pattern_sequence_u8(int proj_w, int proj_h, uint8_t* out, void* stream) {
+  if (proj_w < 2 || proj_h < 1 || !out) { set_error("bad argument"); return kErrBadArg; }
+  int n = 0;
+  while ((1 << n) < (proj_w > proj_h ? proj_w : proj_h)) ++n;       // ceil(log2(max(w, h))), generate_codes.py:22-25
+  if (n < 1 || n > 16) { set_error("panel size out of range"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_patterns(proj_w, proj_h, n, out, sms, (cudaStream_t)stream);
+}
+
 int sl_bgr_to_gray_u8(const uint8_t* bgr, int64_t npix, uint8_t* gray, void* stream) {
   if (npix < 0 || (npix > 0 && (!bgr || !gray))) { set_error("bad argument"); return kErrBadArg; }
   int sms = 0, rc;

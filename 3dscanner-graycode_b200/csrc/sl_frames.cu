@@ -67,6 +67,45 @@ __global__ void __launch_bounds__(256) pair_diff_kernel(const uint8_t* __restric
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + k, (unsigned long long)c);
 }
 
+// Projector pattern sequence (scanner/grayCode/generate_codes.py:34-81) written straight into device memory:
+// frame 0 black, 1 white, 2+2j column bit j (MSB first), 3+2k row bit k (LSB first), +2n the inverses;
+// portrait panels (height > width) get all-black patterns like the reference (stripe width 0).
+__global__ void __launch_bounds__(256) pattern_kernel(int pw, int ph, int n, uint8_t* __restrict__ out) {
+  const long long npix = (long long)pw * ph;
+  const long long total = npix * (4 * n + 2);
+  const bool draw = pw >= ph;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / npix);
+    const long long p = i - (long long)f * npix;
+    const int y = (int)(p / pw), x = (int)(p - (long long)y * pw);
+    uint8_t val = 0;
+    if (f == 1) val = 255;
+    else if (f >= 2) {
+      const int g = f - 2;
+      const bool inverse = g >= 2 * n;
+      const int k = inverse ? g - 2 * n : g;
+      if (draw) {
+        uint32_t bit;
+        if ((k & 1) == 0) { const uint32_t gray = (uint32_t)x ^ ((uint32_t)x >> 1); bit = (gray >> (n - 1 - (k >> 1))) & 1u; }
+        else              { const uint32_t gray = (uint32_t)y ^ ((uint32_t)y >> 1); bit = (gray >> (k >> 1)) & 1u; }
+        val = (bit ^ (inverse ? 1u : 0u)) ? 255 : 0;
+      }
+    }
+    out[i] = val;
+  }
+}
+
+int launch_patterns(int pw, int ph, int n, uint8_t* out, int num_sms, cudaStream_t st) {
+  const long long total = (long long)pw * ph * (4 * n + 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms * 32) blocks = (long long)num_sms * 32;
+  pattern_kernel<<<(int)blocks, 256, 0, st>>>(pw, ph, n, out);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int launch_bgr_to_gray(const uint8_t* bgr, long long npix, uint8_t* gray, int num_sms, cudaStream_t st) {
   if (npix == 0) return kOk;
   long long blocks = ((npix >> 2) + 255) / 256;

@@ -24,6 +24,7 @@ int launch_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, 
                            int num_sms, cudaStream_t st);
 
 // ---- capture front end (sl_frames.cu)
+int launch_patterns(int pw, int ph, int n, uint8_t* out, int num_sms, cudaStream_t st);
 int launch_bgr_to_gray(const uint8_t* bgr, long long npix, uint8_t* gray, int num_sms, cudaStream_t st);
 int launch_pair_diff(const uint8_t* frames, int n_frames, long long elems, size_t frame_pitch, int thresh,
                      unsigned long long* counts, int num_sms, cudaStream_t st);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sl_direct_indirect": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp]),
     "sl_is_lit": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _d, _vp, _vp, _vp]),
     "sl_codes_to_pixels": (_i, [_vp, _vp, _i, _i, _i64, _sz, _vp, _vp, _vp]),
+    "sl_pattern_sequence_u8": (_i, [_i, _i, _vp, _vp]),
     "sl_bgr_to_gray_u8": (_i, [_vp, _i64, _vp, _vp]),
     "sl_pair_diff_counts": (_i, [_vp, _i, _i64, _sz, _i, _vp, _vp]),
     "sl_cloud_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -153,6 +153,19 @@ def _check_stack(frames: torch.Tensor):
 
 
 # --------------------------------------------------------------------------- capture front end
+def pattern_sequence(proj_size: Tuple[int, int], device=None) -> torch.Tensor:
+    """The projector's Gray-code frame sequence ``(4n+2, proj_h, proj_w)`` uint8, generated on the device
+    (same frames as generate_codes.get_image_sequence, reference generate_codes.py:34-81)."""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    pw, ph = int(proj_size[0]), int(proj_size[1])
+    n = max(1, int(np.ceil(np.log2(max(pw, ph)))))
+    out = torch.empty((4 * n + 2, ph, pw), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().sl_pattern_sequence_u8(pw, ph, _ptr(out), _stream()))
+    return out
+
+
 def bgr_to_gray(bgr: torch.Tensor) -> torch.Tensor:
     """cv2.cvtColor(BGR2GRAY) of uint8 CUDA frames ``(..., 3)`` -> ``(...)`` uint8
     (src/3-capture_decode.py:66, decode_codes.py:86)."""

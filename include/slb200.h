@@ -98,6 +98,10 @@ int sl_codes_to_pixels(const int8_t* h_codes, const int8_t* v_codes, int R, int 
 
 /* ------------------------------------------------------------- capture front end */
 
+/* get_image_sequence(get_gray_codes(w, h), w, h) (scanner/grayCode/generate_codes.py:5-81) generated in device
+ * memory: out device u8 [4n+2][proj_h][proj_w], n = ceil(log2(max(proj_w, proj_h))). */
+int sl_pattern_sequence_u8(int proj_w, int proj_h, uint8_t* out, void* stream);
+
 /* cv2.cvtColor(frame, COLOR_BGR2GRAY) on 8-bit frames, as src/3-capture_decode.py:66 and to_gray
  * (scanner/grayCode/decode_codes.py:70-87) apply it before the decode:
  * gray = (3735*B + 19235*G + 9798*R + 16384) >> 15.  bgr device u8 [npix][3], gray device u8 [npix]. */

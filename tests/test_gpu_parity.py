@@ -508,6 +508,21 @@ def test_dropin_scripts_flow(T):
     Triangulate()                                                 # all-default constructor (src/4-triangulate.py:24)
 
 
+@pytest.mark.parametrize("size", [(16, 8), (32, 32), (24, 10), (8, 16), (1024, 768), (1920, 1080)])
+def test_pattern_sequence_on_device(T, golden_dir, size):
+    """the projector sequence generated on the GPU == the host generator (itself pinned to the
+    reference by golden vectors)."""
+    import slb200
+    from scanner.grayCode.generate_codes import get_gray_codes, get_image_sequence
+    pw, ph = size
+    dev = slb200.pattern_sequence(size).cpu().numpy()
+    host = get_image_sequence(get_gray_codes(pw, ph), pw, ph)
+    np.testing.assert_array_equal(dev, host)
+    g = np.load(os.path.join(golden_dir, "decode_golden.npz"))
+    if f"patterns_{pw}x{ph}" in g.files:
+        np.testing.assert_array_equal(dev, g[f"patterns_{pw}x{ph}"])
+
+
 def test_front_end_to_gray_and_remove_bad_images(T, golden_dir):
     """cv2 BGR2GRAY (to_gray) and the transition-frame rejection (remove_bad_images)."""
     import slb200
