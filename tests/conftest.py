@@ -14,6 +14,15 @@ REFERENCE = "/root/reference"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # The extension is built in-tree by __graft_entry__.build() and travels with the snapshot; if a fresh
+    # checkout has no library yet and nvcc is available, build it once so the suite can run.
+    lib = os.path.join(PKG, "lib", "libslb200.so")
+    if not os.path.exists(lib):
+        try:
+            import __graft_entry__ as entry
+            entry.build()
+        except Exception as exc:      # the tests that need the library will fail loudly
+            print(f"[conftest] could not build libslb200.so: {exc}")
 
 
 def pytest_collection_modifyitems(config, items):
