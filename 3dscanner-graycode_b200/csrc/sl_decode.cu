@@ -91,7 +91,6 @@ constexpr int kTilePx = SL_TILE_PX;           // pixels per stage row (bytes per
 constexpr int kSubTiles = kTilePx / 128;      // a warp handles 128 px (32 lanes * 4 px) at a time
 constexpr int kConsumerWarps = SL_CONSUMER_WARPS;
 constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;   // + 1 producer warp
-static_assert(kConsumerWarps % kSubTiles == 0, "end markers are issued per ring slot of kSubTiles sub-tiles");
 constexpr int kMaxStages = SL_MAX_STAGES;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -107,21 +106,9 @@ struct DecodeArgs {
   unsigned int* ticket;  // nullable: compaction workspace ticket, zeroed here (see strip_prefix_kernel)
   long long npix;        // pixels per scan
   long long npix4;       // npix rounded down to a multiple of 4 (part handled by this kernel)
-  // Work is the "virtual" pixel axis of all scans, each padded to a multiple of 128 pixels; CTA c owns the
-  // contiguous range [c * range_px, (c+1) * range_px) of it (range_px is a multiple of 128).
-  unsigned long long padded_px;   // per scan
-  unsigned long long total_px;    // B * padded_px
-  unsigned long long range_px;
+  long long total_tiles; // B * tiles_per_scan
+  int tiles_per_scan;
   int n, F, e, stages;
-};
-
-// Written by the producer into shared memory for every ring slot, read by the consumers after the slot's
-// full-barrier: which pixels the slot holds.  len == 0 marks the end of the CTA's work.
-struct TileHdr {
-  uint32_t b;      // scan
-  uint32_t px;     // first pixel inside the scan (multiple of 128)
-  uint32_t len;    // pixels of the tile that exist (multiple of 4, <= kTilePx)
-  uint32_t pad;
 };
 
 // Register cap: the decode CTA (544 threads, 188 KB of shared memory) leaves room on the SM for one emit
@@ -140,9 +127,8 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   const int stages = a.stages;
   const uint32_t stage_bytes = (uint32_t)F * kTilePx;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-  // bars[0..stages) = full, bars[stages..2*stages) = empty; then the tile headers and the sub-tile claim counter
-  TileHdr* hdrs = reinterpret_cast<TileHdr*>(bars + 2 * stages);
-  unsigned int* next_sub = reinterpret_cast<unsigned int*>(hdrs + stages);
+  // bars[0..stages) = full, bars[stages..2*stages) = empty; then the sub-tile claim counter
+  unsigned int* next_sub = reinterpret_cast<unsigned int*>(bars + 2 * stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -163,33 +149,16 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
       const uint64_t pol = policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
-      unsigned long long v = (unsigned long long)blockIdx.x * a.range_px;
-      unsigned long long end = v + a.range_px;
-      if (end > a.total_px) end = a.total_px;
-      uint32_t b = (uint32_t)(v / a.padded_px);
-      unsigned long long px = v - (unsigned long long)b * a.padded_px;
-      while (v < end) {
-        unsigned long long len = end - v;
-        if (len > (unsigned long long)kTilePx) len = kTilePx;
-        if (len > a.padded_px - px) len = a.padded_px - px;
-        const long long have = a.npix4 - (long long)px;              // pixels of this scan from px on (<= 0 in the padding)
-        const uint32_t valid = have <= 0 ? 0u : (uint32_t)(have < (long long)len ? have : (long long)len);
-        if (valid) {
-          mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
-          hdrs[s].b = b; hdrs[s].px = (uint32_t)px; hdrs[s].len = valid;
-          const uint32_t full = smem_u32(&bars[s]);
-          mbar_arrive_expect_tx(full, stage_bytes);          // the box is always written in full (zero fill)
-          tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)(px >> 2), 0, (int)b, full, pol);
-          if (++s == stages) { s = 0; ph ^= 1u; }
-        }
-        v += len; px += len;
-        if (px >= a.padded_px) { px = 0; ++b; }
-      }
-      // one end marker per consumer warp: kConsumerWarps sub-tiles = kConsumerWarps / kSubTiles ring slots
-      for (int k = 0; k < kConsumerWarps / kSubTiles; ++k) {
+      // 32-bit tile bookkeeping (total_tiles < 2^31 is checked by the launcher); (b, tile) advance
+      // incrementally, a division only when a scan boundary is crossed
+      const uint32_t total = (uint32_t)a.total_tiles, tps = (uint32_t)a.tiles_per_scan, grid = gridDim.x;
+      uint32_t tile = blockIdx.x, b = 0;
+      for (uint32_t t = blockIdx.x; t < total; t += grid, tile += grid) {
+        if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
         mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
-        hdrs[s].len = 0;
-        mbar_arrive(smem_u32(&bars[s]));
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);          // the box is always written in full
+        tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)(tile * (kTilePx / 4)), 0, (int)b, full, pol);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -199,28 +168,31 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   // -------------------------------------------------------------- consumers
   // All consumer warps draw 128-pixel sub-tiles from one counter, in ring order.  A warp that hits the
   // slow path (full rule evaluation) therefore delays nobody: the others keep claiming work up to
-  // `stages - 1` tiles ahead of it.  Ring slot s / phase ph advance incrementally from claim to claim.
+  // `stages - 1` tiles ahead of it.
   const int off_lane = lane * 4;
-  uint32_t it_prev = 0, s = 0, ph = 0;
+  // 32-bit bookkeeping, advanced incrementally from claim to claim (claims of a warp are monotonic):
+  // ring slot s / phase ph of iteration `it`, and (scan b, tile in scan) of tile t = blockIdx.x + it * grid
+  const uint32_t total = (uint32_t)a.total_tiles, tps = (uint32_t)a.tiles_per_scan, grid = gridDim.x;
+  uint32_t it_prev = 0, s = 0, ph = 0, tile = blockIdx.x, b = 0;
   for (;;) {
     unsigned int sub = 0;
     if (lane == 0) sub = atomicAdd(next_sub, 1u);
     sub = __shfl_sync(0xffffffffu, sub, 0);
     const uint32_t it = sub / kSubTiles;                 // kSubTiles is a power of two
     const int part = (int)(sub % kSubTiles);
-    s += it - it_prev;
+    const uint32_t t = blockIdx.x + it * grid;
+    if (t >= total) break;
+    const uint32_t delta = it - it_prev;
     it_prev = it;
+    s += delta;
     while (s >= (uint32_t)stages) { s -= (uint32_t)stages; ph ^= 1u; }
+    tile += delta * grid;
+    if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
     mbar_wait(smem_u32(&bars[s]), ph);
-    const TileHdr hdr = hdrs[s];
-    if (hdr.len == 0) {                                   // end marker: release it and stop
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));
-      break;
-    }
-    const uint32_t b = hdr.b;
-    const long long px0 = (long long)hdr.px;
-    const int cnt = (int)hdr.len;
+
+    const long long px0 = (long long)tile * kTilePx;
+    const long long rem = a.npix4 - px0;
+    const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
     const int off = part * 128 + off_lane;                                 // pixel offset in tile
     uint32_t nib = 0;
     if (off < cnt) {
@@ -239,7 +211,7 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
       nib = ((o.valid & kMsb4) * 0x00204081u) >> 28;      // the 4 msb flags gathered into bits 0..3
     }
     if (a.bitmap) {
-      // 8 neighbouring lanes hold the 32 validity bits of 32 consecutive pixels (tiles start at multiples of 128)
+      // 8 neighbouring lanes hold the 32 validity bits of 32 consecutive pixels
       const uint32_t word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
       if ((lane & 7) == 0 && px0 + off < a.npix)
         a.bitmap[(size_t)b * a.bitmap_words + ((px0 + off) >> 5)] = word;
@@ -453,20 +425,18 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
     a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket;
     a.npix = npix; a.npix4 = tma_px;
-    a.padded_px = ((unsigned long long)tma_px + 127ull) & ~127ull;
-    a.total_px = a.padded_px * (unsigned long long)B;
+    a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
+    a.total_tiles = (long long)a.tiles_per_scan * B;
     a.n = n; a.F = F; a.e = (int)eps;
     const size_t stage_bytes = (size_t)F * kTilePx;
     int stages = (int)((kSmemBudget - 256) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { tma_px = 0; }
     else {
+      if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
       a.stages = stages;
-      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + stages * sizeof(TileHdr) + 16;
-      const unsigned long long tiles = (a.total_px + kTilePx - 1) / kTilePx;
-      const int grid = (int)(tiles < (unsigned long long)num_sms ? tiles : (unsigned long long)num_sms);
-      // equal contiguous ranges (multiples of 128 pixels): every CTA gets the same amount of work
-      a.range_px = (((a.total_px + grid - 1) / grid) + 127ull) & ~127ull;
+      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16;
+      const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
       CUtensorMap tmap;
       int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch);
       if (rc != kOk) return rc;
