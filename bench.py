@@ -233,15 +233,6 @@ def run_gpu(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
-    if world > 1 and not args.no_affinity:
-        # spread the ranks over the host's cores so their pinned staging buffers (first touch) and copy
-        # threads do not pile up on one NUMA node
-        try:
-            cores = sorted(os.sched_getaffinity(0))
-            per = max(1, len(cores) // world)
-            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]))
-        except Exception:
-            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -460,7 +451,6 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--ring", type=int, default=RING)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-affinity", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
