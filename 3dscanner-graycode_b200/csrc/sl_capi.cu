@@ -261,6 +261,24 @@ int sl_filter_cloud_box(const float* cloud, int64_t N, double threshold, float* 
   return launch_filter_cloud(cloud, N, threshold, out_cloud, (long long*)out_count, workspace, (cudaStream_t)stream);
 }
 
+size_t sl_outlier_workspace_bytes(int64_t N) { return (N < 0 || N > (1LL << 30)) ? 0 : outlier_workspace_bytes(N); }
+
+int sl_remove_statistical_outliers(const float* cloud, int64_t N, int nb_neighbors, double std_ratio,
+                                   float* out_cloud, int64_t* out_index, double* mean_dist, double* stats,
+                                   int64_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N < 0 || N > (1LL << 30)) { set_error("N out of range (0..2^30)"); return kErrBadArg; }
+  // Open3D: "the number of neighbors and standard deviation ratio must be positive"
+  if (nb_neighbors < 1 || !(std_ratio > 0.0)) { set_error("nb_neighbors and std_ratio must be positive"); return kErrBadArg; }
+  if (nb_neighbors > 128) { set_error("nb_neighbors up to 128 supported (got %d)", nb_neighbors); return kErrBadArg; }
+  if (!out_count || !workspace) { set_error("null buffer"); return kErrBadArg; }
+  if (N > 0 && !cloud) { set_error("null buffer"); return kErrBadArg; }
+  if (workspace_bytes < outlier_workspace_bytes(N)) { set_error("workspace too small"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_outlier_removal(cloud, N, nb_neighbors, std_ratio, out_cloud, (long long*)out_index, mean_dist, stats,
+                                (long long*)out_count, workspace, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ host-buffer pipeline
 struct SlPipeline {
   int device = 0, max_batch = 0, F = 0, H = 0, W = 0, sms = 0;

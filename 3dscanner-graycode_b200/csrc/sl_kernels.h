@@ -64,4 +64,10 @@ int launch_filter_box(const double* pts, const double* colors, long long N, doub
 int launch_filter_cloud(const float* cloud, long long N, double threshold, float* out_cloud,
                         long long* out_count, void* ws, cudaStream_t st);
 
+// ---- cloud clean-up (sl_outlier.cu)
+size_t outlier_workspace_bytes(long long N);
+int launch_outlier_removal(const float* cloud, long long N, int nb_neighbors, double std_ratio, float* out_cloud,
+                           long long* out_index, double* mean_dist, double* stats, long long* out_count, void* ws,
+                           cudaStream_t st);
+
 }  // namespace sl

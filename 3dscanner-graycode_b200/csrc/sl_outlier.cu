@@ -1,0 +1,474 @@
+// Statistical outlier removal on the packed XYZRGB cloud (sm_100a) -- the clean-up the reference applies
+// right after the hot path: pcd.remove_statistical_outlier(nb_neighbors=20, std_ratio=0.5),
+// scanner/utils/visualize.py:104-105 (Open3D 0.17 PointCloud::RemoveStatisticalOutliers).
+//
+// Exact k-nearest-neighbour mean distances on a hashed uniform grid, no KD-tree:
+//   * cells of side s are hashed (64-bit cell id -> open-addressing table of >= 2N slots), points are
+//     counting-sorted by cell (atomics only; the order inside a cell does not influence any result
+//     because each query keeps its k smallest squared distances SORTED and sums them nearest first);
+//   * a query scans the 3x3x3 block of cells around its own cell and is final when its k-th distance is
+//     not larger than the distance to the faces of that block (nothing outside can be closer);
+//   * the few queries that are not final (sparse noise points) are retried on a grid with 4x larger
+//     cells, up to kLevels times; the last level covers the whole bounding box with <= 2 cells per axis.
+//   s of level 0 is chosen from a pilot build so that occupied cells hold ~kTargetOcc points.
+// Distances: float32 coordinates (the reference narrows to float32, visualize.py:100), differences,
+// squares and the (dx^2 + dy^2) + dz^2 sum in float64 with one rounding per operation, sqrt and the mean in
+// float64 -- the per-point mean distances are bit-identical to the oracle's.  The cloud mean / standard
+// deviation are fixed-order tree reductions (deterministic; last-ulp differences from a sequential sum).
+// Everything is stream-ordered: no host synchronisation, work sizes live in device memory.
+#include <cuda_runtime.h>
+#include <math.h>
+#include "sl_common.cuh"
+#include "sl_kernels.h"
+
+namespace sl {
+
+constexpr int kLevels = 12;             // cell side s0 * 4^level; s0 >= extent / 2^20, so level 11 has <= 2 cells per axis
+constexpr double kTargetOcc = 6.0;      // points per occupied cell at level 0 (~100 candidates per query on a surface,
+                                        // ~1 % of the surface queries retried one level up)
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kSorBlocks = 148 * 4;     // grid of the grid-stride kernels
+constexpr int kRedBlocks = 256;         // partial sums of the two reductions
+constexpr int kCompactBlock = 1024;
+
+struct SorParams {
+  uint32_t bb[6];                  // order-preserving uint images of min x,y,z / max x,y,z
+  uint32_t n_finite;
+  uint32_t occupied;               // distinct cells of the pilot build
+  uint32_t cursor;                 // range allocator of the counting sort
+  uint32_t counts[kLevels + 1];    // queries pending at each level
+  double org[3], ext[3];
+  double cell[kLevels];            // cell side per level
+  int dim[kLevels][3];
+  double mean, stddev, thr;
+};
+
+struct SorWs {
+  SorParams* prm;
+  unsigned long long* keys;   // [M]
+  uint32_t* cnt;              // [M]
+  uint32_t* start;            // [M]  after the scatter: END of the cell's range in `sorted`
+  uint32_t* slot;             // [N]
+  float4* sorted;             // [N]  xyz + original index
+  double* avg;                // [N]
+  uint32_t* pend[2];          // [N]
+  double* part;               // [2 * kRedBlocks]
+  uint32_t* blk_cnt;          // [blocks + 1]
+  long long* blk_base;        // [blocks + 1]
+  uint32_t M;
+};
+
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+static uint32_t table_size(long long N) {
+  uint64_t m = 1024;
+  while (m < (uint64_t)N * 2) m <<= 1;
+  return (uint32_t)m;
+}
+
+static size_t sor_carve(void* base, long long N, SorWs* w) {
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  const uint32_t M = table_size(N);
+  const size_t n = (size_t)(N < 1 ? 1 : N);
+  const size_t blocks = (n + kCompactBlock - 1) / kCompactBlock + 1;
+  auto take = [&](size_t bytes) { uint8_t* q = p ? p + off : nullptr; off += up256(bytes); return q; };
+  SorWs s;
+  s.prm = (SorParams*)take(sizeof(SorParams));
+  s.keys = (unsigned long long*)take((size_t)M * 8);
+  s.cnt = (uint32_t*)take((size_t)M * 4);
+  s.start = (uint32_t*)take((size_t)M * 4);
+  s.slot = (uint32_t*)take(n * 4);
+  s.sorted = (float4*)take(n * 16);
+  s.avg = (double*)take(n * 8);
+  s.pend[0] = (uint32_t*)take(n * 4);
+  s.pend[1] = (uint32_t*)take(n * 4);
+  s.part = (double*)take(2 * kRedBlocks * 8);
+  s.blk_cnt = (uint32_t*)take(blocks * 4);
+  s.blk_base = (long long*)take(blocks * 8);
+  s.M = M;
+  if (w) *w = s;
+  return off;
+}
+
+size_t outlier_workspace_bytes(long long N) { return sor_carve(nullptr, N, nullptr); }
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t ord_u32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_f32(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ bool finite3(const float4& q) { return isfinite(q.x) && isfinite(q.y) && isfinite(q.z); }
+
+__device__ __forceinline__ int cell_of(double u, double inv, int dim) {
+  int c = (int)floor(u * inv);
+  return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+}
+__device__ __forceinline__ unsigned long long cell_key(int cx, int cy, int cz) {
+  return (unsigned long long)cx | ((unsigned long long)cy << 21) | ((unsigned long long)cz << 42);
+}
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k, uint32_t mask) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k & mask;
+}
+
+// ------------------------------------------------------------------ planning
+__global__ void sor_init_kernel(SorParams* prm) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { prm->bb[i] = 0xffffffffu; prm->bb[3 + i] = 0u; }
+    prm->n_finite = 0; prm->occupied = 0; prm->cursor = 0;
+    for (int i = 0; i <= kLevels; ++i) prm->counts[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) sor_bbox_kernel(const float4* __restrict__ cloud, long long N, SorParams* prm,
+                                                        double* __restrict__ avg) {
+  uint32_t lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u}, nf = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const float4 q = __ldg(cloud + i);
+    if (!finite3(q)) { avg[i] = -1.0; continue; }     // dropped: never a neighbour, never an inlier
+    const uint32_t u[3] = {ord_u32(q.x), ord_u32(q.y), ord_u32(q.z)};
+    for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], u[a]); hi[a] = max(hi[a], u[a]); }
+    ++nf;
+  }
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+    hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+  }
+  nf = __reduce_add_sync(0xffffffffu, nf);
+  if ((threadIdx.x & 31) == 0 && nf) {
+    for (int a = 0; a < 3; ++a) { atomicMin(&prm->bb[a], lo[a]); atomicMax(&prm->bb[3 + a], hi[a]); }
+    atomicAdd(&prm->n_finite, nf);
+  }
+}
+
+__device__ void sor_set_levels(SorParams* prm, double s0) {
+  double lmax = fmax(prm->ext[0], fmax(prm->ext[1], prm->ext[2]));
+  const double floor_s = lmax / 1048576.0;           // <= 2^20 cells per axis (21-bit key fields)
+  if (!(s0 > floor_s)) s0 = floor_s;
+  if (!(s0 > 0.0)) s0 = 1.0;                          // all points coincide
+  for (int l = 0; l < kLevels; ++l) {
+    prm->cell[l] = s0;
+    for (int a = 0; a < 3; ++a) prm->dim[l][a] = (int)floor(prm->ext[a] / s0) + 1;
+    s0 *= 4.0;
+  }
+}
+
+// pilot cell side from the bounding box: a surface of area (two largest extents) holding n_finite points
+__global__ void sor_plan_pilot_kernel(SorParams* prm) {
+  if (threadIdx.x) return;
+  const uint32_t nf = prm->n_finite;
+  if (nf == 0) { for (int a = 0; a < 3; ++a) { prm->org[a] = 0; prm->ext[a] = 0; } sor_set_levels(prm, 1.0); return; }
+  double e[3];
+  for (int a = 0; a < 3; ++a) {
+    const double lo = (double)ord_f32(prm->bb[a]), hi = (double)ord_f32(prm->bb[3 + a]);
+    prm->org[a] = lo; prm->ext[a] = e[a] = hi - lo;
+  }
+  const double l1 = fmax(e[0], fmax(e[1], e[2])), l3 = fmin(e[0], fmin(e[1], e[2]));
+  const double l2 = e[0] + e[1] + e[2] - l1 - l3;
+  double s = sqrt(kTargetOcc * l1 * l2 / (double)nf);
+  if (!(s > 0.0)) s = kTargetOcc * l1 / (double)nf;
+  sor_set_levels(prm, s);
+}
+
+// level-0 cell side from the pilot's occupancy (points per occupied cell scale ~ s^2 on a surface)
+__global__ void sor_plan_final_kernel(SorParams* prm) {
+  if (threadIdx.x) return;
+  const uint32_t nf = prm->n_finite;
+  if (nf == 0) return;
+  const double occ = (double)nf / (double)(prm->occupied ? prm->occupied : 1u);
+  sor_set_levels(prm, prm->cell[0] * sqrt(kTargetOcc / occ));
+  prm->counts[0] = nf;
+}
+
+// ------------------------------------------------------------------ grid build (one level)
+__global__ void __launch_bounds__(256) sor_clear_kernel(SorParams* prm, int level, unsigned long long* __restrict__ keys,
+                                                         uint32_t* __restrict__ cnt, uint32_t M) {
+  if (level >= 0 && prm->counts[level] == 0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) prm->cursor = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    keys[i] = kEmptyKey;
+    cnt[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) sor_insert_kernel(const float4* __restrict__ cloud, long long N, SorParams* prm,
+                                                          int level, unsigned long long* keys, uint32_t* cnt,
+                                                          uint32_t mask, uint32_t* __restrict__ slot) {
+  const int lv = level < 0 ? 0 : level;
+  if (level >= 0 && prm->counts[level] == 0) return;
+  const double inv = 1.0 / prm->cell[lv];
+  const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
+  const int dx = prm->dim[lv][0], dy = prm->dim[lv][1], dz = prm->dim[lv][2];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const float4 q = __ldg(cloud + i);
+    if (!finite3(q)) continue;
+    const unsigned long long key = cell_key(cell_of((double)q.x - ox, inv, dx), cell_of((double)q.y - oy, inv, dy),
+                                            cell_of((double)q.z - oz, inv, dz));
+    uint32_t h = hash_key(key, mask);
+    for (;;) {
+      const unsigned long long old = atomicCAS(&keys[h], kEmptyKey, key);
+      if (old == kEmptyKey) { if (level < 0) atomicAdd(&prm->occupied, 1u); break; }
+      if (old == key) break;
+      h = (h + 1) & mask;
+    }
+    if (level >= 0) { atomicAdd(&cnt[h], 1u); slot[i] = h; }
+  }
+}
+
+__global__ void __launch_bounds__(256) sor_alloc_kernel(SorParams* prm, int level, const uint32_t* __restrict__ cnt,
+                                                         uint32_t* __restrict__ start, uint32_t M) {
+  if (prm->counts[level] == 0) return;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    const uint32_t c = cnt[i];
+    if (c) start[i] = atomicAdd(&prm->cursor, c);
+  }
+}
+
+__global__ void __launch_bounds__(256) sor_scatter_kernel(const float4* __restrict__ cloud, long long N, SorParams* prm,
+                                                           int level, const uint32_t* __restrict__ slot,
+                                                           uint32_t* start, float4* __restrict__ sorted) {
+  if (prm->counts[level] == 0) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    float4 q = __ldg(cloud + i);
+    if (!finite3(q)) continue;
+    const uint32_t pos = atomicAdd(&start[slot[i]], 1u);     // start[] ends up as the END of each cell's range
+    q.w = __uint_as_float((uint32_t)i);
+    sorted[pos] = q;
+  }
+}
+
+// ------------------------------------------------------------------ k-NN query (one level)
+template <int KMAX>
+__global__ void __launch_bounds__(128) sor_query_kernel(const float4* __restrict__ cloud, SorParams* prm, int level,
+                                                         const float4* __restrict__ sorted,
+                                                         const unsigned long long* __restrict__ keys,
+                                                         const uint32_t* __restrict__ cnt,
+                                                         const uint32_t* __restrict__ start, uint32_t mask, int k,
+                                                         const uint32_t* __restrict__ pend_in,
+                                                         uint32_t* __restrict__ pend_out, double* __restrict__ avg) {
+  const uint32_t nq = prm->counts[level];
+  if (nq == 0) return;
+  const double s = prm->cell[level], inv = 1.0 / s;
+  const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
+  const int dimx = prm->dim[level][0], dimy = prm->dim[level][1], dimz = prm->dim[level][2];
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nq; t += gridDim.x * blockDim.x) {
+    float4 q;
+    uint32_t orig;
+    if (level == 0) { q = sorted[t]; orig = __float_as_uint(q.w); }
+    else { orig = pend_in[t]; q = __ldg(cloud + orig); }
+    const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
+    const double ux = qx - ox, uy = qy - oy, uz = qz - oz;
+    const int cx = cell_of(ux, inv, dimx), cy = cell_of(uy, inv, dimy), cz = cell_of(uz, inv, dimz);
+
+    double best[KMAX];
+    int found = 0;
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, dimz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, dimy - 1); ++y)
+        for (int x = max(cx - 1, 0); x <= min(cx + 1, dimx - 1); ++x) {
+          const unsigned long long key = cell_key(x, y, z);
+          uint32_t h = hash_key(key, mask);
+          unsigned long long kk;
+          while ((kk = keys[h]) != key && kk != kEmptyKey) h = (h + 1) & mask;
+          if (kk != key) continue;
+          const uint32_t end = start[h];
+          for (uint32_t j = end - cnt[h]; j < end; ++j) {
+            const float4 p = sorted[j];
+            const double ex = (double)p.x - qx, ey = (double)p.y - qy, ez = (double)p.z - qz;
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+            int pos;
+            if (found < k) pos = found++;
+            else if (d2 < best[k - 1]) pos = k - 1;
+            else continue;
+            while (pos > 0 && best[pos - 1] > d2) { best[pos] = best[pos - 1]; --pos; }
+            best[pos] = d2;
+          }
+        }
+
+    // distance from the query to the faces of the scanned block that have unscanned cells behind them
+    double g = INFINITY;
+    if (cx - 1 > 0) g = fmin(g, ux - (double)(cx - 1) * s);
+    if (cx + 1 < dimx - 1) g = fmin(g, (double)(cx + 2) * s - ux);
+    if (cy - 1 > 0) g = fmin(g, uy - (double)(cy - 1) * s);
+    if (cy + 1 < dimy - 1) g = fmin(g, (double)(cy + 2) * s - uy);
+    if (cz - 1 > 0) g = fmin(g, uz - (double)(cz - 1) * s);
+    if (cz + 1 < dimz - 1) g = fmin(g, (double)(cz + 2) * s - uz);
+    g -= 1e-6 * s;                                  // rounding of the cell assignment, with a wide margin
+    const bool final_ = isinf(g) || (found >= k && g > 0.0 && best[k - 1] <= g * g) || level == kLevels - 1;
+    if (final_) {
+      double sum = 0.0;
+      for (int j = 0; j < found; ++j) sum = __dadd_rn(sum, sqrt(best[j]));      // nearest first
+      avg[orig] = found ? sum / (double)found : -1.0;
+    } else {
+      pend_out[atomicAdd(&prm->counts[level + 1], 1u)] = orig;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ statistics (fixed-order reductions)
+// pass 0: sum of the positive mean distances; pass 1: sum of (avg - mean)^2 over the same points
+__global__ void __launch_bounds__(256) sor_partial_kernel(const double* __restrict__ avg, long long N,
+                                                           const SorParams* prm, int pass, double* __restrict__ part) {
+  __shared__ double sh[256];
+  const double mean = pass ? prm->mean : 0.0;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const double a = avg[i];
+    if (a > 0.0) acc += pass ? (a - mean) * (a - mean) : a;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[pass * kRedBlocks + blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(kRedBlocks) sor_final_kernel(SorParams* prm, int pass, const double* __restrict__ part,
+                                                                double std_ratio, double* __restrict__ stats) {
+  __shared__ double sh[kRedBlocks];
+  sh[threadIdx.x] = part[pass * kRedBlocks + threadIdx.x];
+  __syncthreads();
+  for (int w = kRedBlocks / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x) return;
+  const double nf = (double)prm->n_finite;
+  if (pass == 0) { prm->mean = sh[0] / nf; return; }
+  prm->stddev = sqrt(sh[0] / (nf - 1.0));                       // Bessel's correction, as Open3D
+  prm->thr = prm->mean + std_ratio * prm->stddev;
+  if (stats) { stats[0] = prm->mean; stats[1] = prm->stddev; stats[2] = prm->thr; }
+}
+
+// ------------------------------------------------------------------ ordered compaction of the inliers
+__device__ __forceinline__ bool sor_keep(double a, double thr) { return a > 0.0 && a < thr; }
+
+__global__ void __launch_bounds__(256) sor_count_kernel(const double* __restrict__ avg, long long N, const SorParams* prm,
+                                                         uint32_t* __restrict__ blk_cnt) {
+  const double thr = prm->thr;
+  const long long base = (long long)blockIdx.x * kCompactBlock;
+  uint32_t c = 0;
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < N && sor_keep(avg[i], thr)) ++c;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ uint32_t ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int i = 0; i < 8; ++i) s += ws[i];
+    blk_cnt[blockIdx.x] = s;
+  }
+}
+
+// exclusive scan of the block counts by one CTA (chunks of 1024 with a running carry)
+__global__ void __launch_bounds__(1024) sor_scan_kernel(const uint32_t* __restrict__ blk_cnt, long long blocks,
+                                                         long long* __restrict__ blk_base, long long* __restrict__ total) {
+  __shared__ long long sh[1024];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long long c0 = 0; c0 < blocks; c0 += 1024) {
+    const long long i = c0 + threadIdx.x;
+    const long long v = i < blocks ? (long long)blk_cnt[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      const long long add = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < blocks) blk_base[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(256) sor_emit_kernel(const float4* __restrict__ cloud, const double* __restrict__ avg,
+                                                        long long N, const SorParams* prm,
+                                                        const long long* __restrict__ blk_base,
+                                                        float4* __restrict__ out_cloud, long long* __restrict__ out_index) {
+  __shared__ uint32_t ws[8];
+  const double thr = prm->thr;
+  const long long base = (long long)blockIdx.x * kCompactBlock;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long run = blk_base[blockIdx.x];
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    const bool keep = i < N && sor_keep(avg[i], thr);
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) ws[warp] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) { const uint32_t c = ws[w]; if (w < warp) before += c; total += c; }
+    if (keep) {
+      const long long o = run + before + __popc(m & ((1u << lane) - 1u));
+      if (out_cloud) out_cloud[o] = __ldg(cloud + i);
+      if (out_index) out_index[o] = i;
+    }
+    run += total;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ launcher
+int launch_outlier_removal(const float* cloud_f, long long N, int nb_neighbors, double std_ratio, float* out_cloud,
+                           long long* out_index, double* mean_dist, double* stats, long long* out_count, void* ws,
+                           cudaStream_t st) {
+  SorWs w;
+  sor_carve(ws, N, &w);
+  const float4* cloud = reinterpret_cast<const float4*>(cloud_f);
+  int launches = 0;
+  if (N == 0) {
+    SL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(long long), st));
+    if (stats) SL_CUDA(cudaMemsetAsync(stats, 0xff, 3 * sizeof(double), st));      // NaN
+    return kOk;
+  }
+  const uint32_t mask = w.M - 1;
+  sor_init_kernel<<<1, 32, 0, st>>>(w.prm); ++launches;
+  sor_bbox_kernel<<<kSorBlocks, 256, 0, st>>>(cloud, N, w.prm, w.avg); ++launches;
+  sor_plan_pilot_kernel<<<1, 32, 0, st>>>(w.prm); ++launches;
+  sor_clear_kernel<<<kSorBlocks, 256, 0, st>>>(w.prm, -1, w.keys, w.cnt, w.M); ++launches;
+  sor_insert_kernel<<<kSorBlocks, 256, 0, st>>>(cloud, N, w.prm, -1, w.keys, w.cnt, mask, w.slot); ++launches;
+  sor_plan_final_kernel<<<1, 32, 0, st>>>(w.prm); ++launches;
+  for (int l = 0; l < kLevels; ++l) {
+    sor_clear_kernel<<<kSorBlocks, 256, 0, st>>>(w.prm, l, w.keys, w.cnt, w.M);
+    sor_insert_kernel<<<kSorBlocks, 256, 0, st>>>(cloud, N, w.prm, l, w.keys, w.cnt, mask, w.slot);
+    sor_alloc_kernel<<<kSorBlocks, 256, 0, st>>>(w.prm, l, w.cnt, w.start, w.M);
+    sor_scatter_kernel<<<kSorBlocks, 256, 0, st>>>(cloud, N, w.prm, l, w.slot, w.start, w.sorted);
+    const uint32_t* pin = w.pend[l & 1];
+    uint32_t* pout = w.pend[(l + 1) & 1];
+    if (nb_neighbors <= 32)
+      sor_query_kernel<32><<<kSorBlocks * 2, 128, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
+                                                           nb_neighbors, pin, pout, w.avg);
+    else
+      sor_query_kernel<128><<<kSorBlocks * 2, 128, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
+                                                            nb_neighbors, pin, pout, w.avg);
+    launches += 5;
+  }
+  sor_partial_kernel<<<kRedBlocks, 256, 0, st>>>(w.avg, N, w.prm, 0, w.part);
+  sor_final_kernel<<<1, kRedBlocks, 0, st>>>(w.prm, 0, w.part, std_ratio, stats);
+  sor_partial_kernel<<<kRedBlocks, 256, 0, st>>>(w.avg, N, w.prm, 1, w.part);
+  sor_final_kernel<<<1, kRedBlocks, 0, st>>>(w.prm, 1, w.part, std_ratio, stats);
+  const long long blocks = (N + kCompactBlock - 1) / kCompactBlock;
+  sor_count_kernel<<<(int)blocks, 256, 0, st>>>(w.avg, N, w.prm, w.blk_cnt);
+  sor_scan_kernel<<<1, 1024, 0, st>>>(w.blk_cnt, blocks, w.blk_base, out_count);
+  sor_emit_kernel<<<(int)blocks, 256, 0, st>>>(cloud, w.avg, N, w.prm, w.blk_base, reinterpret_cast<float4*>(out_cloud),
+                                               out_index);
+  launches += 7;
+  if (mean_dist) SL_CUDA(cudaMemcpyAsync(mean_dist, w.avg, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < launches; ++i) count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace sl

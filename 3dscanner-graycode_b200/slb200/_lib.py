@@ -56,6 +56,8 @@ SIGNATURES = {
     "sl_filter_box": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sl_filter_workspace_bytes": (_sz, [_i64]),
     "sl_filter_cloud_box": (_i, [_vp, _i64, _d, _vp, _vp, _vp, _sz, _vp]),
+    "sl_remove_statistical_outliers": (_i, [_vp, _i64, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sl_outlier_workspace_bytes": (_sz, [_i64]),
     "sl_pipeline_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "sl_pipeline_destroy": (None, [_vp]),
     "sl_scan_to_cloud_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(SlCalib), _i, _d, _vp, _vp, _vp, _i64, _vp]),

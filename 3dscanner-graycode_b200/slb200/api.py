@@ -416,6 +416,34 @@ def filter_cloud_box(cloud: torch.Tensor, threshold: float = .5) -> torch.Tensor
     return out[: int(cnt.item())]
 
 
+def remove_statistical_outliers(cloud: torch.Tensor, nb_neighbors: int = 20, std_ratio: float = 0.5,
+                                details: bool = False):
+    """``pcd.remove_statistical_outlier(nb_neighbors, std_ratio)`` (scanner/utils/visualize.py:104-105, Open3D 0.17)
+    on a packed XYZRGB cloud ``(N,4)`` f32 (CUDA).  Returns ``(inlier_cloud (M,4), ind (M,) int64)``; with
+    ``details`` also ``mean_dist (N,) f64`` and ``stats (3,) f64`` = cloud mean, standard deviation, threshold."""
+    if not (cloud.is_cuda and cloud.dtype == torch.float32 and cloud.dim() == 2 and cloud.shape[1] == 4):
+        raise TypeError("cloud must be a CUDA float32 (N,4) tensor")
+    if nb_neighbors < 1 or not std_ratio > 0:
+        raise ValueError("nb_neighbors and std_ratio must be positive")        # Open3D's own check
+    cloud = cloud.contiguous()
+    n, dev = cloud.shape[0], cloud.device
+    out = torch.empty_like(cloud)
+    ind = torch.empty(n, dtype=torch.int64, device=dev)
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    mean_dist = torch.empty(n, dtype=torch.float64, device=dev) if details else None
+    stats = torch.empty(3, dtype=torch.float64, device=dev) if details else None
+    nbytes = lib().sl_outlier_workspace_bytes(n)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().sl_remove_statistical_outliers(_ptr(cloud), n, int(nb_neighbors), float(std_ratio), _ptr(out),
+                                                   _ptr(ind), _ptr(mean_dist), _ptr(stats), _ptr(cnt), _ptr(ws),
+                                                   nbytes, _stream()))
+    m = int(cnt.item())
+    if details:
+        return out[:m], ind[:m], mean_dist, stats
+    return out[:m], ind[:m]
+
+
 def unpack_rgb(word: torch.Tensor) -> torch.Tensor:
     """Colour words (R | G<<8 | B<<16, int32 / float32 bit patterns) -> (N,3) uint8."""
     flat = torch.empty(word.shape, dtype=word.dtype, device=word.device)      # fresh, unit-stride storage

@@ -181,6 +181,24 @@ size_t sl_filter_workspace_bytes(int64_t N);
 int sl_filter_cloud_box(const float* cloud, int64_t N, double threshold, float* out_cloud,
                         int64_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* pcd.remove_statistical_outlier(nb_neighbors, std_ratio) as scanner/utils/visualize.py:104-105 applies it to
+ * the filtered cloud (Open3D 0.17 PointCloud::RemoveStatisticalOutliers; the reference narrows the points to
+ * float32 first, visualize.py:100): mean distance of every point to its nb_neighbors nearest points (itself
+ * included), threshold = mean + std_ratio * standard deviation (Bessel) of those means, inliers
+ * 0 < mean_dist < threshold in ascending index order.  Exact k-NN on a hashed uniform grid; 1 <= nb_neighbors <= 128.
+ *   cloud       device f32 (N,4) XYZRGB records (only x, y, z are read; records with a non-finite coordinate
+ *               are dropped and are nobody's neighbour)
+ *   out_cloud   nullable device f32, capacity (N,4): the M inlier records
+ *   out_index   nullable device int64 [N]: the M inlier indices (Open3D's `ind`)
+ *   mean_dist   nullable device f64 [N]: the per-point mean neighbour distance (-1 for dropped records)
+ *   stats       nullable device f64 [3]: cloud mean, standard deviation, threshold
+ *   out_count   device int64 [1] = M
+ *   workspace   device scratch of sl_outlier_workspace_bytes(N) */
+int sl_remove_statistical_outliers(const float* cloud, int64_t N, int nb_neighbors, double std_ratio,
+                                   float* out_cloud, int64_t* out_index, double* mean_dist, double* stats,
+                                   int64_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+size_t sl_outlier_workspace_bytes(int64_t N);
+
 /* -------------------------------------------------------------- host-buffer pipeline */
 
 typedef struct SlPipeline SlPipeline;
