@@ -101,6 +101,26 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
                        bitmap, words, ticket, sms, (cudaStream_t)stream);
 }
 
+int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size_t frame_pitch,
+                     size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx,
+                     void* cloud_workspace, void* stream) {
+  int rc = check_decode_shape(B, F, H, W);
+  if (rc) return rc;
+  if (!frames_bgr || !h_idx || !v_idx) { set_error("frames_bgr, h_idx, v_idx must be non-null"); return kErrBadArg; }
+  const long long npix = (long long)H * W;
+  if (frame_pitch < (size_t)npix * 3) { set_error("frame_pitch smaller than 3*H*W"); return kErrBadArg; }
+  if (B > 1 && scan_pitch < frame_pitch * (size_t)F) { set_error("scan_pitch smaller than F*frame_pitch"); return kErrBadArg; }
+  if (!(eps == eps)) { set_error("eps is NaN"); return kErrBadArg; }
+  int sms = 0;
+  if ((rc = device_gate(&sms))) return rc;
+  uint32_t* bitmap = nullptr;
+  unsigned int* ticket = nullptr;
+  long long words = 0;
+  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &ticket);
+  return launch_decode(frames_bgr, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr,
+                       bitmap, words, ticket, sms, (cudaStream_t)stream, true);
+}
+
 int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
                        double* L_g, void* stream) {
   int rc = check_decode_shape(1, F, H, W);

@@ -221,6 +221,108 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------ K1c decode straight from BGR camera frames
+// The capture loop converts every frame with cv2.cvtColor(BGR2GRAY) before it enters the stack
+// (src/3-capture_decode.py:66).  This variant streams the 3-byte pixels themselves (3F + 4 algorithmic
+// bytes per pixel instead of 3F + F for the conversion pass plus F + 4 for the decode): same persistent
+// producer / consumer structure, 128-pixel tiles (one warp each, F x 384 bytes per stage).  A consumer
+// lane converts its own 4 pixels of every frame (gray4_from_bgr12: two IDP4A per pixel) into a private
+// column of a per-warp gray tile in shared memory, hands the BGR stage back to the producer, and then runs
+// the unchanged per-quad decode on the gray tile.
+constexpr int kBgrTilePx = 128;
+constexpr int kBgrRowBytes = kBgrTilePx * 3;
+
+template <int NB>
+__global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int n = NB ? NB : a.n;
+  const int F = 4 * n + 2;
+  const int stages = a.stages;
+  const uint32_t stage_bytes = (uint32_t)F * kBgrRowBytes;
+  uint8_t* gray_base = smem + (size_t)stages * stage_bytes;                 // [kConsumerWarps][F][32 words]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gray_base + (size_t)kConsumerWarps * F * kBgrTilePx);
+  unsigned int* next_tile = reinterpret_cast<unsigned int*>(bars + 2 * stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && a.ticket) *a.ticket = 0;
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[stages + s]), 1);
+    }
+    *next_tile = 0;
+    mbar_init_fence();
+  }
+  __syncthreads();
+
+  const uint32_t total = (uint32_t)a.total_tiles, tps = (uint32_t)a.tiles_per_scan, grid = gridDim.x;
+  if (warp == kConsumerWarps) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap);
+      const uint64_t pol = policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0, tile = blockIdx.x, b = 0;
+      for (uint32_t t = blockIdx.x; t < total; t += grid, tile += grid) {
+        if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
+        mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)(tile * (kBgrRowBytes / 4)), 0, (int)b, full, pol);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  uint32_t* gray = reinterpret_cast<uint32_t*>(gray_base + (size_t)warp * F * kBgrTilePx) + lane;
+  uint32_t it_prev = 0, s = 0, ph = 0, tile = blockIdx.x, b = 0;
+  for (;;) {
+    unsigned int it = 0;
+    if (lane == 0) it = atomicAdd(next_tile, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    const uint32_t t = blockIdx.x + it * grid;
+    if (t >= total) break;
+    const uint32_t delta = it - it_prev;
+    it_prev = it;
+    s += delta;
+    while (s >= (uint32_t)stages) { s -= (uint32_t)stages; ph ^= 1u; }
+    tile += delta * grid;
+    if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
+    mbar_wait(smem_u32(&bars[s]), ph);
+
+    // BGR stage -> this lane's gray column (out-of-range pixels of the last tile are zero-filled by the TMA)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + lane * 3;
+#pragma unroll 2
+    for (int f = 0; f < F; ++f) {
+      const uint32_t* r = src + f * (kBgrRowBytes / 4);
+      gray[f * 32] = gray4_from_bgr12(r[0], r[1], r[2]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));        // the producer may refill the stage now
+
+    const long long px0 = (long long)tile * kBgrTilePx;
+    const long long rem = a.npix4 - px0;
+    const int cnt = (int)(rem < kBgrTilePx ? rem : kBgrTilePx);
+    const int off = lane * 4;
+    uint32_t nib = 0;
+    if (off < cnt) {
+      auto ld = [&](int f) { return gray[f * 32]; };
+      auto st = [&](int, int, uint32_t) {};
+      const long long px = px0 + off;
+      const QuadOut o = decode_quad<NB, false>(ld, st, n, a.e);
+      st_global_v2(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23);
+      st_global_v2(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23);
+      nib = ((o.valid & kMsb4) * 0x00204081u) >> 28;
+    }
+    if (a.bitmap) {
+      const uint32_t word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
+      if ((lane & 7) == 0 && px0 + off < a.npix)
+        a.bitmap[(size_t)b * a.bitmap_words + ((px0 + off) >> 5)] = word;
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------ K1g generic
 struct GenericArgs {
   const uint8_t* frames;
@@ -235,6 +337,7 @@ struct GenericArgs {
   uint32_t* bitmap;       // nullable: validity bits are OR-ed in (the launcher zeroes the words first)
   long long bitmap_words;
   unsigned int* ticket;   // nullable, zeroed (see DecodeArgs)
+  int bgr;                // frames hold 3-byte BGR pixels, converted like cv2.cvtColor(BGR2GRAY) on load
   const double* ld_in;    // nullable: caller-supplied L_d / L_g (get_is_lit, decode_codes.py:125)
   const double* lg_in;
   double* ld_out;         // nullable: get_direct_indirect outputs (decode_codes.py:90-122)
@@ -261,8 +364,12 @@ __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericArgs a
        i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / span;
     const long long px = a.px_begin + (i - b * span);
-    const uint8_t* f0 = a.frames + (size_t)b * a.scan_pitch + (size_t)px;
-    auto ld = [&](int f) { return (double)__ldg(f0 + (size_t)f * a.frame_pitch); };
+    const uint8_t* f0 = a.frames + (size_t)b * a.scan_pitch + (size_t)px * (a.bgr ? 3 : 1);
+    auto ld = [&](int f) {
+      const uint8_t* p = f0 + (size_t)f * a.frame_pitch;
+      if (!a.bgr) return (double)__ldg(p);
+      return (double)((3735u * __ldg(p) + 19235u * __ldg(p + 1) + 9798u * __ldg(p + 2) + 16384u) >> 15);
+    };
     const double black = ld(0), white = ld(1);
     double lmax = ld(2 + 2 * (n - 1)), lmin = ld(3);
     lmax = fmax(lmax, ld(2 + 2 * (n - 2)));  lmax = fmax(lmax, ld(2 + 2 * (n - 3)));
@@ -341,7 +448,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_frames_tensor_map(CUtensorMap* out, const uint8_t* frames, long long npix4, int F, int B,
-                                  size_t frame_pitch, size_t scan_pitch) {
+                                  size_t frame_pitch, size_t scan_pitch, int bytes_per_px = 1,
+                                  int box_words = kTilePx / 4) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -354,9 +462,9 @@ static int make_frames_tensor_map(CUtensorMap* out, const uint8_t* frames, long 
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   // tensor of uint32 (4 pixels): dim0 = npix4/4 along a frame, dim1 = frame, dim2 = scan
-  const cuuint64_t dims[3] = {(cuuint64_t)(npix4 / 4), (cuuint64_t)F, (cuuint64_t)B};
+  const cuuint64_t dims[3] = {(cuuint64_t)(npix4 / 4) * bytes_per_px, (cuuint64_t)F, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)frame_pitch, (cuuint64_t)(B > 1 ? scan_pitch : frame_pitch * F)};
-  const cuuint32_t box[3] = {(cuuint32_t)(kTilePx / 4), (cuuint32_t)F, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_words, (cuuint32_t)F, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -399,10 +507,35 @@ static int dispatch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, 
   }
 }
 
+template <int NB>
+static int launch_bgr_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+  auto k = decode_bgr_tma_kernel<NB>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured[dev & 63] = true;
+  }
+  k<<<grid, kDecodeThreads, smem, st>>>(tmap, a);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+static int dispatch_bgr_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+  switch (a.n) {
+    case 10: return launch_bgr_tma<10>(tmap, a, grid, smem, st);
+    case 11: return launch_bgr_tma<11>(tmap, a, grid, smem, st);
+    case 12: return launch_bgr_tma<12>(tmap, a, grid, smem, st);
+    default: return launch_bgr_tma<0>(tmap, a, grid, smem, st);
+  }
+}
+
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                   int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
-                  int num_sms, cudaStream_t st) {
+                  int num_sms, cudaStream_t st, bool bgr) {
   const int n = (F - 2) / 4;
   {
     const int trc = ensure_binv_table(st);
@@ -419,7 +552,29 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
   if (valid_bitmap && tma_px < npix)   // some pixels go through the generic kernel, which ORs its bits in
     SL_CUDA(cudaMemsetAsync(valid_bitmap, 0, (size_t)B * bitmap_words * sizeof(uint32_t), st));
 
-  if (tma_px > 0) {
+  if (tma_px > 0 && bgr) {
+    DecodeArgs a;
+    a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
+    a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = nullptr; a.v_codes = nullptr;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket;
+    a.npix = npix; a.npix4 = tma_px;
+    a.tiles_per_scan = (int)((tma_px + kBgrTilePx - 1) / kBgrTilePx);
+    a.total_tiles = (long long)a.tiles_per_scan * B;
+    a.n = n; a.F = F; a.e = (int)eps;
+    const size_t stage_bytes = (size_t)F * kBgrRowBytes;
+    const size_t gray_bytes = (size_t)kConsumerWarps * F * kBgrTilePx;
+    int stages = (int)((kSmemBudget - 256 - gray_bytes) / stage_bytes);
+    if (stages > 12) stages = 12;
+    if (stages < 2) { set_error("frame count too large for the BGR decode"); return kErrBadArg; }
+    if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
+    a.stages = stages;
+    const size_t smem = stages * stage_bytes + gray_bytes + 2 * stages * sizeof(uint64_t) + 16;
+    const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
+    CUtensorMap tmap;
+    int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch, 3, kBgrRowBytes / 4);
+    if (rc != kOk) return rc;
+    if ((rc = dispatch_bgr_tma(tmap, a, grid, smem, st)) != kOk) return rc;
+  } else if (tma_px > 0) {
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
@@ -450,7 +605,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     g.h_idx = h_idx; g.v_idx = v_idx; g.h_codes = h_codes; g.v_codes = v_codes;
     g.npix = npix; g.px_begin = tma_px; g.px_end = npix; g.n = n; g.B = B; g.eps = eps;
     g.bitmap = valid_bitmap; g.bitmap_words = bitmap_words; g.ticket = ticket;
-    g.ld_in = g.lg_in = nullptr; g.ld_out = g.lg_out = nullptr;
+    g.ld_in = g.lg_in = nullptr; g.ld_out = g.lg_out = nullptr; g.bgr = bgr ? 1 : 0;
     const long long total = (npix - tma_px) * B;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
@@ -471,7 +626,7 @@ int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t fra
   g.h_idx = nullptr; g.v_idx = nullptr; g.h_codes = h_codes; g.v_codes = v_codes;
   g.npix = npix; g.px_begin = 0; g.px_end = npix; g.n = (F - 2) / 4; g.B = 1; g.eps = eps;
   g.bitmap = nullptr; g.bitmap_words = 0; g.ticket = nullptr;
-  g.ld_in = ld_in; g.lg_in = lg_in; g.ld_out = ld_out; g.lg_out = lg_out;
+  g.ld_in = ld_in; g.lg_in = lg_in; g.ld_out = ld_out; g.lg_out = lg_out; g.bgr = 0;
   long long blocks = (npix + 255) / 256;
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
   if (blocks < 1) return kOk;

@@ -215,6 +215,33 @@ def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[to
     return h_idx, v_idx
 
 
+def _bgr_view(frames_bgr: torch.Tensor):
+    """``([B,]F,H,W,3)`` uint8 CUDA -> (b, f, h, w, batched, frame_pitch, scan_pitch); dense frames only."""
+    if not (isinstance(frames_bgr, torch.Tensor) and frames_bgr.is_cuda and frames_bgr.dtype == torch.uint8
+            and frames_bgr.dim() in (4, 5) and frames_bgr.shape[-1] == 3):
+        raise TypeError("frames_bgr must be a CUDA uint8 tensor ([B,]F,H,W,3)")
+    if not frames_bgr.is_contiguous():
+        raise ValueError("frames_bgr must be contiguous")
+    batched = frames_bgr.dim() == 5
+    b = frames_bgr.shape[0] if batched else 1
+    f, h, w = frames_bgr.shape[-4:-1]
+    return b, f, h, w, batched, 3 * h * w, 3 * h * w * f
+
+
+def decode_pixels_bgr(frames_bgr: torch.Tensor, eps: float = 1.0):
+    """decode_pixels on the camera's BGR frames ``([B,]F,H,W,3)``: the per-frame
+    ``cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)`` of the capture loop (src/3-capture_decode.py:66) is fused into the
+    decode's load, no gray stack is materialised."""
+    b, f, h, w, batched, fp, sp = _bgr_view(frames_bgr)
+    shape = (b, h, w) if batched else (h, w)
+    h_idx = torch.empty(shape, dtype=torch.int16, device=frames_bgr.device)
+    v_idx = torch.empty(shape, dtype=torch.int16, device=frames_bgr.device)
+    with torch.cuda.device(frames_bgr.device):
+        check(lib().sl_decode_bgr_u8(_ptr(frames_bgr), b, f, h, w, fp, sp, float(eps), _ptr(h_idx), _ptr(v_idx),
+                                     None, _stream()))
+    return h_idx, v_idx
+
+
 def decode_codes(frames: torch.Tensor, eps: float = 1.0):
     """get_codes (decode_codes.py:231-248): tri-state ``h_codes, v_codes`` int8 ``([B,]n,H,W)``
     plus the decoded indices (same launch)."""
@@ -518,7 +545,7 @@ class LensTables:
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
                   precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
                   calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None,
-                  row0: int = 0) -> CloudBuffers:
+                  row0: int = 0, bgr: bool = False) -> CloudBuffers:
     """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
     decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
 
@@ -527,12 +554,19 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     ``row0``: the stack is the row band ``[row0, row0 + H)`` of a larger capture (row-band sharding);
     camera coordinates and ray look-ups use absolute rows, ``tables`` must cover the whole image.
 
+    ``bgr``: ``frames`` holds the camera's BGR frames ``([B,]F,H,W,3)``; the gray conversion of
+    src/3-capture_decode.py:66 happens inside the decode kernel.
+
     Results are in the returned buffers: ``cloud[:counts[B]]`` (XYZRGB records; ``.xyz`` / ``.rgb``
     views) packed scan after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
     Mirrors src/3-capture_decode.py:75-100 + src/4-triangulate.py:50-64.
     """
-    _check_stack(frames)
-    b, f, h, w, _ = _stack_dims(frames)
+    if bgr:
+        b, f, h, w, _, fp, sp = _bgr_view(frames)
+    else:
+        _check_stack(frames)
+        b, f, h, w, _ = _stack_dims(frames)
+        fp, sp = _pitches(frames)
     dev = frames.device
     if buffers is None:
         buffers = CloudBuffers.allocate(b, h, w, dev)
@@ -548,9 +582,12 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     L = lib()
     st = _stream()
     with torch.cuda.device(dev):
-        fp, sp = _pitches(frames)
-        check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
-                             _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, _ptr(buffers.ws), st))
+        if bgr:
+            check(L.sl_decode_bgr_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
+                                     _ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(buffers.ws), st))
+        else:
+            check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
+                                 _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, _ptr(buffers.ws), st))
         check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
         check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
                               _PREC[precision], _ptr(tables.cam) if tables is not None else None,

@@ -79,6 +79,16 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                  int8_t* v_codes, void* cloud_workspace, void* stream);
 
+/* The same decode straight from the camera's 8-bit BGR frames: the capture loop's per-frame
+ * cv2.cvtColor(frame, COLOR_BGR2GRAY) (src/3-capture_decode.py:66; gray = (3735 B + 19235 G + 9798 R + 16384) >> 15)
+ * is applied while the frames stream through shared memory, so no gray stack is ever written or re-read.
+ *   frames_bgr  device u8; pixel p of frame f of scan b at frames_bgr + b*scan_pitch + f*frame_pitch + 3*p
+ *               (B, G, R bytes); pitches in bytes, frame_pitch >= 3*H*W
+ * Other arguments as sl_decode_u8 (the tri-state code planes are not offered here). */
+int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size_t frame_pitch,
+                     size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx,
+                     void* cloud_workspace, void* stream);
+
 /* get_direct_indirect (decode_codes.py:90-122): L_d, L_g device f64 [H*W] (NaN where
  * white+black == 0, as in the reference). */
 int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,

@@ -23,3 +23,15 @@ extern "C" int hostcheck_decode(const uint8_t* frames, int F, long npix, int e,
   }
   return 0;
 }
+
+// BGR -> gray of 4 pixels (sl_pixel.cuh gray4_from_bgr12): bgr holds npix*3 bytes, npix % 4 == 0
+extern "C" int hostcheck_bgr_to_gray(const uint8_t* bgr, long npix, uint8_t* gray) {
+  if (npix % 4) return -1;
+  for (long px = 0; px < npix; px += 4) {
+    uint32_t w[3];
+    std::memcpy(w, bgr + px * 3, 12);
+    const uint32_t g = sl::gray4_from_bgr12(w[0], w[1], w[2]);
+    std::memcpy(gray + px, &g, 4);
+  }
+  return 0;
+}

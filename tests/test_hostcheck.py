@@ -74,3 +74,18 @@ def test_swar_exhaustive_thresholds(hostlib):
     np.testing.assert_array_equal(vc, vo)
     np.testing.assert_array_equal(hi, hpo)
     np.testing.assert_array_equal(vi, vpo)
+
+
+def test_bgr_to_gray_quad_all_colours(hostlib):
+    """gray4_from_bgr12 (byte dot products with split coefficients) on all 2^24 colours, in every one of the four
+    pixel positions of a quad, against cv2's fixed-point formula (3735 B + 19235 G + 9798 R + 16384) >> 15."""
+    c = np.arange(1 << 24, dtype=np.uint32)
+    bgr = np.stack([c & 255, (c >> 8) & 255, c >> 16], axis=1).astype(np.uint8)
+    b32 = bgr.astype(np.uint32)
+    want = ((3735 * b32[:, 0] + 19235 * b32[:, 1] + 9798 * b32[:, 2] + 16384) >> 15).astype(np.uint8)
+    for shift in range(4):                       # rotate so every colour visits every lane of the quad
+        b = np.roll(bgr, shift, axis=0)
+        got = np.empty(len(b), np.uint8)
+        assert hostlib.hostcheck_bgr_to_gray(b.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(b)),
+                                             got.ctypes.data_as(ctypes.c_void_p)) == 0
+        np.testing.assert_array_equal(got, np.roll(want, shift))
