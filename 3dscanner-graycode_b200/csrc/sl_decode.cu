@@ -242,6 +242,10 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
   uint8_t* gray_base = smem + (size_t)stages * stage_bytes;                 // [kConsumerWarps][F][32 words]
   uint64_t* bars = reinterpret_cast<uint64_t*>(gray_base + (size_t)kConsumerWarps * F * kBgrTilePx);
   unsigned int* next_tile = reinterpret_cast<unsigned int*>(bars + 2 * stages);
+  // Tiles the producer has armed so far.  There are more consumer warps (one tile each) than stages, so a warp
+  // can hold a claim that is a whole ring revolution ahead of the stage's current phase; a parity wait
+  // cannot tell that apart from "already complete", hence a warp first waits until ITS tile has been armed.
+  volatile unsigned int* armed = next_tile + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -251,6 +255,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
       mbar_init(smem_u32(&bars[stages + s]), 1);
     }
     *next_tile = 0;
+    *armed = 0;
     mbar_init_fence();
   }
   __syncthreads();
@@ -261,13 +266,15 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
       tma_prefetch_desc(&tmap);
       const uint64_t pol = policy_evict_first();
       int s = 0;
-      uint32_t ph = 0, tile = blockIdx.x, b = 0;
+      uint32_t ph = 0, tile = blockIdx.x, b = 0, n_armed = 0;
       for (uint32_t t = blockIdx.x; t < total; t += grid, tile += grid) {
         if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
         mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
         const uint32_t full = smem_u32(&bars[s]);
         mbar_arrive_expect_tx(full, stage_bytes);
         tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)(tile * (kBgrRowBytes / 4)), 0, (int)b, full, pol);
+        __threadfence_block();
+        *armed = ++n_armed;
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -288,6 +295,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     while (s >= (uint32_t)stages) { s -= (uint32_t)stages; ph ^= 1u; }
     tile += delta * grid;
     if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
+    while (*armed <= it) __nanosleep(20);
     mbar_wait(smem_u32(&bars[s]), ph);
 
     // BGR stage -> this lane's gray column (out-of-range pixels of the last tile are zero-filled by the TMA)

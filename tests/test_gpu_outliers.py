@@ -102,7 +102,7 @@ def test_scan_cloud_large():
     frames, white = synth.render_scan((1280, 720), (1024, 768), seed=5, device="cuda", calib=calib)
     bufs = slb200.scan_to_cloud(frames, white, calib)
     n = int(bufs.counts[1].item())
-    cloud = slb200.filter_cloud_box(bufs.cloud[:n], 0.5)
+    cloud = slb200.filter_cloud_box(bufs.cloud[:n], 2.0)          # the synthetic plane stands 0.9 m away
     assert len(cloud) > 200_000
     out, ind, mean_dist, stats = slb200.remove_statistical_outliers(cloud, 20, 0.5, details=True)
     xyz = cloud[:, :3].cpu().numpy()

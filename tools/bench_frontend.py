@@ -1,0 +1,71 @@
+"""Timing of the stages either side of the hot path (informational; bench.py is the contract benchmark):
+   (1) decode from BGR camera frames: fused (sl_decode_bgr_u8) vs two kernels (sl_bgr_to_gray_u8 + sl_decode_u8);
+   (2) box filter + statistical outlier removal on the cloud of a 1080p scan, next to the oracle on the host.
+   Prints one JSON object."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "3dscanner-graycode_b200")); sys.path.insert(0, ROOT)
+import numpy as np
+import torch, slb200
+from slb200 import synth
+
+dev = torch.device("cuda", 0)
+PEAK = 6535.4
+cam = proj = (1920, 1080)
+calib = synth.synthetic_calibration(cam, proj)
+pats = synth.pattern_stack(proj, dev)
+out = {}
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+# ---- (1) BGR front end: ring of 4 scans x 286 MB > L2
+g = torch.Generator(device=dev); g.manual_seed(1)
+ring = []
+for seed in range(4):
+    frames, white = synth.render_scan(cam, proj, seed=seed, device=dev, patterns=pats, calib=calib)
+    bgr = (frames[..., None].to(torch.int16) + torch.randint(-20, 21, (*frames.shape, 3), generator=g, device=dev, dtype=torch.int16))
+    ring.append(bgr.clamp(0, 255).to(torch.uint8).contiguous())
+F = ring[0].shape[0]
+npix = cam[0] * cam[1]
+k = [0]
+def fused():
+    slb200.decode_pixels_bgr(ring[k[0] % 4]); k[0] += 1
+def split():
+    slb200.decode_pixels(slb200.bgr_to_gray(ring[k[0] % 4])); k[0] += 1
+us_f, us_s = timed(fused, 40), timed(split, 40)
+out["bgr_decode_1080p"] = {
+    "fused_us": us_f, "fused_GBps": (3 * F + 4) * npix / us_f / 1e3, "fused_frac_of_peak": (3 * F + 4) * npix / us_f / 1e3 / PEAK,
+    "two_kernels_us": us_s, "two_kernels_algorithmic_GBps": (5 * F + 4) * npix / us_s / 1e3,
+    "speedup": us_s / us_f, "note": "eager launches (torch allocations included in both arms), ring of 4 BGR stacks (1145 MB)"}
+del ring
+
+# ---- (2) cloud clean-up
+frames, white = synth.render_scan(cam, proj, seed=3, device=dev, patterns=pats, calib=calib)
+tables = slb200.LensTables(calib, cam, dev)
+bufs = slb200.scan_to_cloud(frames, white, calib, tables=tables)
+n = int(bufs.counts[1].item())
+cloud = bufs.cloud[:n].clone()
+us_box = timed(lambda: slb200.filter_cloud_box(cloud, 0.5), 20)
+boxed = slb200.filter_cloud_box(cloud, 0.5)
+us_sor = timed(lambda: slb200.remove_statistical_outliers(boxed, 20, 0.5), 5, warm=1)
+inl, ind = slb200.remove_statistical_outliers(boxed, 20, 0.5)
+out["cloud_cleanup_1080p"] = {"points": n, "after_box": len(boxed), "after_outlier_removal": len(inl),
+                              "box_filter_us": us_box, "outlier_removal_us": us_sor,
+                              "outlier_removal_Mpts_per_s": len(boxed) / us_sor}
+if "--cpu" in sys.argv:
+    from oracle import outlier_oracle as OO
+    xyz = boxed[:, :3].cpu().numpy()
+    sub = xyz[: 200_000]
+    t0 = time.perf_counter(); OO.statistical_outliers(sub, 20, 0.5); dt = time.perf_counter() - t0
+    out["cloud_cleanup_1080p"]["oracle_kdtree_Mpts_per_s"] = len(sub) / dt / 1e6
+    out["cloud_cleanup_1080p"]["oracle_sample"] = "first 200 k points, scipy cKDTree restatement, all host threads scipy uses (1)"
+print(json.dumps(out))
