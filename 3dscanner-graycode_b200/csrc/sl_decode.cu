@@ -281,7 +281,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     return;
   }
 
-  uint32_t* gray = reinterpret_cast<uint32_t*>(gray_base + (size_t)warp * F * kBgrTilePx) + lane;
+  const uint32_t gray_s = smem_u32(gray_base + (size_t)warp * F * kBgrTilePx) + lane * 4;   // this lane's gray column
   uint32_t it_prev = 0, s = 0, ph = 0, tile = blockIdx.x, b = 0;
   for (;;) {
     unsigned int it = 0;
@@ -299,11 +299,11 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     mbar_wait(smem_u32(&bars[s]), ph);
 
     // BGR stage -> this lane's gray column (out-of-range pixels of the last tile are zero-filled by the TMA)
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + lane * 3;
-#pragma unroll 2
-    for (int f = 0; f < F; ++f) {
-      const uint32_t* r = src + f * (kBgrRowBytes / 4);
-      gray[f * 32] = gray4_from_bgr12(r[0], r[1], r[2]);
+    const uint32_t src_s = smem_u32(smem + (size_t)s * stage_bytes) + lane * 12;
+#pragma unroll
+    for (int f = 0; f < (NB ? 4 * NB + 2 : F); ++f) {      // compile-time trip count: immediate smem offsets
+      const uint32_t r = src_s + f * kBgrRowBytes;
+      sts_u32(gray_s + f * kBgrTilePx, gray4_from_bgr12(lds_u32(r), lds_u32(r + 4), lds_u32(r + 8)));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));        // the producer may refill the stage now
@@ -314,8 +314,8 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     const int off = lane * 4;
     uint32_t nib = 0;
     if (off < cnt) {
-      auto ld = [&](int f) { return gray[f * 32]; };
-      auto st = [&](int, int, uint32_t) {};
+      auto ld = [gray_s](int f) { return lds_u32(gray_s + f * kBgrTilePx); };
+      auto st = [](int, int, uint32_t) {};
       const long long px = px0 + off;
       const QuadOut o = decode_quad<NB, false>(ld, st, n, a.e);
       st_global_v2(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23);

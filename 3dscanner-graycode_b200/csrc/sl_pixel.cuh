@@ -110,9 +110,12 @@ SL_HD uint32_t widen_hi(uint32_t x) { return byte_perm(x, 0u, 0x4342u); }
 // ---- BGR -> gray of 4 pixels -----------------------------------------------------
 // cv2.cvtColor(frame, COLOR_BGR2GRAY) on 8-bit data (src/3-capture_decode.py:66, decode_codes.py:86):
 // gray = (3735 B + 19235 G + 9798 R + 16384) >> 15.  The 12 bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3 arrive
-// as three little-endian words.  The coefficients are split into bytes (3735 = 14*256 + 151, 19235 = 75*256 + 35,
-// 9798 = 38*256 + 70) so that one pixel costs two 4-way byte dot products (IDP4A); the unused byte lane of
-// each word meets a zero coefficient, so only pixels 1 and 2 need a byte permute.
+// as three little-endian words.  Evaluated as T = 2 * (3735 B + 19235 G + 9798 R) + 32768 < 2^24, whose byte 2 is
+// the gray value.  The doubled coefficients are split into bytes (7470 = 29*256 + 46, 38470 = 150*256 + 70,
+// 19596 = 76*256 + 140) so that T is two 4-way byte dot products (IDP4A) per source word touched; a pixel that
+// straddles two words chains its dot products through the accumulator, bytes of other pixels meet zero
+// coefficients.  All multiplies run on the FMA pipe -- the decode that follows is bound by the ALU pipe --
+// and the only byte shuffling left is the final gather of the four result bytes (3 PRMT).
 SL_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
   return __dp4a(a, b, c);
@@ -122,14 +125,15 @@ SL_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t c) {
 #endif
 }
 SL_HD uint32_t gray4_from_bgr12(uint32_t w0, uint32_t w1, uint32_t w2) {
-  constexpr uint32_t kLo = 151u | (35u << 8) | (70u << 16), kHi = 14u | (75u << 8) | (38u << 16);
-  const uint32_t p1 = byte_perm(w0, w1, 0x0543u), p2 = byte_perm(w1, w2, 0x0432u);
-  const uint32_t t0 = (dot4_u8(w0, kHi, 0u) << 8) + dot4_u8(w0, kLo, 16384u);
-  const uint32_t t1 = (dot4_u8(p1, kHi, 0u) << 8) + dot4_u8(p1, kLo, 16384u);
-  const uint32_t t2 = (dot4_u8(p2, kHi, 0u) << 8) + dot4_u8(p2, kLo, 16384u);
-  const uint32_t t3 = (dot4_u8(w2, kHi << 8, 0u) << 8) + dot4_u8(w2, kLo << 8, 16384u);
-  // t >> 15 is at most 255: move each result straight to its byte lane
-  return (t0 >> 15) | ((t1 >> 7) & 0x0000ff00u) | ((t2 << 1) & 0x00ff0000u) | ((t3 << 9) & 0xff000000u);
+  constexpr uint32_t hB = 29u, hG = 150u, hR = 76u, lB = 46u, lG = 70u, lR = 140u, kRound = 32768u;
+  const uint32_t t0 = dot4_u8(w0, hB | (hG << 8) | (hR << 16), 0u) * 256u + dot4_u8(w0, lB | (lG << 8) | (lR << 16), kRound);
+  const uint32_t t1 = dot4_u8(w1, hG | (hR << 8), dot4_u8(w0, hB << 24, 0u)) * 256u +
+                      dot4_u8(w1, lG | (lR << 8), dot4_u8(w0, lB << 24, kRound));
+  const uint32_t t2 = dot4_u8(w2, hR, dot4_u8(w1, (hB << 16) | (hG << 24), 0u)) * 256u +
+                      dot4_u8(w2, lR, dot4_u8(w1, (lB << 16) | (lG << 24), kRound));
+  const uint32_t t3 = dot4_u8(w2, (hB << 8) | (hG << 16) | (hR << 24), 0u) * 256u +
+                      dot4_u8(w2, (lB << 8) | (lG << 16) | (lR << 24), kRound);
+  return byte_perm(byte_perm(t0, t1, 0x0062u), byte_perm(t2, t3, 0x0062u), 0x5410u);
 }
 
 // ---- per-pixel thresholds ---------------------------------------------------

@@ -54,8 +54,9 @@ tables = slb200.LensTables(calib, cam, dev)
 bufs = slb200.scan_to_cloud(frames, white, calib, tables=tables)
 n = int(bufs.counts[1].item())
 cloud = bufs.cloud[:n].clone()
-us_box = timed(lambda: slb200.filter_cloud_box(cloud, 0.5), 20)
-boxed = slb200.filter_cloud_box(cloud, 0.5)
+BOX = 2.0        # the synthetic plane stands 0.9 m from the camera; the reference's 0.5 m box would empty the cloud
+us_box = timed(lambda: slb200.filter_cloud_box(cloud, BOX), 20)
+boxed = slb200.filter_cloud_box(cloud, BOX)
 us_sor = timed(lambda: slb200.remove_statistical_outliers(boxed, 20, 0.5), 5, warm=1)
 inl, ind = slb200.remove_statistical_outliers(boxed, 20, 0.5)
 out["cloud_cleanup_1080p"] = {"points": n, "after_box": len(boxed), "after_outlier_removal": len(inl),
