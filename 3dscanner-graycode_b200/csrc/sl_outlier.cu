@@ -9,7 +9,8 @@
 //   * a query scans the 3x3x3 block of cells around its own cell and is final when its k-th distance is
 //     not larger than the distance to the faces of that block (nothing outside can be closer);
 //   * the few queries that are not final (sparse noise points) are retried on a grid with 4x larger
-//     cells, up to kLevels times; the last level covers the whole bounding box with <= 2 cells per axis.
+//     cells, up to kLevels times (one CTA per query there: the block of a sparse query can hold a large part
+//     of the cloud); the last level covers the whole bounding box with <= 2 cells per axis.
 //   s of level 0 is chosen from a pilot build so that occupied cells hold ~kTargetOcc points.
 // Distances: float32 coordinates (the reference narrows to float32, visualize.py:100), differences,
 // squares and the (dx^2 + dy^2) + dz^2 sum in float64 with one rounding per operation, sqrt and the mean in
@@ -202,19 +203,32 @@ __global__ void __launch_bounds__(256) sor_insert_kernel(const float4* __restric
   const double inv = 1.0 / prm->cell[lv];
   const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
   const int dx = prm->dim[lv][0], dy = prm->dim[lv][1], dz = prm->dim[lv][2];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-    const float4 q = __ldg(cloud + i);
-    if (!finite3(q)) continue;
-    const unsigned long long key = cell_key(cell_of((double)q.x - ox, inv, dx), cell_of((double)q.y - oy, inv, dy),
-                                            cell_of((double)q.z - oz, inv, dz));
-    uint32_t h = hash_key(key, mask);
-    for (;;) {
-      const unsigned long long old = atomicCAS(&keys[h], kEmptyKey, key);
-      if (old == kEmptyKey) { if (level < 0) atomicAdd(&prm->occupied, 1u); break; }
-      if (old == key) break;
-      h = (h + 1) & mask;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count (i - lane is the same for all lanes): the lanes of a warp that fall into the same cell
+  // -- nearly all of them on the coarse levels -- share one atomic
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i - lane < N; i += (long long)gridDim.x * blockDim.x) {
+    const float4 q = i < N ? __ldg(cloud + i) : make_float4(NAN, 0.f, 0.f, 0.f);
+    const bool valid = finite3(q);
+    uint32_t h = 0x80000000u | (uint32_t)lane;                       // never equal to a slot or to another lane's
+    if (valid) {
+      const unsigned long long key = cell_key(cell_of((double)q.x - ox, inv, dx), cell_of((double)q.y - oy, inv, dy),
+                                              cell_of((double)q.z - oz, inv, dz));
+      h = hash_key(key, mask);
+      for (;;) {
+        if (*reinterpret_cast<volatile unsigned long long*>(&keys[h]) == key) break;   // common case: no atomic at all
+        const unsigned long long old = atomicCAS(&keys[h], kEmptyKey, key);
+        if (old == kEmptyKey) { if (level < 0) atomicAdd(&prm->occupied, 1u); break; }
+        if (old == key) break;
+        h = (h + 1) & mask;
+      }
     }
-    if (level >= 0) { atomicAdd(&cnt[h], 1u); slot[i] = h; }
+    if (level >= 0) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, h);
+      if (valid) {
+        if (lane == __ffs(peers) - 1) atomicAdd(&cnt[h], (uint32_t)__popc(peers));
+        slot[i] = h;
+      }
+    }
   }
 }
 
@@ -231,40 +245,56 @@ __global__ void __launch_bounds__(256) sor_scatter_kernel(const float4* __restri
                                                            int level, const uint32_t* __restrict__ slot,
                                                            uint32_t* start, float4* __restrict__ sorted) {
   if (prm->counts[level] == 0) return;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-    float4 q = __ldg(cloud + i);
-    if (!finite3(q)) continue;
-    const uint32_t pos = atomicAdd(&start[slot[i]], 1u);     // start[] ends up as the END of each cell's range
-    q.w = __uint_as_float((uint32_t)i);
-    sorted[pos] = q;
+  const int lane = threadIdx.x & 31;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i - lane < N; i += (long long)gridDim.x * blockDim.x) {
+    float4 q = i < N ? __ldg(cloud + i) : make_float4(NAN, 0.f, 0.f, 0.f);
+    const bool valid = finite3(q);
+    const uint32_t h = valid ? slot[i] : (0x80000000u | (uint32_t)lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, h);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) base = atomicAdd(&start[h], (uint32_t)__popc(peers));   // start[] ends up as the END
+    base = __shfl_sync(0xffffffffu, base, leader);                                       // of each cell's range
+    if (valid) {
+      q.w = __uint_as_float((uint32_t)i);
+      sorted[base + __popc(peers & ((1u << lane) - 1u))] = q;
+    }
   }
 }
 
-// ------------------------------------------------------------------ k-NN query (one level)
-template <int KMAX>
-__global__ void __launch_bounds__(128) sor_query_kernel(const float4* __restrict__ cloud, SorParams* prm, int level,
-                                                         const float4* __restrict__ sorted,
-                                                         const unsigned long long* __restrict__ keys,
-                                                         const uint32_t* __restrict__ cnt,
-                                                         const uint32_t* __restrict__ start, uint32_t mask, int k,
-                                                         const uint32_t* __restrict__ pend_in,
-                                                         uint32_t* __restrict__ pend_out, double* __restrict__ avg) {
+// ------------------------------------------------------------------ k-NN query, level 0: one thread per point
+// The k best squared distances of a thread live in a shared-memory column (best[j] at sm[j * blockDim + tid]:
+// 64-bit accesses, bank pair fixed by tid, so lanes inserting at different depths never conflict); the current
+// k-th best stays in a register, so a rejected candidate costs no memory access.  (In local memory the divergent
+// insertions touched a different cache line per lane and the kernel ran at L2 speed: 6.1 ms vs 0.x ms per 1.8 M points.)
+constexpr int kQ0Threads = 128;
+constexpr uint32_t kThreadModeMin = 8192;   // levels >= 1 with at least this many queries keep one thread per query
+__global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __restrict__ cloud, SorParams* prm, int level,
+                                                                const float4* __restrict__ sorted,
+                                                                const unsigned long long* __restrict__ keys,
+                                                                const uint32_t* __restrict__ cnt,
+                                                                const uint32_t* __restrict__ start, uint32_t mask, int k,
+                                                                const uint32_t* __restrict__ pend_in,
+                                                                uint32_t* __restrict__ pend_out, double* __restrict__ avg) {
+  extern __shared__ double q0_best[];
   const uint32_t nq = prm->counts[level];
-  if (nq == 0) return;
+  if (nq == 0 || (level > 0 && nq < kThreadModeMin)) return;
+  double* best = q0_best + threadIdx.x;
+  constexpr int kS = kQ0Threads;                 // stride between a thread's entries
   const double s = prm->cell[level], inv = 1.0 / s;
   const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
   const int dimx = prm->dim[level][0], dimy = prm->dim[level][1], dimz = prm->dim[level][2];
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nq; t += gridDim.x * blockDim.x) {
     float4 q;
     uint32_t orig;
-    if (level == 0) { q = sorted[t]; orig = __float_as_uint(q.w); }
+    if (level == 0) { q = sorted[t]; orig = __float_as_uint(q.w); }   // cell order: neighbouring threads scan the same cells
     else { orig = pend_in[t]; q = __ldg(cloud + orig); }
     const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
     const double ux = qx - ox, uy = qy - oy, uz = qz - oz;
     const int cx = cell_of(ux, inv, dimx), cy = cell_of(uy, inv, dimy), cz = cell_of(uz, inv, dimz);
 
-    double best[KMAX];
     int found = 0;
+    double worst = INFINITY;                      // best[k-1] once k candidates are held
     for (int z = max(cz - 1, 0); z <= min(cz + 1, dimz - 1); ++z)
       for (int y = max(cy - 1, 0); y <= min(cy + 1, dimy - 1); ++y)
         for (int x = max(cx - 1, 0); x <= min(cx + 1, dimx - 1); ++x) {
@@ -278,12 +308,16 @@ __global__ void __launch_bounds__(128) sor_query_kernel(const float4* __restrict
             const float4 p = sorted[j];
             const double ex = (double)p.x - qx, ey = (double)p.y - qy, ez = (double)p.z - qz;
             const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-            int pos;
-            if (found < k) pos = found++;
-            else if (d2 < best[k - 1]) pos = k - 1;
-            else continue;
-            while (pos > 0 && best[pos - 1] > d2) { best[pos] = best[pos - 1]; --pos; }
-            best[pos] = d2;
+            if (!(d2 < worst)) continue;
+            int pos = found < k ? found++ : k - 1;
+            while (pos > 0) {
+              const double above = best[(pos - 1) * kS];
+              if (!(above > d2)) break;
+              best[pos * kS] = above;
+              --pos;
+            }
+            best[pos * kS] = d2;
+            if (found == k) worst = best[(k - 1) * kS];
           }
         }
 
@@ -296,14 +330,134 @@ __global__ void __launch_bounds__(128) sor_query_kernel(const float4* __restrict
     if (cz - 1 > 0) g = fmin(g, uz - (double)(cz - 1) * s);
     if (cz + 1 < dimz - 1) g = fmin(g, (double)(cz + 2) * s - uz);
     g -= 1e-6 * s;                                  // rounding of the cell assignment, with a wide margin
-    const bool final_ = isinf(g) || (found >= k && g > 0.0 && best[k - 1] <= g * g) || level == kLevels - 1;
+    const bool final_ = isinf(g) || (found >= k && g > 0.0 && worst <= g * g) || level == kLevels - 1;
     if (final_) {
       double sum = 0.0;
-      for (int j = 0; j < found; ++j) sum = __dadd_rn(sum, sqrt(best[j]));      // nearest first
+      for (int j = 0; j < found; ++j) sum = __dadd_rn(sum, sqrt(best[j * kS]));      // nearest first
       avg[orig] = found ? sum / (double)found : -1.0;
     } else {
       pend_out[atomicAdd(&prm->counts[level + 1], 1u)] = orig;
     }
+  }
+}
+
+// Levels >= 1 with few queries left: one CTA per query.  The queries that get this far are the sparse ones
+// (noise far from the surface); their 3x3x3 block can hold a large part of the cloud, so the candidates of ONE
+// query are spread over the CTA's threads.  Every thread keeps the k smallest squared distances of its share (sorted); the k smallest of
+// the CTA are then drawn one at a time from the heads of those lists (a k-way selection: block-wide minimum,
+// the owner advances).  Same distances, same nearest-first summation as the thread-per-query kernel.
+constexpr int kQbThreads = 1024;
+constexpr int kQbBatch = 4;          // candidate loads in flight per thread
+template <int KMAX>
+__global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
+    const float4* __restrict__ cloud, SorParams* prm, int level, const float4* __restrict__ sorted,
+    const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ start,
+    uint32_t mask, int k, const uint32_t* __restrict__ pend_in, uint32_t* __restrict__ pend_out,
+    double* __restrict__ avg) {
+  const uint32_t nq = prm->counts[level];
+  if (nq == 0 || nq >= kThreadModeMin) return;
+  __shared__ uint32_t c_begin[27], c_pre[28];      // candidate ranges of the 27 cells, prefix of their sizes
+  __shared__ double w_val[kQbThreads / 32];
+  __shared__ int w_own[kQbThreads / 32];
+  __shared__ double sel[KMAX];
+  const double s = prm->cell[level], inv = 1.0 / s;
+  const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
+  const int dimx = prm->dim[level][0], dimy = prm->dim[level][1], dimz = prm->dim[level][2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t t = blockIdx.x; t < nq; t += gridDim.x) {
+    const uint32_t orig = pend_in[t];
+    const float4 q = __ldg(cloud + orig);
+    const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
+    const double ux = qx - ox, uy = qy - oy, uz = qz - oz;
+    const int cx = cell_of(ux, inv, dimx), cy = cell_of(uy, inv, dimy), cz = cell_of(uz, inv, dimz);
+    if (tid < 27) {
+      const int x = cx + tid % 3 - 1, y = cy + (tid / 3) % 3 - 1, z = cz + tid / 9 - 1;
+      uint32_t n = 0, b0 = 0;
+      if (x >= 0 && x < dimx && y >= 0 && y < dimy && z >= 0 && z < dimz) {
+        const unsigned long long key = cell_key(x, y, z);
+        uint32_t h = hash_key(key, mask);
+        unsigned long long kk;
+        while ((kk = keys[h]) != key && kk != kEmptyKey) h = (h + 1) & mask;
+        if (kk == key) { n = cnt[h]; b0 = start[h] - n; }
+      }
+      c_begin[tid] = b0;
+      c_pre[tid + 1] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      c_pre[0] = 0;
+      for (int i = 0; i < 27; ++i) c_pre[i + 1] += c_pre[i];
+    }
+    __syncthreads();
+    const uint32_t total = c_pre[27];
+
+    double best[KMAX];
+    double worst = INFINITY;
+    int found = 0, cell = 0;
+    for (uint32_t j0 = tid; j0 < total; j0 += kQbThreads * kQbBatch) {
+      float4 p[kQbBatch];
+#pragma unroll
+      for (int u = 0; u < kQbBatch; ++u) {             // the loads of a batch first: they overlap
+        const uint32_t j = j0 + u * kQbThreads;
+        if (j < total) {
+          while (j >= c_pre[cell + 1]) ++cell;
+          p[u] = sorted[c_begin[cell] + (j - c_pre[cell])];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kQbBatch; ++u) {
+        if (j0 + u * kQbThreads >= total) break;
+        const double ex = (double)p[u].x - qx, ey = (double)p[u].y - qy, ez = (double)p[u].z - qz;
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+        if (!(d2 < worst)) continue;
+        int pos = found < k ? found++ : k - 1;
+        while (pos > 0 && best[pos - 1] > d2) { best[pos] = best[pos - 1]; --pos; }
+        best[pos] = d2;
+        if (found == k) worst = best[k - 1];
+      }
+    }
+
+    // k-way selection over the threads' sorted lists
+    const int want = total < (uint32_t)k ? (int)total : k;
+    int head = 0;
+    for (int r = 0; r < want; ++r) {
+      double v = head < found ? best[head] : INFINITY;
+      int o = tid;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double v2 = __shfl_down_sync(0xffffffffu, v, off);
+        const int o2 = __shfl_down_sync(0xffffffffu, o, off);
+        if (v2 < v || (v2 == v && o2 < o)) { v = v2; o = o2; }
+      }
+      if (lane == 0) { w_val[warp] = v; w_own[warp] = o; }
+      __syncthreads();
+      v = w_val[0]; o = w_own[0];
+#pragma unroll
+      for (int w = 1; w < kQbThreads / 32; ++w)
+        if (w_val[w] < v || (w_val[w] == v && w_own[w] < o)) { v = w_val[w]; o = w_own[w]; }
+      if (o == tid) { ++head; sel[r] = v; }
+      __syncthreads();
+    }
+
+    if (tid == 0) {
+      double g = INFINITY;
+      if (cx - 1 > 0) g = fmin(g, ux - (double)(cx - 1) * s);
+      if (cx + 1 < dimx - 1) g = fmin(g, (double)(cx + 2) * s - ux);
+      if (cy - 1 > 0) g = fmin(g, uy - (double)(cy - 1) * s);
+      if (cy + 1 < dimy - 1) g = fmin(g, (double)(cy + 2) * s - uy);
+      if (cz - 1 > 0) g = fmin(g, uz - (double)(cz - 1) * s);
+      if (cz + 1 < dimz - 1) g = fmin(g, (double)(cz + 2) * s - uz);
+      g -= 1e-6 * s;
+      const bool final_ = isinf(g) || (want >= k && g > 0.0 && sel[k - 1] <= g * g) || level == kLevels - 1;
+      if (final_) {
+        double sum = 0.0;
+        for (int j = 0; j < want; ++j) sum = __dadd_rn(sum, sqrt(sel[j]));
+        avg[orig] = want ? sum / (double)want : -1.0;
+      } else {
+        pend_out[atomicAdd(&prm->counts[level + 1], 1u)] = orig;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -341,7 +495,10 @@ __global__ void __launch_bounds__(kRedBlocks) sor_final_kernel(SorParams* prm, i
   if (pass == 0) { prm->mean = sh[0] / nf; return; }
   prm->stddev = sqrt(sh[0] / (nf - 1.0));                       // Bessel's correction, as Open3D
   prm->thr = prm->mean + std_ratio * prm->stddev;
-  if (stats) { stats[0] = prm->mean; stats[1] = prm->stddev; stats[2] = prm->thr; }
+  if (stats) {
+    stats[0] = prm->mean; stats[1] = prm->stddev; stats[2] = prm->thr; stats[3] = nf;
+    for (int l = 0; l < kLevels; ++l) stats[4 + l] = (double)prm->counts[l];
+  }
 }
 
 // ------------------------------------------------------------------ ordered compaction of the inliers
@@ -430,7 +587,7 @@ int launch_outlier_removal(const float* cloud_f, long long N, int nb_neighbors, 
   int launches = 0;
   if (N == 0) {
     SL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(long long), st));
-    if (stats) SL_CUDA(cudaMemsetAsync(stats, 0xff, 3 * sizeof(double), st));      // NaN
+    if (stats) SL_CUDA(cudaMemsetAsync(stats, 0xff, 16 * sizeof(double), st));      // NaN
     return kOk;
   }
   const uint32_t mask = w.M - 1;
@@ -447,13 +604,21 @@ int launch_outlier_removal(const float* cloud_f, long long N, int nb_neighbors, 
     sor_scatter_kernel<<<kSorBlocks, 256, 0, st>>>(cloud, N, w.prm, l, w.slot, w.start, w.sorted);
     const uint32_t* pin = w.pend[l & 1];
     uint32_t* pout = w.pend[(l + 1) & 1];
-    if (nb_neighbors <= 32)
-      sor_query_kernel<32><<<kSorBlocks * 2, 128, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
-                                                           nb_neighbors, pin, pout, w.avg);
-    else
-      sor_query_kernel<128><<<kSorBlocks * 2, 128, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
-                                                            nb_neighbors, pin, pout, w.avg);
-    launches += 5;
+    // the two query kernels decide on the device which of them handles this level (kThreadModeMin)
+    const size_t q0_smem = (size_t)nb_neighbors * kQ0Threads * sizeof(double);      // <= 128 KB at 128 neighbours
+    if (l == 0 && q0_smem > 48 * 1024)
+      SL_CUDA(cudaFuncSetAttribute(sor_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q0_smem));
+    sor_query_kernel<<<kSorBlocks * 4, kQ0Threads, q0_smem, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
+                                                                 nb_neighbors, pin, pout, w.avg);
+    if (l > 0) {
+      if (nb_neighbors <= 32)
+        sor_query_block_kernel<32><<<kSorBlocks, kQbThreads, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start,
+                                                                      mask, nb_neighbors, pin, pout, w.avg);
+      else
+        sor_query_block_kernel<128><<<kSorBlocks, kQbThreads, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start,
+                                                                       mask, nb_neighbors, pin, pout, w.avg);
+    }
+    launches += l > 0 ? 6 : 5;
   }
   sor_partial_kernel<<<kRedBlocks, 256, 0, st>>>(w.avg, N, w.prm, 0, w.part);
   sor_final_kernel<<<1, kRedBlocks, 0, st>>>(w.prm, 0, w.part, std_ratio, stats);

@@ -447,7 +447,8 @@ def remove_statistical_outliers(cloud: torch.Tensor, nb_neighbors: int = 20, std
                                 details: bool = False):
     """``pcd.remove_statistical_outlier(nb_neighbors, std_ratio)`` (scanner/utils/visualize.py:104-105, Open3D 0.17)
     on a packed XYZRGB cloud ``(N,4)`` f32 (CUDA).  Returns ``(inlier_cloud (M,4), ind (M,) int64)``; with
-    ``details`` also ``mean_dist (N,) f64`` and ``stats (3,) f64`` = cloud mean, standard deviation, threshold."""
+    ``details`` also ``mean_dist (N,) f64`` and ``stats (16,) f64`` = cloud mean, standard deviation, threshold, finite records,
+    queries per grid level."""
     if not (cloud.is_cuda and cloud.dtype == torch.float32 and cloud.dim() == 2 and cloud.shape[1] == 4):
         raise TypeError("cloud must be a CUDA float32 (N,4) tensor")
     if nb_neighbors < 1 or not std_ratio > 0:
@@ -458,7 +459,7 @@ def remove_statistical_outliers(cloud: torch.Tensor, nb_neighbors: int = 20, std
     ind = torch.empty(n, dtype=torch.int64, device=dev)
     cnt = torch.empty(1, dtype=torch.int64, device=dev)
     mean_dist = torch.empty(n, dtype=torch.float64, device=dev) if details else None
-    stats = torch.empty(3, dtype=torch.float64, device=dev) if details else None
+    stats = torch.empty(16, dtype=torch.float64, device=dev) if details else None
     nbytes = lib().sl_outlier_workspace_bytes(n)
     ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

@@ -201,7 +201,8 @@ int sl_filter_cloud_box(const float* cloud, int64_t N, double threshold, float* 
  *   out_cloud   nullable device f32, capacity (N,4): the M inlier records
  *   out_index   nullable device int64 [N]: the M inlier indices (Open3D's `ind`)
  *   mean_dist   nullable device f64 [N]: the per-point mean neighbour distance (-1 for dropped records)
- *   stats       nullable device f64 [3]: cloud mean, standard deviation, threshold
+ *   stats       nullable device f64 [16]: cloud mean, standard deviation, threshold, finite records, then the
+ *               number of queries handled at each of the 12 grid levels (diagnostics)
  *   out_count   device int64 [1] = M
  *   workspace   device scratch of sl_outlier_workspace_bytes(N) */
 int sl_remove_statistical_outliers(const float* cloud, int64_t N, int nb_neighbors, double std_ratio,

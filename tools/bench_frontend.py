@@ -58,10 +58,11 @@ BOX = 2.0        # the synthetic plane stands 0.9 m from the camera; the referen
 us_box = timed(lambda: slb200.filter_cloud_box(cloud, BOX), 20)
 boxed = slb200.filter_cloud_box(cloud, BOX)
 us_sor = timed(lambda: slb200.remove_statistical_outliers(boxed, 20, 0.5), 5, warm=1)
-inl, ind = slb200.remove_statistical_outliers(boxed, 20, 0.5)
+inl, ind, _, st = slb200.remove_statistical_outliers(boxed, 20, 0.5, details=True)
 out["cloud_cleanup_1080p"] = {"points": n, "after_box": len(boxed), "after_outlier_removal": len(inl),
                               "box_filter_us": us_box, "outlier_removal_us": us_sor,
-                              "outlier_removal_Mpts_per_s": len(boxed) / us_sor}
+                              "outlier_removal_Mpts_per_s": len(boxed) / us_sor,
+                              "queries_per_grid_level": [int(x) for x in st[4:].tolist()]}
 if "--cpu" in sys.argv:
     from oracle import outlier_oracle as OO
     xyz = boxed[:, :3].cpu().numpy()
