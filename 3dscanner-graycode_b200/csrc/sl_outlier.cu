@@ -267,6 +267,16 @@ __global__ void __launch_bounds__(256) sor_scatter_kernel(const float4* __restri
 // 64-bit accesses, bank pair fixed by tid, so lanes inserting at different depths never conflict); the current
 // k-th best stays in a register, so a rejected candidate costs no memory access.  (In local memory the divergent
 // insertions touched a different cache line per lane and the kernel ran at L2 speed: 6.1 ms vs 0.x ms per 1.8 M points.)
+// The 27 cells are visited nearest first (own cell, 6 face, 12 edge, 8 corner neighbours) and a cell is skipped once
+// k candidates are held and the cell's box is farther than the k-th best: most of the final neighbours are found in
+// the first cells, so the later ones are mostly rejected by one compare or skipped whole.
+__constant__ int8_t kCellOrder[27][3] = {
+    {0, 0, 0},
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+    {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1},
+    {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
+    {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
+
 constexpr int kQ0Threads = 128;
 constexpr uint32_t kThreadModeMin = 8192;   // levels >= 1 with at least this many queries keep one thread per query
 __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __restrict__ cloud, SorParams* prm, int level,
@@ -295,31 +305,41 @@ __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __r
 
     int found = 0;
     double worst = INFINITY;                      // best[k-1] once k candidates are held
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, dimz - 1); ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, dimy - 1); ++y)
-        for (int x = max(cx - 1, 0); x <= min(cx + 1, dimx - 1); ++x) {
-          const unsigned long long key = cell_key(x, y, z);
-          uint32_t h = hash_key(key, mask);
-          unsigned long long kk;
-          while ((kk = keys[h]) != key && kk != kEmptyKey) h = (h + 1) & mask;
-          if (kk != key) continue;
-          const uint32_t end = start[h];
-          for (uint32_t j = end - cnt[h]; j < end; ++j) {
-            const float4 p = sorted[j];
-            const double ex = (double)p.x - qx, ey = (double)p.y - qy, ez = (double)p.z - qz;
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-            if (!(d2 < worst)) continue;
-            int pos = found < k ? found++ : k - 1;
-            while (pos > 0) {
-              const double above = best[(pos - 1) * kS];
-              if (!(above > d2)) break;
-              best[pos * kS] = above;
-              --pos;
-            }
-            best[pos * kS] = d2;
-            if (found == k) worst = best[(k - 1) * kS];
-          }
+    // distance from the query to the neighbour cells along each axis (0 for the own cell), shortened by a margin
+    // that covers the rounding of the cell assignment
+    const double marg = 1e-6 * s;
+    const double lox = fmax(ux - (double)cx * s - marg, 0.0), hix = fmax((double)(cx + 1) * s - ux - marg, 0.0);
+    const double loy = fmax(uy - (double)cy * s - marg, 0.0), hiy = fmax((double)(cy + 1) * s - uy - marg, 0.0);
+    const double loz = fmax(uz - (double)cz * s - marg, 0.0), hiz = fmax((double)(cz + 1) * s - uz - marg, 0.0);
+    for (int c = 0; c < 27; ++c) {
+      const int ax = kCellOrder[c][0], ay = kCellOrder[c][1], az = kCellOrder[c][2];
+      const int x = cx + ax, y = cy + ay, z = cz + az;
+      if (x < 0 || x >= dimx || y < 0 || y >= dimy || z < 0 || z >= dimz) continue;
+      const double gx = ax < 0 ? lox : (ax > 0 ? hix : 0.0), gy = ay < 0 ? loy : (ay > 0 ? hiy : 0.0),
+                   gz = az < 0 ? loz : (az > 0 ? hiz : 0.0);
+      if (gx * gx + gy * gy + gz * gz > worst) continue;      // nothing in that cell can enter the k best
+      const unsigned long long key = cell_key(x, y, z);
+      uint32_t h = hash_key(key, mask);
+      unsigned long long kk;
+      while ((kk = keys[h]) != key && kk != kEmptyKey) h = (h + 1) & mask;
+      if (kk != key) continue;
+      const uint32_t end = start[h];
+      for (uint32_t j = end - cnt[h]; j < end; ++j) {
+        const float4 p = sorted[j];
+        const double ex = (double)p.x - qx, ey = (double)p.y - qy, ez = (double)p.z - qz;
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+        if (!(d2 < worst)) continue;
+        int pos = found < k ? found++ : k - 1;
+        while (pos > 0) {
+          const double above = best[(pos - 1) * kS];
+          if (!(above > d2)) break;
+          best[pos * kS] = above;
+          --pos;
         }
+        best[pos * kS] = d2;
+        if (found == k) worst = best[(k - 1) * kS];
+      }
+    }
 
     // distance from the query to the faces of the scanned block that have unscanned cells behind them
     double g = INFINITY;
@@ -343,11 +363,36 @@ __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __r
 
 // Levels >= 1 with few queries left: one CTA per query.  The queries that get this far are the sparse ones
 // (noise far from the surface); their 3x3x3 block can hold a large part of the cloud, so the candidates of ONE
-// query are spread over the CTA's threads.  Every thread keeps the k smallest squared distances of its share (sorted); the k smallest of
-// the CTA are then drawn one at a time from the heads of those lists (a k-way selection: block-wide minimum,
-// the owner advances).  Same distances, same nearest-first summation as the thread-per-query kernel.
+// query are spread over the CTA's threads.  Keeping a sorted k-best list per thread makes nearly every candidate
+// step a divergent insertion, so the scan is done twice without any list instead:
+//   pass 1  every thread takes the minimum squared distance of its (strided) share; the k-th smallest of those
+//           1024 minima, T, is an upper bound of the query's k-th neighbour distance (they are k distinct candidates);
+//   pass 2  the candidates with d2 <= T -- a few dozen -- are appended to a shared list.
+// The k smallest of the list are then drawn one at a time (block-wide minimum, the owner advances), nearest first.
+// If the list overflows (thousands of exact ties at T) the CTA falls back to per-thread sorted lists, which is exact
+// for any input.  Same distances, same summation order as the thread-per-query kernel.
 constexpr int kQbThreads = 1024;
 constexpr int kQbBatch = 4;          // candidate loads in flight per thread
+constexpr int kQbList = 4096;        // capacity of the shared candidate list (4 per thread)
+
+// minimum over the CTA of (v, owner = tid); ties go to the lowest tid.  All threads get the result.
+__device__ __forceinline__ void block_min(double& v, int& o, double* w_val, int* w_own) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double v2 = __shfl_down_sync(0xffffffffu, v, off);
+    const int o2 = __shfl_down_sync(0xffffffffu, o, off);
+    if (v2 < v || (v2 == v && o2 < o)) { v = v2; o = o2; }
+  }
+  if (lane == 0) { w_val[warp] = v; w_own[warp] = o; }
+  __syncthreads();
+  v = w_val[0]; o = w_own[0];
+#pragma unroll
+  for (int w = 1; w < kQbThreads / 32; ++w)
+    if (w_val[w] < v || (w_val[w] == v && w_own[w] < o)) { v = w_val[w]; o = w_own[w]; }
+  __syncthreads();
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
     const float4* __restrict__ cloud, SorParams* prm, int level, const float4* __restrict__ sorted,
@@ -360,10 +405,12 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
   __shared__ double w_val[kQbThreads / 32];
   __shared__ int w_own[kQbThreads / 32];
   __shared__ double sel[KMAX];
+  __shared__ double list[kQbList];
+  __shared__ unsigned int list_n;
   const double s = prm->cell[level], inv = 1.0 / s;
   const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
   const int dimx = prm->dim[level][0], dimy = prm->dim[level][1], dimz = prm->dim[level][2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   for (uint32_t t = blockIdx.x; t < nq; t += gridDim.x) {
     const uint32_t orig = pend_in[t];
     const float4 q = __ldg(cloud + orig);
@@ -383,6 +430,7 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
       c_begin[tid] = b0;
       c_pre[tid + 1] = n;
     }
+    if (tid == 32) list_n = 0;
     __syncthreads();
     if (tid == 0) {
       c_pre[0] = 0;
@@ -391,30 +439,63 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
     __syncthreads();
     const uint32_t total = c_pre[27];
 
-    double best[KMAX];
-    double worst = INFINITY;
-    int found = 0, cell = 0;
-    for (uint32_t j0 = tid; j0 < total; j0 += kQbThreads * kQbBatch) {
-      float4 p[kQbBatch];
+    // f(d2) for every candidate of this thread's share; the loads of a batch are issued together
+    auto scan = [&](auto f) {
+      int cell = 0;
+      for (uint32_t j0 = tid; j0 < total; j0 += kQbThreads * kQbBatch) {
+        float4 p[kQbBatch];
 #pragma unroll
-      for (int u = 0; u < kQbBatch; ++u) {             // the loads of a batch first: they overlap
-        const uint32_t j = j0 + u * kQbThreads;
-        if (j < total) {
-          while (j >= c_pre[cell + 1]) ++cell;
-          p[u] = sorted[c_begin[cell] + (j - c_pre[cell])];
+        for (int u = 0; u < kQbBatch; ++u) {
+          const uint32_t j = j0 + u * kQbThreads;
+          if (j < total) {
+            while (j >= c_pre[cell + 1]) ++cell;
+            p[u] = sorted[c_begin[cell] + (j - c_pre[cell])];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kQbBatch; ++u) {
+          if (j0 + u * kQbThreads >= total) break;
+          const double ex = (double)p[u].x - qx, ey = (double)p[u].y - qy, ez = (double)p[u].z - qz;
+          f(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
         }
       }
-#pragma unroll
-      for (int u = 0; u < kQbBatch; ++u) {
-        if (j0 + u * kQbThreads >= total) break;
-        const double ex = (double)p[u].x - qx, ey = (double)p[u].y - qy, ez = (double)p[u].z - qz;
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-        if (!(d2 < worst)) continue;
-        int pos = found < k ? found++ : k - 1;
-        while (pos > 0 && best[pos - 1] > d2) { best[pos] = best[pos - 1]; --pos; }
-        best[pos] = d2;
-        if (found == k) worst = best[k - 1];
+    };
+
+    double thr = INFINITY;                 // total <= kQbList: every candidate goes to the list
+    if (total > kQbList) {
+      double tmin = INFINITY;
+      scan([&](double d2) { tmin = fmin(tmin, d2); });
+      for (int r = 0; r < k; ++r) {        // k-th smallest of the per-thread minima
+        double v = tmin;
+        int o = tid;
+        block_min(v, o, w_val, w_own);
+        if (o == tid) tmin = INFINITY;
+        thr = v;
       }
+    }
+    scan([&](double d2) {
+      if (d2 <= thr) {
+        const unsigned int i = atomicAdd(&list_n, 1u);
+        if (i < kQbList) list[i] = d2;
+      }
+    });
+    __syncthreads();
+    const bool overflow = list_n > kQbList;
+
+    double best[KMAX];                     // this thread's candidates for the final selection, sorted
+    int found = 0;
+    auto insert = [&](double d2, int cap) {
+      int pos;
+      if (found < cap) pos = found++;
+      else if (d2 < best[cap - 1]) pos = cap - 1;
+      else return;
+      while (pos > 0 && best[pos - 1] > d2) { best[pos] = best[pos - 1]; --pos; }
+      best[pos] = d2;
+    };
+    if (!overflow) {
+      for (uint32_t i = tid; i < list_n; i += kQbThreads) insert(list[i], kQbList / kQbThreads);
+    } else {
+      scan([&](double d2) { insert(d2, k); });
     }
 
     // k-way selection over the threads' sorted lists
@@ -423,21 +504,10 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
     for (int r = 0; r < want; ++r) {
       double v = head < found ? best[head] : INFINITY;
       int o = tid;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double v2 = __shfl_down_sync(0xffffffffu, v, off);
-        const int o2 = __shfl_down_sync(0xffffffffu, o, off);
-        if (v2 < v || (v2 == v && o2 < o)) { v = v2; o = o2; }
-      }
-      if (lane == 0) { w_val[warp] = v; w_own[warp] = o; }
-      __syncthreads();
-      v = w_val[0]; o = w_own[0];
-#pragma unroll
-      for (int w = 1; w < kQbThreads / 32; ++w)
-        if (w_val[w] < v || (w_val[w] == v && w_own[w] < o)) { v = w_val[w]; o = w_own[w]; }
+      block_min(v, o, w_val, w_own);
       if (o == tid) { ++head; sel[r] = v; }
-      __syncthreads();
     }
+    __syncthreads();
 
     if (tid == 0) {
       double g = INFINITY;

@@ -77,6 +77,17 @@ def test_degenerate_geometry():
     check(np.r_[scene(rng, 500, 0), [[1e6, -1e6, 1e6]]].astype(np.float32))            # one far point stretches the box
 
 
+def test_far_queries_against_a_dense_cluster():
+    """Sparse far points whose neighbours are a big dense cluster: they are handled one CTA per query, with the
+    threshold / candidate-list pass; 6000 coincident points make thousands of exact ties at the threshold (list
+    overflow -> the per-thread-list fallback), the jittered cluster takes the list path."""
+    rng = np.random.default_rng(15)
+    far = rng.uniform(-3, 3, (40, 3))
+    check(np.r_[np.zeros((6000, 3)), far].astype(np.float32))
+    check(np.r_[rng.normal(0, 0.01, (9000, 3)), far].astype(np.float32))
+    check(np.r_[np.repeat(rng.normal(0, 0.01, (30, 3)), 300, axis=0), far].astype(np.float32))   # 30 x 300 duplicates
+
+
 def test_non_finite_records_are_dropped():
     rng = np.random.default_rng(13)
     xyz = scene(rng, 1500, 20)
