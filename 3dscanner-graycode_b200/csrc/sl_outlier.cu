@@ -115,6 +115,20 @@ __device__ __forceinline__ uint32_t hash_key(unsigned long long k, uint32_t mask
   return (uint32_t)k & mask;
 }
 
+// Exact squared distance (float32 coordinates widened to float64, one rounding per operation) and its cheap
+// float32 estimate.  The estimate is within 1e-6 relative of the exact value (the inputs are exact, every float32
+// operation adds 2^-24), so `est > bound_up(limit)` proves `exact > limit` and the float64 path -- three
+// conversions and eight fp64 operations per candidate, all on slow pipes -- runs only for candidates that may count.
+__device__ __forceinline__ double dist2_exact(const float4& p, double qx, double qy, double qz) {
+  const double ex = (double)p.x - qx, ey = (double)p.y - qy, ez = (double)p.z - qz;
+  return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+}
+__device__ __forceinline__ float dist2_est(const float4& p, const float4& q) {
+  const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+  return ex * ex + ey * ey + ez * ez;
+}
+__device__ __forceinline__ float bound_up(double limit) { return __double2float_ru(limit * 1.00001); }
+
 // ------------------------------------------------------------------ planning
 __global__ void sor_init_kernel(SorParams* prm) {
   if (threadIdx.x == 0) {
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __r
 
     int found = 0;
     double worst = INFINITY;                      // best[k-1] once k candidates are held
+    float worst_f = INFINITY;                     // its float32 image, rounded up
     // distance from the query to the neighbour cells along each axis (0 for the own cell), shortened by a margin
     // that covers the rounding of the cell assignment
     const double marg = 1e-6 * s;
@@ -326,8 +341,8 @@ __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __r
       const uint32_t end = start[h];
       for (uint32_t j = end - cnt[h]; j < end; ++j) {
         const float4 p = sorted[j];
-        const double ex = (double)p.x - qx, ey = (double)p.y - qy, ez = (double)p.z - qz;
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+        if (dist2_est(p, q) > worst_f) continue;
+        const double d2 = dist2_exact(p, qx, qy, qz);
         if (!(d2 < worst)) continue;
         int pos = found < k ? found++ : k - 1;
         while (pos > 0) {
@@ -337,7 +352,7 @@ __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __r
           --pos;
         }
         best[pos * kS] = d2;
-        if (found == k) worst = best[(k - 1) * kS];
+        if (found == k) { worst = best[(k - 1) * kS]; worst_f = bound_up(worst); }
       }
     }
 
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
     __syncthreads();
     const uint32_t total = c_pre[27];
 
-    // f(d2) for every candidate of this thread's share; the loads of a batch are issued together
+    // f(point) for every candidate of this thread's share; the loads of a batch are issued together
     auto scan = [&](auto f) {
       int cell = 0;
       for (uint32_t j0 = tid; j0 < total; j0 += kQbThreads * kQbBatch) {
@@ -455,28 +470,29 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
 #pragma unroll
         for (int u = 0; u < kQbBatch; ++u) {
           if (j0 + u * kQbThreads >= total) break;
-          const double ex = (double)p[u].x - qx, ey = (double)p[u].y - qy, ez = (double)p[u].z - qz;
-          f(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
+          f(p[u]);
         }
       }
     };
 
-    double thr = INFINITY;                 // total <= kQbList: every candidate goes to the list
+    float thr_f = INFINITY;                // total <= kQbList: every candidate goes to the list
     if (total > kQbList) {
-      double tmin = INFINITY;
-      scan([&](double d2) { tmin = fmin(tmin, d2); });
+      float tmin = INFINITY;               // float32 estimates are enough for a bound
+      scan([&](const float4& p) { tmin = fminf(tmin, dist2_est(p, q)); });
+      double kth = INFINITY;
       for (int r = 0; r < k; ++r) {        // k-th smallest of the per-thread minima
-        double v = tmin;
+        double v = (double)tmin;
         int o = tid;
         block_min(v, o, w_val, w_own);
         if (o == tid) tmin = INFINITY;
-        thr = v;
+        kth = v;
       }
+      thr_f = bound_up(kth * 1.00001);     // estimate -> exact -> estimate: two margins
     }
-    scan([&](double d2) {
-      if (d2 <= thr) {
+    scan([&](const float4& p) {
+      if (dist2_est(p, q) <= thr_f) {
         const unsigned int i = atomicAdd(&list_n, 1u);
-        if (i < kQbList) list[i] = d2;
+        if (i < kQbList) list[i] = dist2_exact(p, qx, qy, qz);
       }
     });
     __syncthreads();
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
     if (!overflow) {
       for (uint32_t i = tid; i < list_n; i += kQbThreads) insert(list[i], kQbList / kQbThreads);
     } else {
-      scan([&](double d2) { insert(d2, k); });
+      scan([&](const float4& p) { insert(dist2_exact(p, qx, qy, qz), k); });
     }
 
     // k-way selection over the threads' sorted lists
