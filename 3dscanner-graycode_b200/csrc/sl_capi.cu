@@ -246,6 +246,17 @@ int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
                            cloud, (cudaStream_t)stream);
 }
 
+int sl_decode_triangulate_fused(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
+                                size_t scan_pitch, double eps, const uint8_t* white_rgb, const SlCalib* calib,
+                                int precision, const float* cam_rays, const float* proj_rays, int16_t* h_idx,
+                                int16_t* v_idx, void* workspace, float* cloud, int64_t* counts, void* stream) {
+  if (!workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
+  int rc = sl_decode_u8(frames, B, F, H, W, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr, workspace, stream);
+  if (rc) return rc;
+  if ((rc = sl_compact_offsets_decoded(B, H, W, workspace, counts, stream))) return rc;
+  return sl_emit_cloud(h_idx, v_idx, white_rgb, calib, precision, cam_rays, proj_rays, B, H, W, workspace, cloud, stream);
+}
+
 int sl_triangulate_points(const float* cam_pts, const float* proj_pts, int64_t N,
                           const SlCalib* calib, int precision, double* out, void* stream) {
   if (N < 0 || !calib) { set_error("bad argument"); return kErrBadArg; }

@@ -53,6 +53,8 @@ SIGNATURES = {
     "sl_emit_pairs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _vp, _vp, _vp]),
     "sl_emit_cloud": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sl_decode_triangulate_fused": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _vp, _vp]),
     "sl_triangulate_points": (_i, [_vp, _vp, _i64, C.POINTER(SlCalib), _i, _vp, _vp]),
     "sl_filter_box": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sl_filter_workspace_bytes": (_sz, [_i64]),

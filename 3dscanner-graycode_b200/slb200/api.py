@@ -582,18 +582,19 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
         raise ValueError("lens tables were built for another image / panel size")
     L = lib()
     st = _stream()
+    cam_t = _ptr(tables.cam) if tables is not None else None
+    proj_t = _ptr(tables.proj) if tables is not None else None
     with torch.cuda.device(dev):
         if bgr:
             check(L.sl_decode_bgr_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
                                      _ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(buffers.ws), st))
+            check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
+            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
+                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
         else:
-            check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
-                                 _ptr(buffers.h_idx), _ptr(buffers.v_idx), None, None, _ptr(buffers.ws), st))
-        check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
-        check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
-                              _PREC[precision], _ptr(tables.cam) if tables is not None else None,
-                              _ptr(tables.proj) if tables is not None else None,
-                              b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
+            check(L.sl_decode_triangulate_fused(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(white_rgb), C.byref(s),
+                                                _PREC[precision], cam_t, proj_t, _ptr(buffers.h_idx), _ptr(buffers.v_idx),
+                                                _ptr(buffers.ws), _ptr(buffers.cloud), _ptr(buffers.counts), st))
     return buffers
 
 

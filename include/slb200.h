@@ -170,6 +170,17 @@ int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
                   const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
                   int B, int H, int W, const void* workspace, float* cloud, void* stream);
 
+/* The whole device-resident path in one call: sl_decode_u8 (validity bitmap into `workspace`) ->
+ * sl_compact_offsets_decoded -> sl_emit_cloud, queued back to back on `stream`
+ * (src/3-capture_decode.py:75-100 + src/4-triangulate.py:50-64).  Arguments as in those three entry points;
+ * h_idx / v_idx are outputs the caller may also use.  "Fused" is about the interface: ordered compaction needs
+ * every column's point count before the first record can be placed, so the decode and the emission stay
+ * separate kernels joined by the offsets kernel. */
+int sl_decode_triangulate_fused(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
+                                size_t scan_pitch, double eps, const uint8_t* white_rgb, const SlCalib* calib,
+                                int precision, const float* cam_rays, const float* proj_rays, int16_t* h_idx,
+                                int16_t* v_idx, void* workspace, float* cloud, int64_t* counts, void* stream);
+
 /* Triangulate.triangulate (triangulate.py:73-97) on caller-supplied point pairs.
  * cam_pts, proj_pts device f32 (N,2); out device f64 (3,N) like the reference's return. */
 int sl_triangulate_points(const float* cam_pts, const float* proj_pts, int64_t N,
