@@ -299,11 +299,23 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     mbar_wait(smem_u32(&bars[s]), ph);
 
     // BGR stage -> this lane's gray column (out-of-range pixels of the last tile are zero-filled by the TMA)
-    const uint32_t src_s = smem_u32(smem + (size_t)s * stage_bytes) + lane * 12;
+    // plain loads from the stage (free to be scheduled several frames ahead; the mbarrier wait above is a compiler
+    // barrier), explicit st.shared into the gray column
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + lane * 3;
+    constexpr int kGroup = 4;                              // frames whose loads are issued before any is converted
+    const int nf = NB ? 4 * NB + 2 : F;                    // compile-time trip count: immediate smem offsets
 #pragma unroll
-    for (int f = 0; f < (NB ? 4 * NB + 2 : F); ++f) {      // compile-time trip count: immediate smem offsets
-      const uint32_t r = src_s + f * kBgrRowBytes;
-      sts_u32(gray_s + f * kBgrTilePx, gray4_from_bgr12(lds_u32(r), lds_u32(r + 4), lds_u32(r + 8)));
+    for (int f0 = 0; f0 < nf; f0 += kGroup) {
+      uint32_t w[kGroup][3];
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u)
+        if (f0 + u < nf) {
+          const uint32_t* r = src + (f0 + u) * (kBgrRowBytes / 4);
+          w[u][0] = r[0]; w[u][1] = r[1]; w[u][2] = r[2];
+        }
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u)
+        if (f0 + u < nf) sts_u32(gray_s + (f0 + u) * kBgrTilePx, gray4_from_bgr12(w[u][0], w[u][1], w[u][2]));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));        // the producer may refill the stage now

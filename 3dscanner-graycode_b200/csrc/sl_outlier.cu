@@ -56,8 +56,11 @@ struct SorWs {
   double* part;               // [2 * kRedBlocks]
   uint32_t* blk_cnt;          // [blocks + 1]
   long long* blk_base;        // [blocks + 1]
+  double* part_best;          // [kPartSlots * 128] sorted k-best lists of the query parts (sor_query_part_kernel)
+  uint32_t* q_total;          // [kPartSlots] candidates of each sparse query
   uint32_t M;
 };
+constexpr size_t kPartSlots = 8192 + 148 * 8;      // >= queries x parts on any level handled by the part kernel
 
 static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 static uint32_t table_size(long long N) {
@@ -86,6 +89,8 @@ static size_t sor_carve(void* base, long long N, SorWs* w) {
   s.part = (double*)take(2 * kRedBlocks * 8);
   s.blk_cnt = (uint32_t*)take(blocks * 4);
   s.blk_base = (long long*)take(blocks * 8);
+  s.part_best = (double*)take(kPartSlots * 128 * 8);
+  s.q_total = (uint32_t*)take(kPartSlots * 4);
   s.M = M;
   if (w) *w = s;
   return off;
@@ -376,19 +381,29 @@ __global__ void __launch_bounds__(kQ0Threads) sor_query_kernel(const float4* __r
   }
 }
 
-// Levels >= 1 with few queries left: one CTA per query.  The queries that get this far are the sparse ones
-// (noise far from the surface); their 3x3x3 block can hold a large part of the cloud, so the candidates of ONE
-// query are spread over the CTA's threads.  Keeping a sorted k-best list per thread makes nearly every candidate
-// step a divergent insertion, so the scan is done twice without any list instead:
-//   pass 1  every thread takes the minimum squared distance of its (strided) share; the k-th smallest of those
-//           1024 minima, T, is an upper bound of the query's k-th neighbour distance (they are k distinct candidates);
-//   pass 2  the candidates with d2 <= T -- a few dozen -- are appended to a shared list.
-// The k smallest of the list are then drawn one at a time (block-wide minimum, the owner advances), nearest first.
-// If the list overflows (thousands of exact ties at T) the CTA falls back to per-thread sorted lists, which is exact
-// for any input.  Same distances, same summation order as the thread-per-query kernel.
-constexpr int kQbThreads = 1024;
+// Levels >= 1 with few queries left (< kThreadModeMin).  The queries that get this far are the sparse ones (noise
+// far from the surface); their 3x3x3 block can hold a large part of the cloud, so the candidates of ONE query are
+// spread over the threads of a CTA and, when there are fewer queries than CTAs, over several CTAs ("parts",
+// contiguous slices of the candidate list).  Keeping a sorted k-best list per thread would make nearly every
+// candidate step a divergent insertion, so a part is scanned twice without any list instead:
+//   pass 1  every thread takes the minimum (float32 estimate) of its strided share; the k-th smallest of those
+//           minima bounds the part's k-th distance from above (they are k distinct candidates);
+//   pass 2  the candidates under the bound -- a few dozen -- get their exact distance and go to a shared list.
+// The k smallest of the list are drawn one at a time (block-wide minimum, the owner advances) and written, sorted,
+// to the part's slot of a scratch array; sor_query_merge_kernel merges the parts of a query (nearest first) and
+// applies the same finality test and summation as the thread-per-query kernel.  If the list overflows (thousands
+// of exact ties at the bound) the CTA falls back to per-thread sorted lists, which is exact for any input.
+constexpr int kQbThreads = 256;
 constexpr int kQbBatch = 4;          // candidate loads in flight per thread
-constexpr int kQbList = 4096;        // capacity of the shared candidate list (4 per thread)
+constexpr int kQbList = 4096;        // capacity of the shared candidate list
+constexpr int kQbItems = 148 * 8;    // CTAs of the part kernel; a query is cut into up to kQbMaxParts parts
+constexpr int kQbMaxParts = 64;
+constexpr int kMaxNeighbors = 128;
+
+__device__ __forceinline__ int parts_per_query(uint32_t nq) {
+  const int g = kQbItems / (int)(nq ? nq : 1u);
+  return g < 1 ? 1 : (g > kQbMaxParts ? kQbMaxParts : g);
+}
 
 // minimum over the CTA of (v, owner = tid); ties go to the lowest tid.  All threads get the result.
 __device__ __forceinline__ void block_min(double& v, int& o, double* w_val, int* w_own) {
@@ -409,29 +424,29 @@ __device__ __forceinline__ void block_min(double& v, int& o, double* w_val, int*
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
-    const float4* __restrict__ cloud, SorParams* prm, int level, const float4* __restrict__ sorted,
+__global__ void __launch_bounds__(kQbThreads) sor_query_part_kernel(
+    const float4* __restrict__ cloud, const SorParams* prm, int level, const float4* __restrict__ sorted,
     const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ start,
-    uint32_t mask, int k, const uint32_t* __restrict__ pend_in, uint32_t* __restrict__ pend_out,
-    double* __restrict__ avg) {
+    uint32_t mask, int k, const uint32_t* __restrict__ pend_in, double* __restrict__ part_best,
+    uint32_t* __restrict__ q_total) {
   const uint32_t nq = prm->counts[level];
   if (nq == 0 || nq >= kThreadModeMin) return;
   __shared__ uint32_t c_begin[27], c_pre[28];      // candidate ranges of the 27 cells, prefix of their sizes
   __shared__ double w_val[kQbThreads / 32];
   __shared__ int w_own[kQbThreads / 32];
-  __shared__ double sel[KMAX];
   __shared__ double list[kQbList];
   __shared__ unsigned int list_n;
-  const double s = prm->cell[level], inv = 1.0 / s;
+  const double inv = 1.0 / prm->cell[level];
   const double ox = prm->org[0], oy = prm->org[1], oz = prm->org[2];
   const int dimx = prm->dim[level][0], dimy = prm->dim[level][1], dimz = prm->dim[level][2];
   const int tid = threadIdx.x;
-  for (uint32_t t = blockIdx.x; t < nq; t += gridDim.x) {
-    const uint32_t orig = pend_in[t];
-    const float4 q = __ldg(cloud + orig);
+  const int G = parts_per_query(nq);
+  for (uint32_t item = blockIdx.x; item < nq * (uint32_t)G; item += gridDim.x) {
+    const uint32_t t = item / (uint32_t)G;
+    const int part = (int)(item - t * (uint32_t)G);
+    const float4 q = __ldg(cloud + pend_in[t]);
     const double qx = (double)q.x, qy = (double)q.y, qz = (double)q.z;
-    const double ux = qx - ox, uy = qy - oy, uz = qz - oz;
-    const int cx = cell_of(ux, inv, dimx), cy = cell_of(uy, inv, dimy), cz = cell_of(uz, inv, dimz);
+    const int cx = cell_of(qx - ox, inv, dimx), cy = cell_of(qy - oy, inv, dimy), cz = cell_of(qz - oz, inv, dimz);
     if (tid < 27) {
       const int x = cx + tid % 3 - 1, y = cy + (tid / 3) % 3 - 1, z = cz + tid / 9 - 1;
       uint32_t n = 0, b0 = 0;
@@ -453,34 +468,37 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
     }
     __syncthreads();
     const uint32_t total = c_pre[27];
+    if (part == 0 && tid == 0) q_total[t] = total;
+    const uint32_t slice = (total + (uint32_t)G - 1) / (uint32_t)G;
+    const uint32_t lo = min(total, (uint32_t)part * slice), hi = min(total, lo + slice);
 
-    // f(point) for every candidate of this thread's share; the loads of a batch are issued together
+    // f(point) for every candidate of this thread's share of [lo, hi); the loads of a batch are issued together
     auto scan = [&](auto f) {
       int cell = 0;
-      for (uint32_t j0 = tid; j0 < total; j0 += kQbThreads * kQbBatch) {
+      for (uint32_t j0 = lo + tid; j0 < hi; j0 += kQbThreads * kQbBatch) {
         float4 p[kQbBatch];
 #pragma unroll
         for (int u = 0; u < kQbBatch; ++u) {
           const uint32_t j = j0 + u * kQbThreads;
-          if (j < total) {
+          if (j < hi) {
             while (j >= c_pre[cell + 1]) ++cell;
             p[u] = sorted[c_begin[cell] + (j - c_pre[cell])];
           }
         }
 #pragma unroll
         for (int u = 0; u < kQbBatch; ++u) {
-          if (j0 + u * kQbThreads >= total) break;
+          if (j0 + u * kQbThreads >= hi) break;
           f(p[u]);
         }
       }
     };
 
-    float thr_f = INFINITY;                // total <= kQbList: every candidate goes to the list
-    if (total > kQbList) {
+    float thr_f = INFINITY;                // small part: every candidate goes to the list
+    if (hi - lo > kQbList) {
       float tmin = INFINITY;               // float32 estimates are enough for a bound
       scan([&](const float4& p) { tmin = fminf(tmin, dist2_est(p, q)); });
       double kth = INFINITY;
-      for (int r = 0; r < k; ++r) {        // k-th smallest of the per-thread minima
+      for (int r = 0; r < k; ++r) {        // k-th smallest of the per-thread minima (k <= 128 < kQbThreads)
         double v = (double)tmin;
         int o = tid;
         block_min(v, o, w_val, w_own);
@@ -514,18 +532,59 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
       scan([&](const float4& p) { insert(dist2_exact(p, qx, qy, qz), k); });
     }
 
-    // k-way selection over the threads' sorted lists
-    const int want = total < (uint32_t)k ? (int)total : k;
+    // k-way selection over the threads' sorted lists -> the part's k best, sorted (INFINITY-padded)
+    double* out = part_best + (size_t)item * k;
     int head = 0;
-    for (int r = 0; r < want; ++r) {
+    for (int r = 0; r < k; ++r) {
       double v = head < found ? best[head] : INFINITY;
       int o = tid;
       block_min(v, o, w_val, w_own);
-      if (o == tid) { ++head; sel[r] = v; }
+      if (o == tid) { if (head < found) ++head; out[r] = v; }
     }
     __syncthreads();
+  }
+}
 
-    if (tid == 0) {
+// one warp per query: merge the sorted k-best lists of its parts, then the finality test of the level
+__global__ void __launch_bounds__(128) sor_query_merge_kernel(const float4* __restrict__ cloud, SorParams* prm, int level,
+                                                               int k, const uint32_t* __restrict__ pend_in,
+                                                               const double* __restrict__ part_best,
+                                                               const uint32_t* __restrict__ q_total,
+                                                               uint32_t* __restrict__ pend_out, double* __restrict__ avg) {
+  const uint32_t nq = prm->counts[level];
+  if (nq == 0 || nq >= kThreadModeMin) return;
+  __shared__ double sel_all[4][kMaxNeighbors];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sel = sel_all[warp];
+  const int G = parts_per_query(nq);
+  const double s = prm->cell[level], inv = 1.0 / s;
+  const int dimx = prm->dim[level][0], dimy = prm->dim[level][1], dimz = prm->dim[level][2];
+  for (uint32_t t = blockIdx.x * 4 + warp; t < nq; t += gridDim.x * 4) {
+    // lane l owns the lists of parts l and l + 32 (G <= 64)
+    const double* la = part_best + ((size_t)t * G + lane) * k;
+    const double* lb = part_best + ((size_t)t * G + lane + 32) * k;
+    int ha = lane < G ? 0 : k, hb = lane + 32 < G ? 0 : k;
+    const uint32_t total = q_total[t];
+    const int want = total < (uint32_t)k ? (int)total : k;
+    for (int r = 0; r < want; ++r) {
+      const double va = ha < k ? la[ha] : INFINITY, vb = hb < k ? lb[hb] : INFINITY;
+      double v = fmin(va, vb);
+      int o = lane;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, off);
+        const int o2 = __shfl_xor_sync(0xffffffffu, o, off);
+        if (v2 < v || (v2 == v && o2 < o)) { v = v2; o = o2; }
+      }
+      if (o == lane) { if (va <= vb) ++ha; else ++hb; }
+      if (lane == 0) sel[r] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t orig = pend_in[t];
+      const float4 q = __ldg(cloud + orig);
+      const double ux = (double)q.x - prm->org[0], uy = (double)q.y - prm->org[1], uz = (double)q.z - prm->org[2];
+      const int cx = cell_of(ux, inv, dimx), cy = cell_of(uy, inv, dimy), cz = cell_of(uz, inv, dimz);
       double g = INFINITY;
       if (cx - 1 > 0) g = fmin(g, ux - (double)(cx - 1) * s);
       if (cx + 1 < dimx - 1) g = fmin(g, (double)(cx + 2) * s - ux);
@@ -543,7 +602,7 @@ __global__ void __launch_bounds__(kQbThreads) sor_query_block_kernel(
         pend_out[atomicAdd(&prm->counts[level + 1], 1u)] = orig;
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -698,13 +757,15 @@ int launch_outlier_removal(const float* cloud_f, long long N, int nb_neighbors, 
                                                                  nb_neighbors, pin, pout, w.avg);
     if (l > 0) {
       if (nb_neighbors <= 32)
-        sor_query_block_kernel<32><<<kSorBlocks, kQbThreads, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start,
-                                                                      mask, nb_neighbors, pin, pout, w.avg);
+        sor_query_part_kernel<32><<<kQbItems, kQbThreads, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
+                                                                   nb_neighbors, pin, w.part_best, w.q_total);
       else
-        sor_query_block_kernel<128><<<kSorBlocks, kQbThreads, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start,
-                                                                       mask, nb_neighbors, pin, pout, w.avg);
+        sor_query_part_kernel<128><<<kQbItems, kQbThreads, 0, st>>>(cloud, w.prm, l, w.sorted, w.keys, w.cnt, w.start, mask,
+                                                                    nb_neighbors, pin, w.part_best, w.q_total);
+      sor_query_merge_kernel<<<kSorBlocks, 128, 0, st>>>(cloud, w.prm, l, nb_neighbors, pin, w.part_best, w.q_total, pout,
+                                                         w.avg);
     }
-    launches += l > 0 ? 6 : 5;
+    launches += l > 0 ? 7 : 5;
   }
   sor_partial_kernel<<<kRedBlocks, 256, 0, st>>>(w.avg, N, w.prm, 0, w.part);
   sor_final_kernel<<<1, kRedBlocks, 0, st>>>(w.prm, 0, w.part, std_ratio, stats);

@@ -260,7 +260,7 @@ def run_gpu(args):
         slb200.scan_to_cloud(ring_frames[i % RING], ring_white[i % RING], calib, precision="fp32",
                              buffers=bufsets[k], calib_struct=cstruct, tables=tables)
 
-    # One CUDA graph per ring slot (the 4 launches of a step replay without host launch latency); slot i
+    # One CUDA graph per ring slot (the 3 launches of a step replay without host launch latency); slot i
     # always runs on stream i % S with that stream's buffers, so consecutive scans overlap: the small
     # compaction / emit kernels of one scan run beside the decode of the next.
     before = slb200.launch_count()
@@ -420,7 +420,7 @@ def run_gpu(args):
                                 else "5 Brown-Conrady iterations per valid pixel in the emit kernel"),
                        "parallelism": f"scan-sharded x{world}",
                        "l2": f"inputs rotate over a ring of {RING} resident scans ({RING * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": f"CUDA graph per scan (decode, strip-prefix, column-scan, emit); independent scans pipelined over {S} CUDA streams"},
+                       "launch": f"CUDA graph per scan (decode, strip-prefix + column scan, emit: 3 kernels); independent scans pipelined over {S} CUDA streams"},
             "scans_per_s": world * K / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),

@@ -32,7 +32,7 @@ g = torch.Generator(device=dev); g.manual_seed(1)
 ring = []
 for seed in range(4):
     frames, white = synth.render_scan(cam, proj, seed=seed, device=dev, patterns=pats, calib=calib)
-    bgr = (frames[..., None].to(torch.int16) + torch.randint(-20, 21, (*frames.shape, 3), generator=g, device=dev, dtype=torch.int16))
+    bgr = (frames[..., None].to(torch.int16) + torch.randint(-4, 5, (*frames.shape, 3), generator=g, device=dev, dtype=torch.int16))
     ring.append(bgr.clamp(0, 255).to(torch.uint8).contiguous())
 F = ring[0].shape[0]
 npix = cam[0] * cam[1]

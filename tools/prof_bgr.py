@@ -9,7 +9,7 @@ cam = proj = (1920, 1080)
 calib = synth.synthetic_calibration(cam, proj)
 frames, white = synth.render_scan(cam, proj, seed=3, device=dev, calib=calib)
 g = torch.Generator(device=dev); g.manual_seed(1)
-bgr = (frames[..., None].to(torch.int16) + torch.randint(-20, 21, (*frames.shape, 3), generator=g, device=dev, dtype=torch.int16))
+bgr = (frames[..., None].to(torch.int16) + torch.randint(-4, 5, (*frames.shape, 3), generator=g, device=dev, dtype=torch.int16))
 bgr = bgr.clamp(0, 255).to(torch.uint8).contiguous()
 for _ in range(3):
     h, v = slb200.decode_pixels_bgr(bgr)
