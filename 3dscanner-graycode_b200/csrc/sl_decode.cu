@@ -196,8 +196,16 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
     const int off = part * 128 + off_lane;                                 // pixel offset in tile
     uint32_t nib = 0;
     if (off < cnt) {
+#if !defined(SL_DECODE_GENERIC_LD)
+      // explicit ld.shared with a 32-bit address.  Through the lambda the compiler only sees a generic pointer and
+      // emits LD.E (generic loads with 64-bit addresses); measured 24.6 -> 22.9 us per isolated 1080p launch and
+      // 18.0 -> 17.3 us pipelined (88 % -> 92 % of the measured HBM peak).
+      const uint32_t base_s = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)off;
+      auto ld = [base_s](int f) { return lds_u32(base_s + (uint32_t)f * kTilePx); };
+#else
       const uint32_t* base = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes) + (off >> 2);
       auto ld = [&](int f) { return base[f * (kTilePx / 4)]; };
+#endif
       const long long px = px0 + off;
       int8_t* hc = CODES ? a.h_codes + (size_t)b * n * a.npix + px : nullptr;
       int8_t* vc = CODES ? a.v_codes + (size_t)b * n * a.npix + px : nullptr;
