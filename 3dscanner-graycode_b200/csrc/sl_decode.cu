@@ -239,6 +239,8 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
 // the unchanged per-quad decode on the gray tile.
 constexpr int kBgrTilePx = 128;
 constexpr int kBgrRowBytes = kBgrTilePx * 3;
+constexpr int kBgrFullBars = 32;     // per-tile "landed" barriers (> stages + consumer warps, see the kernel)
+static_assert(kConsumerWarps + 12 <= kBgrFullBars, "claims may run stages + warps - 1 tiles ahead");
 
 template <int NB>
 __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DecodeArgs a) {
@@ -249,21 +251,19 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
   const uint32_t stage_bytes = (uint32_t)F * kBgrRowBytes;
   uint8_t* gray_base = smem + (size_t)stages * stage_bytes;                 // [kConsumerWarps][F][32 words]
   uint64_t* bars = reinterpret_cast<uint64_t*>(gray_base + (size_t)kConsumerWarps * F * kBgrTilePx);
-  unsigned int* next_tile = reinterpret_cast<unsigned int*>(bars + 2 * stages);
-  // Tiles the producer has armed so far.  There are more consumer warps (one tile each) than stages, so a warp
-  // can hold a claim that is a whole ring revolution ahead of the stage's current phase; a parity wait
-  // cannot tell that apart from "already complete", hence a warp first waits until ITS tile has been armed.
-  volatile unsigned int* armed = next_tile + 1;
+  // bars[0..kBgrFullBars) = "tile landed", one per tile modulo kBgrFullBars; then `stages` "stage free" barriers.
+  // There are more consumer warps (one tile each) than stages, so a warp can hold a claim that is a whole revolution
+  // of the stage ring ahead; a parity wait on a per-STAGE barrier could not tell that apart from "already complete".
+  // Claims never run more than stages + kConsumerWarps - 1 (<= 27) tiles ahead of the oldest unreleased tile (the
+  // producer stalls on that tile's stage), so with 32 per-TILE barriers the previous use of a barrier has always
+  // landed when a warp waits for the next one, and the parity (tile / 32) & 1 is unambiguous.
+  unsigned int* next_tile = reinterpret_cast<unsigned int*>(bars + kBgrFullBars + stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0 && a.ticket) *a.ticket = 0;
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[stages + s]), 1);
-    }
+    for (int i = 0; i < kBgrFullBars + stages; ++i) mbar_init(smem_u32(&bars[i]), 1);
     *next_tile = 0;
-    *armed = 0;
     mbar_init_fence();
   }
   __syncthreads();
@@ -274,15 +274,13 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
       tma_prefetch_desc(&tmap);
       const uint64_t pol = policy_evict_first();
       int s = 0;
-      uint32_t ph = 0, tile = blockIdx.x, b = 0, n_armed = 0;
-      for (uint32_t t = blockIdx.x; t < total; t += grid, tile += grid) {
+      uint32_t ph = 0, tile = blockIdx.x, b = 0, it = 0;
+      for (uint32_t t = blockIdx.x; t < total; t += grid, tile += grid, ++it) {
         if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
-        mbar_wait(smem_u32(&bars[stages + s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bars[s]);
+        mbar_wait(smem_u32(&bars[kBgrFullBars + s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bars[it % kBgrFullBars]);
         mbar_arrive_expect_tx(full, stage_bytes);
         tma_load_3d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)(tile * (kBgrRowBytes / 4)), 0, (int)b, full, pol);
-        __threadfence_block();
-        *armed = ++n_armed;
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -303,8 +301,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     while (s >= (uint32_t)stages) { s -= (uint32_t)stages; ph ^= 1u; }
     tile += delta * grid;
     if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
-    while (*armed <= it) __nanosleep(20);
-    mbar_wait(smem_u32(&bars[s]), ph);
+    mbar_wait(smem_u32(&bars[it % kBgrFullBars]), (it / kBgrFullBars) & 1u);
 
     // BGR stage -> this lane's gray column (out-of-range pixels of the last tile are zero-filled by the TMA)
     // plain loads from the stage (free to be scheduled several frames ahead; the mbarrier wait above is a compiler
@@ -326,7 +323,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
         if (f0 + u < nf) sts_u32(gray_s + (f0 + u) * kBgrTilePx, gray4_from_bgr12(w[u][0], w[u][1], w[u][2]));
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&bars[stages + s]));        // the producer may refill the stage now
+    if (lane == 0) mbar_arrive(smem_u32(&bars[kBgrFullBars + s]));  // the producer may refill the stage now
 
     const long long px0 = (long long)tile * kBgrTilePx;
     const long long rem = a.npix4 - px0;
@@ -591,12 +588,12 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     a.n = n; a.F = F; a.e = (int)eps;
     const size_t stage_bytes = (size_t)F * kBgrRowBytes;
     const size_t gray_bytes = (size_t)kConsumerWarps * F * kBgrTilePx;
-    int stages = (int)((kSmemBudget - 256 - gray_bytes) / stage_bytes);
+    int stages = (int)((kSmemBudget - 512 - gray_bytes) / stage_bytes);
     if (stages > 12) stages = 12;
     if (stages < 2) { set_error("frame count too large for the BGR decode"); return kErrBadArg; }
     if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
     a.stages = stages;
-    const size_t smem = stages * stage_bytes + gray_bytes + 2 * stages * sizeof(uint64_t) + 16;
+    const size_t smem = stages * stage_bytes + gray_bytes + (kBgrFullBars + stages) * sizeof(uint64_t) + 16;
     const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
     CUtensorMap tmap;
     int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch, 3, kBgrRowBytes / 4);

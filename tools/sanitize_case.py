@@ -19,6 +19,18 @@ for cam in ((160, 96), (131, 67)):
     slb200.filter_box(pts, rgb.to(torch.float64), 5.0)
     slb200.decode_pixels(fr, eps=0.5)
     slb200.bgr_to_gray(wh); slb200.pair_diff_counts(fr)
+    # decode straight from BGR frames (TMA path for the aligned size, fp64-compare kernel for the ragged one)
+    bgr = fr[..., None].repeat(1, 1, 1, 3).contiguous()
+    bgr[..., 0] += 3
+    hb, vb = slb200.decode_pixels_bgr(bgr)
+    slb200.scan_to_cloud(torch.stack([bgr, bgr]).contiguous(), torch.stack([wh, wh]).contiguous(), calib, tables=tab, bgr=True)
+    # cloud clean-up: every level of the grid (surface + sparse far points + coincident points + a NaN record)
+    n = int(b.counts[-1])
+    cloud = torch.cat([b.cloud[:n], torch.rand((40, 4), device="cuda") * 8 - 4, torch.zeros((50, 4), device="cuda"),
+                       torch.full((1, 4), float("nan"), device="cuda")])
+    inl, ind = slb200.remove_statistical_outliers(cloud, 20, 0.5)
+    slb200.remove_statistical_outliers(cloud, 40, 1.0)
+    slb200.filter_cloud_box(cloud, 0.5)
     torch.cuda.synchronize()
-    print(cam, "points", int(b.counts[-1]))
+    print(cam, "points", n, "inliers", len(ind))
 print("done")
