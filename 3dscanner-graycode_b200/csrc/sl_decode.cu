@@ -288,7 +288,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
   }
 
   const uint32_t gray_s = smem_u32(gray_base + (size_t)warp * F * kBgrTilePx) + lane * 4;   // this lane's gray column
-  uint32_t it_prev = 0, s = 0, ph = 0, tile = blockIdx.x, b = 0;
+  uint32_t it_prev = 0, s = 0, tile = blockIdx.x, b = 0;
   for (;;) {
     unsigned int it = 0;
     if (lane == 0) it = atomicAdd(next_tile, 1u);
@@ -298,7 +298,7 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
     const uint32_t delta = it - it_prev;
     it_prev = it;
     s += delta;
-    while (s >= (uint32_t)stages) { s -= (uint32_t)stages; ph ^= 1u; }
+    while (s >= (uint32_t)stages) s -= (uint32_t)stages;
     tile += delta * grid;
     if (tile >= tps) { const uint32_t q = tile / tps; b += q; tile -= q * tps; }
     mbar_wait(smem_u32(&bars[it % kBgrFullBars]), (it / kBgrFullBars) & 1u);
