@@ -74,6 +74,8 @@ const char* sl_last_error(void) { return g_err; }
 int sl_version(void) { return 100; }
 int64_t sl_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int sl_set_decode_sm_reserve(int sms) { return set_decode_sm_reserve(sms); }
+
 int sl_device_check(int device) {
   if (device >= 0) SL_CUDA(cudaSetDevice(device));
   int sms = 0;

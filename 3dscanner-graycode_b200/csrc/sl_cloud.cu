@@ -716,6 +716,26 @@ __global__ void __launch_bounds__(256) filter_emit_kernel(const void* __restrict
 }
 
 // ------------------------------------------------------------------ launchers
+// Tuning knob (SL_STAGE2_PRIORITY): launch the stage-2 kernels with the highest stream priority, so that the short
+// offsets / emit kernels of one scan are placed ahead of the pending decode CTAs of the other streams.
+template <class Kernel, class... Args>
+static cudaError_t launch_stage2(Kernel k, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+#if defined(SL_STAGE2_PRIORITY)
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributePriority;
+  attr[0].val.priority = hi;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, args...);
+#else
+  k<<<grid, block, smem, st>>>(args...);
+  return cudaSuccess;
+#endif
+}
+
 static int grid_for(long long items, int per_block, int cap = 1 << 20) {
   long long g = (items + per_block - 1) / per_block;
   if (g > cap) g = cap;
@@ -732,9 +752,9 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   const size_t strip_smem = (size_t)c.bands * 32 * sizeof(uint32_t);
   if (strip_smem > 48 * 1024)     // rare (more than 12288 rows): opt in to the larger carve-out
     SL_CUDA(cudaFuncSetAttribute(strip_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem));
-  strip_prefix_kernel<<<B * strips, kStripWarps * 32, strip_smem, st>>>(
-      c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot, c.col_base, B, counts,
-      c.ticket);
+  SL_CUDA(launch_stage2(strip_prefix_kernel, B * strips, kStripWarps * 32, strip_smem, st,
+                        (const uint32_t*)c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot,
+                        c.col_base, B, counts, c.ticket));
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
@@ -833,7 +853,7 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   if ((rc = check_emit_size(a))) return rc;
   if (cam_rays) {
     if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmemCloud, st>>>(a);
-    else emit_kernel<kModeTable32><<<g, thr, kEmitSmemCloud, st>>>(a);
+    else SL_CUDA(launch_stage2(emit_kernel<kModeTable32>, g, thr, (size_t)kEmitSmemCloud, st, a));
   } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmemCloud, st>>>(a);
   else emit_kernel<kModeCloud32><<<g, thr, kEmitSmemCloud, st>>>(a);
   count_launch();

@@ -11,6 +11,7 @@
 // K1g decode_generic_kernel any alignment / any eps: direct loads, fp64 compares exactly as
 //                           scanner/grayCode/decode_codes.py:172-182 writes them.
 // K1m codes_to_pixels_kernel run merge (src/3-capture_decode.py:95-96) + Gray->decimal (:99-100).
+#include <atomic>
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 #if !defined(SL_NO_BINV_TABLE) && !defined(SL_BINV_TABLE)
@@ -467,6 +468,19 @@ __global__ void __launch_bounds__(256) codes_to_pixels_kernel(const int8_t* __re
 }
 
 // ------------------------------------------------------------------ launchers
+// SMs the persistent decode kernels leave to other work (sl_set_decode_sm_reserve).  A caller that pipelines
+// independent scans over several streams gets more out of the GPU when the decode grid does not cover every SM:
+// the offsets / emit kernels of the other scans then always find SMs of their own instead of the two CTA slots
+// beside a resident decode CTA.  Measured on the bench step (4 streams): 34.2 us per scan with 148 CTAs, 33.4 with
+// 145, 32.4 with 140, 32.6 with 138 / 135; a launch on its own gets slower instead (21.9 -> 23.0 us at 140), so the
+// default is 0.
+static std::atomic<int> g_decode_sm_reserve{0};
+int set_decode_sm_reserve(int sms) { return g_decode_sm_reserve.exchange(sms < 0 ? 0 : sms); }
+static int decode_grid_sms(int num_sms) {
+  const int r = g_decode_sm_reserve.load(std::memory_order_relaxed);
+  return num_sms > 2 * r ? num_sms - r : num_sms;
+}
+
 // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link dependency
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -594,7 +608,8 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
     a.stages = stages;
     const size_t smem = stages * stage_bytes + gray_bytes + (kBgrFullBars + stages) * sizeof(uint64_t) + 16;
-    const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
+    const int sms = decode_grid_sms(num_sms);
+    const int grid = (int)(a.total_tiles < sms ? a.total_tiles : sms);
     CUtensorMap tmap;
     int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch, 3, kBgrRowBytes / 4);
     if (rc != kOk) return rc;
@@ -616,7 +631,8 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
       if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
       a.stages = stages;
       const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16;
-      const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
+      const int sms = decode_grid_sms(num_sms);
+      const int grid = (int)(a.total_tiles < sms ? a.total_tiles : sms);
       CUtensorMap tmap;
       int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch);
       if (rc != kOk) return rc;

@@ -38,6 +38,7 @@ SIGNATURES = {
     "sl_last_error": (C.c_char_p, []),
     "sl_version": (_i, []),
     "sl_device_check": (_i, [_i]),
+    "sl_set_decode_sm_reserve": (_i, [_i]),
     "sl_decode_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sl_decode_bgr_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp]),
     "sl_direct_indirect": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp]),

@@ -36,6 +36,12 @@ def launch_count() -> int:
     return int(lib().sl_launch_count())
 
 
+def set_decode_sm_reserve(sms: int) -> int:
+    """SMs the persistent decode kernels leave to the kernels of other streams (``sl_set_decode_sm_reserve``);
+    set it (8 on a B200) when independent scans are pipelined over several CUDA streams.  Returns the previous value."""
+    return int(lib().sl_set_decode_sm_reserve(int(sms)))
+
+
 # --------------------------------------------------------------------------- calibration
 @dataclass
 class Calibration:

@@ -251,6 +251,10 @@ def run_gpu(args):
         ring_frames.append(fr); ring_white.append(wh)
     del pats
     S = max(1, min(args.streams, RING))
+    # the persistent decode grid leaves a few SMs to the offsets / emit kernels of the scans in flight on the other
+    # streams (sl_set_decode_sm_reserve; launch geometry is fixed when the graphs below are captured)
+    sm_reserve = (8 if S > 1 else 0) if args.sm_reserve is None else max(0, args.sm_reserve)
+    slb200.set_decode_sm_reserve(sm_reserve)
     bufsets = [CloudBuffers.allocate(1, H, W, dev) for _ in range(S)]
     bufs = bufsets[0]
     tables = None if args.lens == "iterate" else slb200.LensTables(calib, CAM_SIZE, dev)   # once per calibration
@@ -333,7 +337,9 @@ def run_gpu(args):
     torch.cuda.synchronize()
     decode_ms = timed(dgraphs, kr) / kr
     # (b) isolated: ONE graph holding RING decode launches in sequence on one stream (kernel after kernel, no
-    # overlap between launches; the graph only removes the host launch latency)
+    # overlap between launches; the graph only removes the host launch latency).  Nothing else runs, so the
+    # grid covers every SM.
+    slb200.set_decode_sm_reserve(0)
     with torch.cuda.stream(streams[0]):
         chain = torch.cuda.CUDAGraph()
         with torch.cuda.graph(chain, stream=streams[0]):
@@ -348,6 +354,7 @@ def run_gpu(args):
         d1.record(streams[0])
     torch.cuda.synchronize()
     decode_solo_ms = d0.elapsed_time(d1) / (reps * RING)
+    slb200.set_decode_sm_reserve(sm_reserve)
     peak, peak_src = load_peaks()
     algo_bytes = (N_FRAMES + 4) * W * H                      # F u8 reads + two int16 writes per pixel
     achieved = algo_bytes / (decode_ms * 1e-3) / 1e9
@@ -420,7 +427,8 @@ def run_gpu(args):
                                 else "5 Brown-Conrady iterations per valid pixel in the emit kernel"),
                        "parallelism": f"scan-sharded x{world}",
                        "l2": f"inputs rotate over a ring of {RING} resident scans ({RING * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": f"CUDA graph per scan (decode, strip-prefix + column scan, emit: 3 kernels); independent scans pipelined over {S} CUDA streams"},
+                       "launch": f"CUDA graph per scan (decode, strip-prefix + column scan, emit: 3 kernels); independent scans pipelined over {S} CUDA streams",
+                       "decode_grid": f"one persistent CTA per SM, {sm_reserve} SMs left to the other streams' kernels"},
             "scans_per_s": world * K / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
@@ -449,6 +457,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lens", default="tables", choices=["tables", "iterate"])
     ap.add_argument("--streams", type=int, default=STREAMS)
+    ap.add_argument("--sm-reserve", type=int, default=None,
+                    help="SMs the decode grid leaves to the other streams' kernels (default: 8 when pipelining, else 0)")
     ap.add_argument("--ring", type=int, default=RING)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

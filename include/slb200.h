@@ -59,6 +59,12 @@ int sl_version(void);
 /* 0 if `device` (or the current device when < 0) is an sm_100 GPU */
 int sl_device_check(int device);
 
+/* Process-wide tuning option: the persistent decode kernels launch one CTA per SM; `sms` SMs are left out of that
+ * grid (default 0).  Worth setting (8 on a B200) by callers that pipeline independent scans over several CUDA
+ * streams: the short offsets / emit kernels of the other scans then find SMs of their own (bench step 34.2 -> 32.4 us
+ * per 1080p scan); a decode launch running alone gets ~5 % slower.  Returns the previous value. */
+int sl_set_decode_sm_reserve(int sms);
+
 /* ---------------------------------------------------------------- decode (stage 1) */
 
 /* Fused decode of B frame stacks.

@@ -58,6 +58,7 @@ def single_scan(name, cam, proj, ring, iters, streams):
     torch.cuda.synchronize()
     res = {}
     for s_ in sorted({1, streams}):
+        slb200.set_decode_sm_reserve(8 if s_ > 1 else 0)     # pipelined: leave 8 SMs to the other streams' kernels
         fns = [(lambda i=i: slb200.scan_to_cloud(scans[i][0], scans[i][1], calib, buffers=bufs[i % s_], tables=tables,
                                                  calib_struct=cs)) for i in range(ring)]
         us = time_graphs(fns, iters, s_)
@@ -68,6 +69,7 @@ def single_scan(name, cam, proj, ring, iters, streams):
         gbs = (F + 4) * cam[0] * cam[1] / (dus * 1e-6) / 1e9
         res[f"streams_{s_}"] = {"us_per_scan": us, "Mpx_per_s": mpx / (us * 1e-6), "scans_per_s": 1e6 / us,
                                 "decode_us": dus, "decode_GBps": gbs, "decode_frac_of_measured_peak": gbs / PEAK}
+    slb200.set_decode_sm_reserve(0)
     res["valid_fraction"] = float(bufs[0].counts[1]) / (cam[0] * cam[1])
     out[name] = res
     del scans, bufs
