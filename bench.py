@@ -363,7 +363,8 @@ def run_gpu(args):
     # ---- e2e through the host-buffer C-ABI call: pinned host frames in, host cloud out
     e2e = None
     if not args.no_e2e:
-        eb = min(4, RING)                                    # scans per call, overlapped on the pipeline's streams
+        eb = min(12, RING)                                   # scans per call (a turntable batch), overlapped on the pipeline's
+                                                             # streams; a call returns when its last cloud is in host memory
         host_frames = torch.empty((eb, N_FRAMES, H, W), dtype=torch.uint8).pin_memory()
         host_white = torch.empty((eb, H, W, 3), dtype=torch.uint8).pin_memory()
         for i in range(eb):
@@ -371,7 +372,7 @@ def run_gpu(args):
         pipe = slb200.Pipeline(N_FRAMES, H, W, max_batch=eb, device=local)
         cloud_h = torch.empty((eb * H * W, 4), dtype=torch.float32).pin_memory()
         cnt_h = torch.empty(eb + 1, dtype=torch.int64)
-        calls = max(2, min(10, (K + eb - 1) // eb))
+        calls = max(2, min(5, (K + eb - 1) // eb))
         pipe.scan_to_cloud(host_frames, host_white, calib, cloud=cloud_h, counts=cnt_h)   # warm-up
         barrier()
         t0 = time.perf_counter()
