@@ -327,7 +327,14 @@ struct SlPipeline {
     long long* counts = nullptr;       // device [2]
     long long* counts_pinned = nullptr; // host pinned [2]
     float* cloud = nullptr;      // [H*W][4] packed records
+    // streaming API: the scan in flight on this slot (sl_pipeline_submit) and where its results go
+    bool pending = false;
+    float* user_cloud = nullptr;
+    long long user_cap = 0;
+    int64_t* user_count = nullptr;
   } slot[kSlots];
+  long long submitted = 0;       // scans handed to sl_pipeline_submit so far
+  bool stream_overflow = false;  // a submitted scan did not fit its cloud buffer (reported by sl_pipeline_flush)
   int8_t* h_codes = nullptr;   // lazily allocated for sl_decode_host with codes
   int8_t* v_codes = nullptr;
   // lens tables of the last calibration seen (rebuilt when the calibration changes)
@@ -402,6 +409,8 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
   if (B < 1 || B > p->max_batch) { set_error("B=%d outside 1..max_batch=%d", B, p->max_batch); return kErrBadArg; }
   if ((h_idx_host == nullptr) != (v_idx_host == nullptr)) { set_error("h_idx_host and v_idx_host go together"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  for (auto& s : p->slot)
+    if (s.pending) { set_error("scans submitted with sl_pipeline_submit are still in flight: call sl_pipeline_flush first"); return kErrState; }
   SL_CUDA(cudaSetDevice(p->device));
   const size_t npix = (size_t)p->H * p->W;
   const size_t stack = (size_t)p->F * npix;
@@ -478,6 +487,88 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
   if (rc != kOk) return rc;
   counts_host[B] = total;
   if (overflow) { set_error("cloud of %lld points exceeds cap_points=%lld", total, (long long)cap_points); return kErrBadArg; }
+  return kOk;
+}
+
+// ---- streaming: scans are submitted one at a time and complete in the background ----------------------------
+static int pipeline_tables(SlPipeline* p, const SlCalib* calib) {
+  const size_t npix = (size_t)p->H * p->W;
+  if (calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad projector size"); return kErrBadArg; }
+  if (p->have_tables && memcmp(&p->table_calib, calib, sizeof(SlCalib)) == 0) return kOk;
+  for (auto& s : p->slot) SL_CUDA(cudaStreamSynchronize(s.stream));
+  const size_t pe = (size_t)calib->proj_w * calib->proj_h * 2;
+  if (!p->cam_rays) SL_CUDA(cudaMalloc(&p->cam_rays, npix * 2 * sizeof(float)));
+  if (pe > p->proj_rays_elems) {
+    cudaFree(p->proj_rays); p->proj_rays = nullptr; p->proj_rays_elems = 0;
+    SL_CUDA(cudaMalloc(&p->proj_rays, pe * sizeof(float)));
+    p->proj_rays_elems = pe;
+  }
+  const int trc = launch_lens_tables(*calib, p->W, p->H, p->cam_rays, p->proj_rays, p->slot[0].stream);
+  if (trc) return trc;
+  SL_CUDA(cudaStreamSynchronize(p->slot[0].stream));
+  p->table_calib = *calib;
+  p->have_tables = true;
+  return kOk;
+}
+
+// the scan occupying `s` is on its way out: its count is read, its cloud copy queued on the slot's stream
+static int pipeline_retire(SlPipeline* p, SlPipeline::Slot& s) {
+  if (!s.pending) return kOk;
+  SL_CUDA(cudaEventSynchronize(s.counted));
+  const long long n = s.counts_pinned[0];
+  *s.user_count = n;
+  if (n > s.user_cap) p->stream_overflow = true;
+  else if (n > 0)
+    SL_CUDA(cudaMemcpyAsync(s.user_cloud, s.cloud, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+  s.pending = false;
+  return kOk;
+}
+
+int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host, const SlCalib* calib,
+                       int precision, double eps, float* cloud_host, int64_t cap_points, int64_t* count_host) {
+  if (!p || !frames_host || !calib || !cloud_host || !count_host) { set_error("null argument"); return kErrBadArg; }
+  if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  SL_CUDA(cudaSetDevice(p->device));
+  int rc = pipeline_tables(p, calib);
+  if (rc) return rc;
+  const size_t npix = (size_t)p->H * p->W;
+  const size_t stack = (size_t)p->F * npix;
+  auto& s = p->slot[p->submitted % SlPipeline::kSlots];
+  if ((rc = pipeline_retire(p, s))) return rc;        // the scan submitted kSlots calls ago leaves the slot first
+  SL_CUDA(cudaMemcpyAsync(s.frames, frames_host, stack, cudaMemcpyHostToDevice, s.stream));
+  if (white_rgb_host) SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host, npix * 3, cudaMemcpyHostToDevice, s.stream));
+  long long bm_words = 0;
+  unsigned int* ticket = nullptr;
+  uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &ticket);
+  if ((rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
+                          ticket, p->sms, s.stream))) return rc;
+  if ((rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream))) return rc;
+  SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
+  if ((rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
+                              1, p->H, p->W, s.ws, s.cloud, s.stream))) return rc;
+  SL_CUDA(cudaEventRecord(s.counted, s.stream));
+  s.pending = true;
+  s.user_cloud = cloud_host; s.user_cap = cap_points; s.user_count = count_host;
+  ++p->submitted;
+  return kOk;
+}
+
+int sl_pipeline_flush(SlPipeline* p) {
+  if (!p) { set_error("null argument"); return kErrBadArg; }
+  SL_CUDA(cudaSetDevice(p->device));
+  int rc = kOk;
+  for (int k = 0; k < SlPipeline::kSlots && rc == kOk; ++k)      // oldest first
+    rc = pipeline_retire(p, p->slot[(p->submitted + k) % SlPipeline::kSlots]);
+  for (auto& s : p->slot) {
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess && rc == kOk) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (rc != kOk) return rc;
+  if (p->stream_overflow) {
+    p->stream_overflow = false;
+    set_error("a submitted scan produced more points than its cap_points (its count is written, its cloud is not)");
+    return kErrBadArg;
+  }
   return kOk;
 }
 

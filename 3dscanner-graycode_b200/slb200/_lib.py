@@ -65,6 +65,8 @@ SIGNATURES = {
     "sl_pipeline_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "sl_pipeline_destroy": (None, [_vp]),
     "sl_scan_to_cloud_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(SlCalib), _i, _d, _vp, _vp, _vp, _i64, _vp]),
+    "sl_pipeline_submit": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _d, _vp, _i64, _vp]),
+    "sl_pipeline_flush": (_i, [_vp]),
     "sl_decode_host": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp]),
     "sl_launch_count": (_i64, []),
 }

@@ -660,6 +660,24 @@ class Pipeline:
         n = int(counts[b])
         return cloud[:n], counts
 
+    def submit(self, frames, white_rgb, calib: Calibration, cloud, count, precision="fp32", eps: float = 1.0):
+        """Streaming form (``sl_pipeline_submit``): queue ONE scan ``(F,H,W)`` uint8 (host, ideally pinned) and
+        return; its records go to the host tensor ``cloud`` ``(cap,4)`` f32 and its point count to ``count``
+        (int64 host tensor / array of one element).  Results are valid after :meth:`flush`; the buffers must
+        stay alive until then."""
+        if tuple(frames.shape) != (self.f, self.h, self.w):
+            raise ValueError(f"frames must be ({self.f},{self.h},{self.w})")
+        if getattr(frames, "dtype", None) not in (np.uint8, torch.uint8):
+            raise TypeError("frames must be uint8")
+        s = calib.struct()
+        check(lib().sl_pipeline_submit(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), C.byref(s),
+                                       _PREC[precision], float(eps), self._host_ptr(cloud), int(cloud.shape[0]),
+                                       self._host_ptr(count)))
+
+    def flush(self):
+        """Wait until every submitted scan's cloud and count are in host memory (``sl_pipeline_flush``)."""
+        check(lib().sl_pipeline_flush(self._h))
+
     def decode(self, frames, eps: float = 1.0, codes: bool = False):
         """Host uint8 ``(B,F,H,W)`` -> host int16 ``h_pixels, v_pixels`` [+ int8 tri-state codes]."""
         shape = tuple(frames.shape)

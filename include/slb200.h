@@ -248,6 +248,21 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
                           int16_t* h_idx_host, int16_t* v_idx_host, float* cloud_host,
                           int64_t cap_points, int64_t* counts_host);
 
+/* Streaming form of the same path (one scan per call, as a capture loop produces them): sl_pipeline_submit queues the
+ * H2D copies, the kernels and the count read-back of one scan on the next of the pipeline's streams and returns; the
+ * scan submitted 3 calls earlier is retired first (its count is written to its count_host, its cloud copy queued).
+ * sl_pipeline_flush retires everything still in flight and returns when every submitted scan's cloud and count are
+ * in host memory (results may only be read after it).  Host buffers must stay valid until then; pinned memory keeps
+ * the copies asynchronous.
+ *   frames_host  u8 [F][H][W]     white_rgb_host  u8 [H][W][3] (nullable)
+ *   cloud_host   f32, capacity cap_points*4      count_host  int64 [1]
+ * A scan with more than cap_points points gets its count but not its cloud; sl_pipeline_flush then fails with
+ * SL_ERR_BAD_ARG.  The blocking calls fail with SL_ERR_STATE while submitted scans are in flight. */
+int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host,
+                       const SlCalib* calib, int precision, double eps, float* cloud_host, int64_t cap_points,
+                       int64_t* count_host);
+int sl_pipeline_flush(SlPipeline* p);
+
 /* Decode only, HOST buffers (get_codes + gray_to_decimal loops for one or more scans). */
 int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
                    int16_t* h_idx_host, int16_t* v_idx_host, int8_t* h_codes_host,

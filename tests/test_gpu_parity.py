@@ -445,6 +445,45 @@ def test_pipeline_host_buffers(T):
     pipe.close()
 
 
+def test_pipeline_streaming_submit_flush(T):
+    """sl_pipeline_submit / sl_pipeline_flush: scans submitted one at a time (more than the pipeline has slots, two
+    calibrations) give the same records as the device-resident path, bit for bit."""
+    import slb200
+    from slb200 import synth
+    cam_size, proj_size = (320, 200), (1024, 768)
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    calib2 = synth.synthetic_calibration(cam_size, proj_size)
+    calib2.proj_T = calib.proj_T * 1.25
+    scans = [synth.render_scan(cam_size, proj_size, seed=s, device="cpu") for s in range(8)]
+    frames = [s[0].contiguous().pin_memory() for s in scans]
+    white = [s[1].contiguous().pin_memory() for s in scans]
+    pipe = slb200.Pipeline(frames[0].shape[0], 200, 320, max_batch=1)
+    clouds = [T.zeros((200 * 320, 4), dtype=T.float32).pin_memory() for _ in scans]
+    counts = [T.zeros(1, dtype=T.int64) for _ in scans]
+    cals = [calib if i < 5 else calib2 for i in range(8)]
+    for i in range(8):
+        pipe.submit(frames[i], white[i] if i != 3 else None, cals[i], clouds[i], counts[i])
+    with pytest.raises(slb200.SlError):                       # blocking call while scans are in flight
+        pipe.scan_to_cloud(frames[0][None], white[0][None], calib)
+    pipe.flush()
+    for i in range(8):
+        tables = slb200.LensTables(cals[i], cam_size, "cuda")
+        dev = slb200.scan_to_cloud(frames[i].cuda(), white[i].cuda() if i != 3 else None, cals[i], tables=tables)
+        n = int(dev.counts[1])
+        assert int(counts[i]) == n and n > 0
+        assert T.equal(clouds[i][:n].view(T.int32), dev.cloud[:n].cpu().view(T.int32))
+    pipe.flush()                                              # nothing pending: a no-op
+    # a cloud buffer that is too small: the count arrives, flush reports the overflow
+    small = T.zeros((10, 4), dtype=T.float32).pin_memory()
+    pipe.submit(frames[0], white[0], calib, small, counts[0])
+    with pytest.raises(slb200.SlError):
+        pipe.flush()
+    assert int(counts[0]) > 10
+    cloud, cnt = pipe.scan_to_cloud(frames[1][None], white[1][None], calib)      # the pipeline is usable again
+    assert int(cnt[1]) == int(counts[1])
+    pipe.close()
+
+
 def test_dropin_scripts_flow(T):
     """The logic of src/3-capture_decode.py:75-104 and src/4-triangulate.py:50-71 against the drop-in
     `scanner` package, with the oracle standing in for the reference."""
