@@ -33,6 +33,46 @@ def test_library_exports_every_declared_symbol():
     assert lib.sl_launch_count() == 0
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every prototype in include/slb200.h has as many parameters as its ctypes signature, pointers bound as
+    pointer-sized arguments and integer widths as declared."""
+    import ctypes as C
+    from slb200 import _lib
+    text = open(os.path.join(ROOT, "include", "slb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b([A-Za-z_][\w \*]*?)\b(sl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for ret, name, params in protos:
+        res, args = _lib.SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, ctypes {len(args)}"
+        for decl, ctype in zip(plist, args):
+            if "*" in decl:
+                assert ctype in (C.c_void_p, C.c_char_p) or issubclass(ctype, C._Pointer), f"{name}: {decl}"
+            elif decl.startswith("double"):
+                assert ctype is C.c_double, f"{name}: {decl}"
+            elif decl.startswith("size_t"):
+                assert ctype is C.c_size_t, f"{name}: {decl}"
+            elif decl.startswith("int64_t"):
+                assert ctype is C.c_int64, f"{name}: {decl}"
+            elif decl.startswith("int "):
+                assert ctype is C.c_int, f"{name}: {decl}"
+            else:
+                raise AssertionError(f"{name}: unhandled parameter declaration {decl!r}")
+        if "*" in ret and "char" in ret:
+            assert res is C.c_char_p
+        elif "*" in ret:
+            assert res is C.c_void_p
+        elif ret.strip() == "void":
+            assert res is None
+        elif "size_t" in ret:
+            assert res is C.c_size_t
+        elif "int64_t" in ret:
+            assert res is C.c_int64
+        else:
+            assert res is C.c_int, f"{name}: return type {ret!r}"
+
+
 def test_struct_layout_matches_header():
     from slb200 import SlCalib
     assert ctypes.sizeof(SlCalib) == (9 + 8 + 9 + 8 + 9 + 3) * 8 + 4 * 4
@@ -52,6 +92,13 @@ def test_no_cpu_fallback_without_gpu():
     t = Triangulate(np.zeros((4, 4), np.int64), np.zeros((4, 4), np.int64), (4, 4))
     with pytest.raises(RuntimeError):
         t.get_cam_proj_pts(np.zeros((4, 4, 3), np.uint8))
+    from scanner.utils import visualize
+    with pytest.raises(RuntimeError):                                    # the clean-up has no CPU path either
+        visualize.clean_point_cloud(np.zeros((3, 30)), np.zeros((30, 3)))
+    with pytest.raises(TypeError):
+        slb200.remove_statistical_outliers(torch.zeros((30, 4)))         # host tensor
+    with pytest.raises(TypeError):
+        slb200.decode_pixels_bgr(torch.zeros((14, 4, 4, 3), dtype=torch.uint8))
     # the C ABI itself refuses too (no device -> CUDA error, never a computed result)
     assert slb200.lib().sl_device_check(-1) != 0
     assert b"CUDA" in slb200.lib().sl_last_error() or b"sm_" in slb200.lib().sl_last_error()
