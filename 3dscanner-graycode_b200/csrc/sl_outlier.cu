@@ -254,9 +254,20 @@ __global__ void __launch_bounds__(256) sor_insert_kernel(const float4* __restric
 __global__ void __launch_bounds__(256) sor_alloc_kernel(SorParams* prm, int level, const uint32_t* __restrict__ cnt,
                                                          uint32_t* __restrict__ start, uint32_t M) {
   if (prm->counts[level] == 0) return;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
-    const uint32_t c = cnt[i];
-    if (c) start[i] = atomicAdd(&prm->cursor, c);
+  const int lane = threadIdx.x & 31;
+  // one range allocation per warp (a warp-wide prefix of the cell sizes), not one atomic per occupied cell
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i - lane < M; i += gridDim.x * blockDim.x) {
+    const uint32_t c = i < M ? cnt[i] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    uint32_t base = 0;
+    if (lane == 31 && incl) base = atomicAdd(&prm->cursor, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (c) start[i] = base + incl - c;
   }
 }
 
