@@ -6,11 +6,12 @@
 //   * cells of side s are hashed (64-bit cell id -> open-addressing table of >= 2N slots), points are
 //     counting-sorted by cell (atomics only; the order inside a cell does not influence any result
 //     because each query keeps its k smallest squared distances SORTED and sums them nearest first);
-//   * a query scans the 3x3x3 block of cells around its own cell and is final when its k-th distance is
-//     not larger than the distance to the faces of that block (nothing outside can be closer);
-//   * the few queries that are not final (sparse noise points) are retried on a grid with 4x larger
-//     cells, up to kLevels times (one CTA per query there: the block of a sparse query can hold a large part
-//     of the cloud); the last level covers the whole bounding box with <= 2 cells per axis.
+//   * a query scans the 3x3x3 block of cells around its own cell (nearest cells first, cells beyond the current
+//     k-th best skipped) and is final when its k-th distance is not larger than the distance to the faces of
+//     that block (nothing outside can be closer); a near miss scans the 5x5x5 shell at the same level;
+//   * the few queries that are still not final (sparse noise points) are retried on a grid with 4x larger
+//     cells, up to kLevels times (cut into parts over several CTAs there: the block of a sparse query can hold a
+//     large part of the cloud); the last level covers the whole bounding box with <= 2 cells per axis.
 //   s of level 0 is chosen from a pilot build so that occupied cells hold ~kTargetOcc points.
 // Distances: float32 coordinates (the reference narrows to float32, visualize.py:100), differences,
 // squares and the (dx^2 + dy^2) + dz^2 sum in float64 with one rounding per operation, sqrt and the mean in
@@ -26,7 +27,7 @@ namespace sl {
 
 constexpr int kLevels = 12;             // cell side s0 * 4^level; s0 >= extent / 2^20, so level 11 has <= 2 cells per axis
 constexpr double kTargetOcc = 6.0;      // points per occupied cell at level 0 (~100 candidates per query on a surface,
-                                        // ~1 % of the surface queries retried one level up)
+                                        // ~5 % of the surface queries need the 5x5x5 shell)
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kSorBlocks = 148 * 4;     // grid of the grid-stride kernels
 constexpr int kRedBlocks = 256;         // partial sums of the two reductions
