@@ -118,3 +118,23 @@ def test_bgr_argument_errors():
         slb200.decode_pixels_bgr(torch.zeros((14, 8, 8), dtype=torch.uint8, device="cuda"))
     with pytest.raises(slb200.SlError):
         slb200.decode_pixels_bgr(torch.zeros((13, 8, 8, 3), dtype=torch.uint8, device="cuda"))
+
+
+def test_bgr_identity_full_size_4k():
+    """BASELINE config 3 size (3840x2160, n = 12, F = 50; 1.24 GB of BGR frames): the projector sequence seen through
+    an identity camera, painted in colour (every pixel keeps its gray level under cv2's formula only for grey
+    colours, so the lit level is a grey 255 and the dark level a saturated blue whose gray value is 29), decodes
+    to the identity map -- the reference's own known-answer property, at full size, through the BGR kernel."""
+    import torch
+    import slb200
+    pats = slb200.pattern_sequence((3840, 2160))                       # (50, 2160, 3840) u8, 0 / 255
+    lit = pats > 0
+    bgr = torch.empty((*pats.shape, 3), dtype=torch.uint8, device="cuda")
+    bgr[..., 0] = 255                                                  # B: 255 either way
+    bgr[..., 1] = torch.where(lit, 255, 0)
+    bgr[..., 2] = torch.where(lit, 255, 0)
+    del lit
+    h, v = slb200.decode_pixels_bgr(bgr)
+    xs = torch.arange(3840, device="cuda", dtype=torch.int16)[None, :].expand(2160, 3840)
+    ys = torch.arange(2160, device="cuda", dtype=torch.int16)[:, None].expand(2160, 3840)
+    assert torch.equal(h, xs) and torch.equal(v, ys)

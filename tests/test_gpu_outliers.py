@@ -149,3 +149,37 @@ def test_argument_errors():
         slb200.remove_statistical_outliers(cloud, 129, 0.5)
     with pytest.raises(TypeError):
         slb200.remove_statistical_outliers(cloud[:, :3], 20, 0.5)
+
+
+def test_full_size_cloud_properties():
+    """Size-independent properties on the cloud of a 1080p scan (1.8 M points, BASELINE config 2), where the oracle
+    would take minutes: (1) the per-point mean distances do not depend on the order of the records (the kernel
+    sorts points into cells with atomics, every run in a different order): a shuffled copy gives bit-identical
+    values; (2) same for a repeated run; (3) the inliers are exactly {0 < mean < threshold}, in ascending order;
+    (4) the threshold is mean + ratio * std of the positive means (float64 on the host, 1e-12)."""
+    import torch
+    import slb200
+    from slb200 import synth
+    calib = synth.synthetic_calibration((1920, 1080), (1920, 1080))
+    frames, white = synth.render_scan((1920, 1080), (1920, 1080), seed=7, device="cuda", calib=calib)
+    bufs = slb200.scan_to_cloud(frames, white, calib)
+    cloud = slb200.filter_cloud_box(bufs.cloud[: int(bufs.counts[1].item())], 2.0)
+    n = len(cloud)
+    assert n > 1_500_000
+    out, ind, md, stats = slb200.remove_statistical_outliers(cloud, 20, 0.5, details=True)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    out2, ind2, md2, stats2 = slb200.remove_statistical_outliers(cloud[perm].contiguous(), 20, 0.5, details=True)
+    assert torch.equal(md2, md[perm])                                  # (1)
+    _, ind3, md3, _ = slb200.remove_statistical_outliers(cloud, 20, 0.5, details=True)
+    assert torch.equal(md3, md) and torch.equal(ind3, ind)             # (2)
+    keep = (md > 0) & (md < stats[2])
+    assert torch.equal(ind, torch.nonzero(keep).flatten())             # (3)
+    assert torch.equal(out, cloud[ind])
+    m = md.cpu().numpy()
+    pos = m[m > 0]
+    mean = pos.sum() / n
+    std = np.sqrt(((pos - mean) ** 2).sum() / (n - 1))
+    assert float(stats[0]) == pytest.approx(mean, rel=1e-12) and float(stats[1]) == pytest.approx(std, rel=1e-10)
+    assert float(stats[2]) == pytest.approx(mean + 0.5 * std, rel=1e-11)   # (4)
+    assert torch.equal(torch.sort(perm[ind2]).values, ind)             # the same points survive in the shuffled copy
