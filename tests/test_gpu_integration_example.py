@@ -47,6 +47,21 @@ def test_ctypes_only_host_pipeline():
                                   ctypes.c_void_p(v_idx.ctypes.data), ctypes.c_void_p(cloud.ctypes.data),
                                   ctypes.c_int64(cloud.shape[0]), ctypes.c_void_p(counts.ctypes.data))
     assert rc == 0, sl.sl_last_error()
+    # the streaming form shown in INTEGRATION.md: one scan per call, results valid after the flush
+    clouds = [np.zeros((H * W, 4), np.float32) for _ in range(B)]
+    cnts = [np.zeros(1, np.int64) for _ in range(B)]
+    for i in range(B):
+        rc = sl.sl_pipeline_submit(pipe, ctypes.c_void_p(frames[i].ctypes.data), ctypes.c_void_p(white[i].ctypes.data),
+                                   ctypes.byref(c), 1, ctypes.c_double(1.0), ctypes.c_void_p(clouds[i].ctypes.data),
+                                   ctypes.c_int64(clouds[i].shape[0]), ctypes.c_void_p(cnts[i].ctypes.data))
+        assert rc == 0, sl.sl_last_error()
+    assert sl.sl_pipeline_flush(pipe) == 0, sl.sl_last_error()
+    off = 0
+    for i in range(B):
+        assert int(cnts[i][0]) == int(counts[i])
+        np.testing.assert_array_equal(clouds[i][: int(counts[i])].view(np.int32),
+                                      cloud[off: off + int(counts[i])].view(np.int32))
+        off += int(counts[i])
     sl.sl_pipeline_destroy(pipe)
     start = 0
     for b in range(B):
