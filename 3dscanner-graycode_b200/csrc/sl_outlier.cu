@@ -26,8 +26,10 @@
 namespace sl {
 
 constexpr int kLevels = 12;             // cell side s0 * 4^level; s0 >= extent / 2^20, so level 11 has <= 2 cells per axis
-constexpr double kTargetOcc = 6.0;      // points per occupied cell at level 0 (~100 candidates per query on a surface,
-                                        // ~5 % of the surface queries need the 5x5x5 shell)
+#ifndef SL_SOR_TARGET_OCC
+#define SL_SOR_TARGET_OCC 8.0           // measured on the 1.8 M-point cloud of a 1080p scan: 5.4 / 4.8 / 4.4 / 4.3 / 3.8 / 4.3 / 4.0 / 4.4 ms
+#endif                                  // for 3 / 4 / 5 / 6 / 8 / 10 / 12 / 16 (larger cells: fewer probes, more coherent warps;
+constexpr double kTargetOcc = SL_SOR_TARGET_OCC;   // the box test and the float32 filter discard the extra candidates)
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kSorBlocks = 148 * 4;     // grid of the grid-stride kernels
 constexpr int kRedBlocks = 256;         // partial sums of the two reductions
