@@ -45,9 +45,14 @@ static int device_gate(int* sms) {
     SL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     SL_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
     SL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    d.checked = 1; d.ok = (major == 10 && minor == 0); d.sms = n;
-    if (!d.ok) { d.sms = -(major * 10 + minor); }
-    else { const int trc = init_device_tables(); if (trc) return trc; }
+    const bool ok = (major == 10 && minor == 0);
+    if (ok) {       // everything the launch paths need once per device, before any kernel of ours can be queued
+      int trc = decode_device_init();
+      if (trc == kOk) trc = cloud_device_init();
+      if (trc) return trc;
+    }
+    d.ok = ok; d.sms = ok ? n : -(major * 10 + minor);
+    d.checked = 1;
   }
   if (!d.ok) {
     set_error("slb200 is built for sm_100a only; device %d is sm_%d (no fallback path exists)", dev, -d.sms);
@@ -56,6 +61,13 @@ static int device_gate(int* sms) {
   *sms = d.sms;
   return kOk;
 }
+
+// Entry points that select a device (pipelines, sl_device_check) restore the caller's current device on return.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static int check_decode_shape(int B, int F, int H, int W) {
   if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive (got %d, %d, %d)", B, H, W); return kErrBadArg; }
@@ -74,9 +86,8 @@ const char* sl_last_error(void) { return g_err; }
 int sl_version(void) { return 100; }
 int64_t sl_launch_count(void) { return (int64_t)g_launches.load(); }
 
-int sl_set_decode_sm_reserve(int sms) { return set_decode_sm_reserve(sms); }
-
 int sl_device_check(int device) {
+  DeviceGuard guard;
   if (device >= 0) SL_CUDA(cudaSetDevice(device));
   int sms = 0;
   return device_gate(&sms);
@@ -84,7 +95,7 @@ int sl_device_check(int device) {
 
 int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                 int8_t* v_codes, void* cloud_workspace, void* stream) {
+                 int8_t* v_codes, void* cloud_workspace, int sm_reserve, void* stream) {
   int rc = check_decode_shape(B, F, H, W);
   if (rc) return rc;
   if (!frames || !h_idx || !v_idx) { set_error("frames, h_idx, v_idx must be non-null"); return kErrBadArg; }
@@ -99,15 +110,17 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
   unsigned int* ticket = nullptr;
   long long words = 0;
   if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &ticket);
+  if (sm_reserve < 0) { set_error("sm_reserve must be >= 0"); return kErrBadArg; }
   return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, h_codes, v_codes,
-                       bitmap, words, ticket, sms, (cudaStream_t)stream);
+                       bitmap, words, ticket, sms, (cudaStream_t)stream, false, sm_reserve);
 }
 
 int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size_t frame_pitch,
                      size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx,
-                     void* cloud_workspace, void* stream) {
+                     void* cloud_workspace, int sm_reserve, void* stream) {
   int rc = check_decode_shape(B, F, H, W);
   if (rc) return rc;
+  if (sm_reserve < 0) { set_error("sm_reserve must be >= 0"); return kErrBadArg; }
   if (!frames_bgr || !h_idx || !v_idx) { set_error("frames_bgr, h_idx, v_idx must be non-null"); return kErrBadArg; }
   const long long npix = (long long)H * W;
   if (frame_pitch < (size_t)npix * 3) { set_error("frame_pitch smaller than 3*H*W"); return kErrBadArg; }
@@ -120,7 +133,7 @@ int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size
   long long words = 0;
   if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &ticket);
   return launch_decode(frames_bgr, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr,
-                       bitmap, words, ticket, sms, (cudaStream_t)stream, true);
+                       bitmap, words, ticket, sms, (cudaStream_t)stream, true, sm_reserve);
 }
 
 int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
@@ -196,6 +209,9 @@ int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H,
                        void* workspace, int64_t* counts, void* stream) {
   if (!h_idx || !v_idx || !workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive"); return kErrBadArg; }
+  if ((uintptr_t)h_idx % 2 || (uintptr_t)v_idx % 2 || (uintptr_t)workspace % 256 || (uintptr_t)counts % 8) {
+    set_error("h_idx / v_idx must be 2-byte aligned, workspace 256-byte, counts 8-byte"); return kErrBadArg;
+  }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
   return launch_compact_offsets(h_idx, v_idx, B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
@@ -204,6 +220,7 @@ int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H,
 int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream) {
   if (!workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive"); return kErrBadArg; }
+  if ((uintptr_t)workspace % 256 || (uintptr_t)counts % 8) { set_error("workspace must be 256-byte aligned, counts 8-byte"); return kErrBadArg; }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
   return launch_offsets_from_bitmap(B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
@@ -220,6 +237,9 @@ int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
   if (!h_idx || !v_idx || !workspace || !pairs) { set_error("null buffer"); return kErrBadArg; }
   if (rgb32 && !white_rgb) { set_error("rgb32 needs white_rgb"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1 || proj_w < 1 || proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
+  if ((uintptr_t)pairs % 16 || (uintptr_t)rgb32 % 4 || (uintptr_t)h_idx % 2 || (uintptr_t)v_idx % 2) {
+    set_error("pairs must be 16-byte aligned, rgb32 4-byte, h_idx / v_idx 2-byte"); return kErrBadArg;
+  }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
   return launch_emit_pairs(h_idx, v_idx, white_rgb, B, H, W, proj_w, proj_h, workspace, pairs, rgb32,
@@ -235,25 +255,51 @@ int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, 
   return launch_lens_tables(*calib, cam_w, cam_h, cam_rays, proj_rays, (cudaStream_t)stream);
 }
 
-int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
-                  const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
-                  int B, int H, int W, const void* workspace, float* cloud, void* stream) {
-  if (!h_idx || !v_idx || !workspace || !cloud || !calib) { set_error("null buffer"); return kErrBadArg; }
+static int emit_cloud_checked(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                             const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                             int B, int H, int W, const void* workspace, float* const* clouds, int n_clouds,
+                             int remote, int64_t max_points, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !clouds || !calib) { set_error("null buffer"); return kErrBadArg; }
+  if (n_clouds < 1 || n_clouds > kMaxWorld) { set_error("n_clouds must be 1..%d", kMaxWorld); return kErrBadArg; }
   if ((cam_rays == nullptr) != (proj_rays == nullptr)) { set_error("cam_rays and proj_rays go together"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  for (int k = 0; k < n_clouds; ++k)
+    if (!clouds[k] || (uintptr_t)clouds[k] % 16) { set_error("cloud buffers must be non-null and 16-byte aligned"); return kErrBadArg; }
+  if ((uintptr_t)cam_rays % 16 || (uintptr_t)proj_rays % 8 || (uintptr_t)h_idx % 2 || (uintptr_t)v_idx % 2) {
+    set_error("cam_rays must be 16-byte aligned, proj_rays 8-byte, h_idx / v_idx 2-byte"); return kErrBadArg;
+  }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
   return launch_emit_cloud(h_idx, v_idx, white_rgb, *calib, precision, cam_rays, proj_rays, B, H, W, workspace,
-                           cloud, (cudaStream_t)stream);
+                           clouds[0], (cudaStream_t)stream, clouds + 1, n_clouds - 1, remote, max_points);
+}
+
+int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                  const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                  int B, int H, int W, const void* workspace, float* cloud, void* stream) {
+  float* one[1] = {cloud};
+  return emit_cloud_checked(h_idx, v_idx, white_rgb, calib, precision, cam_rays, proj_rays, B, H, W, workspace,
+                            one, 1, 0, 0, stream);
+}
+
+int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                        const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                        int B, int H, int W, const void* workspace, float* const* clouds, int n_clouds,
+                        int64_t max_points, void* stream) {
+  if (max_points < 1) { set_error("max_points must be positive"); return kErrBadArg; }
+  return emit_cloud_checked(h_idx, v_idx, white_rgb, calib, precision, cam_rays, proj_rays, B, H, W, workspace,
+                            clouds, n_clouds, 1, max_points, stream);
 }
 
 int sl_decode_triangulate_fused(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                                 size_t scan_pitch, double eps, const uint8_t* white_rgb, const SlCalib* calib,
                                 int precision, const float* cam_rays, const float* proj_rays, int16_t* h_idx,
-                                int16_t* v_idx, void* workspace, float* cloud, int64_t* counts, void* stream) {
+                                int16_t* v_idx, void* workspace, float* cloud, int64_t* counts, int sm_reserve,
+                                void* stream) {
   if (!workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
-  int rc = sl_decode_u8(frames, B, F, H, W, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr, workspace, stream);
+  int rc = sl_decode_u8(frames, B, F, H, W, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr, workspace,
+                        sm_reserve, stream);
   if (rc) return rc;
   if ((rc = sl_compact_offsets_decoded(B, H, W, workspace, counts, stream))) return rc;
   return sl_emit_cloud(h_idx, v_idx, white_rgb, calib, precision, cam_rays, proj_rays, B, H, W, workspace, cloud, stream);
@@ -315,6 +361,7 @@ int sl_remove_statistical_outliers(const float* cloud, int64_t N, int nb_neighbo
 // ------------------------------------------------------------------ host-buffer pipeline
 struct SlPipeline {
   int device = 0, max_batch = 0, F = 0, H = 0, W = 0, sms = 0;
+  int sm_reserve = 0;   // sl_pipeline_set_sm_reserve
   static constexpr int kSlots = 3;
   struct Slot {
     cudaStream_t stream = nullptr;
@@ -347,6 +394,7 @@ struct SlPipeline {
 
 static void pipeline_free(SlPipeline* p) {
   if (!p) return;
+  DeviceGuard guard;
   cudaSetDevice(p->device);
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
@@ -366,6 +414,7 @@ int sl_pipeline_create(SlPipeline** out, int device, int max_batch, int F, int H
   int rc = check_decode_shape(max_batch < 1 ? 0 : 1, F, H, W);
   if (rc) return rc;
   if (max_batch < 1) { set_error("max_batch must be >= 1"); return kErrBadArg; }
+  DeviceGuard guard;
   if (device >= 0) SL_CUDA(cudaSetDevice(device));
   int sms = 0;
   if ((rc = device_gate(&sms))) return rc;
@@ -398,6 +447,12 @@ int sl_pipeline_create(SlPipeline** out, int device, int max_batch, int F, int H
 
 void sl_pipeline_destroy(SlPipeline* p) { pipeline_free(p); }
 
+int sl_pipeline_set_sm_reserve(SlPipeline* p, int sms) {
+  if (!p || sms < 0) { set_error("bad argument"); return kErrBadArg; }
+  p->sm_reserve = sms;
+  return kOk;
+}
+
 // Scan i goes through slot i % kSlots: H2D -> decode -> offsets -> emit -> D2H(count).  The cloud
 // D2H needs the count (packed host output), so it is issued one step later, after the slot's
 // `counted` event, while the next scans' copies and kernels are already queued on other streams.
@@ -411,6 +466,7 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
   for (auto& s : p->slot)
     if (s.pending) { set_error("scans submitted with sl_pipeline_submit are still in flight: call sl_pipeline_flush first"); return kErrState; }
+  DeviceGuard guard;
   SL_CUDA(cudaSetDevice(p->device));
   const size_t npix = (size_t)p->H * p->W;
   const size_t stack = (size_t)p->F * npix;
@@ -462,7 +518,7 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     unsigned int* ticket = nullptr;
     uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &ticket);
     rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
-                       ticket, p->sms, s.stream);
+                       ticket, p->sms, s.stream, false, p->sm_reserve);
     if (rc) break;
     if (h_idx_host) {
       SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, s.h, npix * 2, cudaMemcpyDeviceToHost, s.stream));
@@ -528,6 +584,7 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
                        int precision, double eps, float* cloud_host, int64_t cap_points, int64_t* count_host) {
   if (!p || !frames_host || !calib || !cloud_host || !count_host) { set_error("null argument"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  DeviceGuard guard;
   SL_CUDA(cudaSetDevice(p->device));
   int rc = pipeline_tables(p, calib);
   if (rc) return rc;
@@ -541,7 +598,7 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
   unsigned int* ticket = nullptr;
   uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &ticket);
   if ((rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
-                          ticket, p->sms, s.stream))) return rc;
+                          ticket, p->sms, s.stream, false, p->sm_reserve))) return rc;
   if ((rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream))) return rc;
   SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
   if ((rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
@@ -555,6 +612,7 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
 
 int sl_pipeline_flush(SlPipeline* p) {
   if (!p) { set_error("null argument"); return kErrBadArg; }
+  DeviceGuard guard;
   SL_CUDA(cudaSetDevice(p->device));
   int rc = kOk;
   for (int k = 0; k < SlPipeline::kSlots && rc == kOk; ++k)      // oldest first
@@ -578,6 +636,7 @@ int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
   if (!p || !frames_host || !h_idx_host || !v_idx_host) { set_error("null argument"); return kErrBadArg; }
   if (B < 1 || B > p->max_batch) { set_error("B=%d outside 1..max_batch=%d", B, p->max_batch); return kErrBadArg; }
   if ((h_codes_host == nullptr) != (v_codes_host == nullptr)) { set_error("codes buffers go together"); return kErrBadArg; }
+  DeviceGuard guard;
   SL_CUDA(cudaSetDevice(p->device));
   const size_t npix = (size_t)p->H * p->W;
   const size_t stack = (size_t)p->F * npix;
@@ -598,7 +657,7 @@ int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
     SL_CUDA(cudaMemcpyAsync(u.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, st));
     rc = launch_decode(u.frames, 1, p->F, (long long)npix, npix, stack, eps, u.h, u.v,
                        h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, nullptr, 0, nullptr,
-                       p->sms, st);
+                       p->sms, st, false, p->sm_reserve);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, u.h, npix * 2, cudaMemcpyDeviceToHost, st));
     SL_CUDA(cudaMemcpyAsync(v_idx_host + (size_t)i * npix, u.v, npix * 2, cudaMemcpyDeviceToHost, st));

@@ -423,6 +423,10 @@ struct EmitArgs {
   const uint32_t* col_bits;
   const long long* col_base;
   float* out;               // (N,4) records, see emit_kernel
+  float* out_extra[kMaxWorld - 1];   // further destinations of the same records (peer-mapped clouds of other ranks)
+  int n_extra;
+  int remote;               // `out` may be a peer mapping: plain stores (no L2 policy hint)
+  int aligned;              // h, v, white, out, cam_rays meet the vector path's alignment (else scalar loads)
   uint32_t* out_rgb32;      // pairs mode only, nullable: (N,) packed colour
   const float2* cam_rays;   // table modes: [H][W] undistorted camera rays (rotated by R)
   const float2* proj_rays;  // table modes: [proj_h][proj_w] undistorted projector rays
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
   const size_t img = (size_t)b * a.H * a.W;
   const size_t cell = ((size_t)b * a.bands + band) * a.W + x0;       // (scan, band, column x0)
   const bool has_rgb = a.white != nullptr;
-  const bool vec = ((a.W & 3) == 0) && cols == kEmitCols;
+  const bool vec = ((a.W & 3) == 0) && cols == kEmitCols && a.aligned;
   constexpr bool kTable = (MODE == kModeTable32 || MODE == kModeTable64);
 
   // lane c <-> column x0+c: packed output offset of the column's first point in this band, and its bits
@@ -612,7 +616,10 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
     const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, cidx)
                                    : __shfl_sync(0xffffffffu, my_base, cidx);
     if (lane < cnt) {
-      stg_u4_hint(out + base + lane, tile.rec[cidx * kRunPitch + lane], stream);
+      const uint4 rec = tile.rec[cidx * kRunPitch + lane];
+      if (a.remote) out[base + lane] = rec;
+      else stg_u4_hint(out + base + lane, rec, stream);
+      for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + lane] = rec;
       if (MODE == kModePairs && a.out_rgb32) a.out_rgb32[base + lane] = tile.aux[cidx * kRunPitch + lane];
     }
   }
@@ -780,18 +787,13 @@ uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_s
 constexpr int kEmitSmem = (int)(sizeof(EmitTile<true>) * kEmitWarps);       // pairs mode
 constexpr int kEmitSmemCloud = (int)(sizeof(EmitTile<false>) * kEmitWarps);
 
-// > 48 KB of dynamic shared memory needs an opt-in per kernel, once per device
-static int emit_configure() {
-  static bool done[64] = {false};
-  int dev = 0;
-  SL_CUDA(cudaGetDevice(&dev));
-  if (done[dev & 63]) return kOk;
+// > 48 KB of dynamic shared memory needs an opt-in per kernel: once per device, from sl_capi.cu's device gate
+int cloud_device_init() {
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModePairs>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
-  done[dev & 63] = true;
   return kOk;
 }
 
@@ -807,6 +809,10 @@ static EmitArgs make_emit(const int16_t* h, const int16_t* v, const uint8_t* whi
   a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_bits = c.col_bits; a.col_base = c.col_base;
   a.out = out; a.out_rgb32 = out_rgb32; a.H = H; a.W = W; a.bands = c.bands;
   a.cam_rays = nullptr; a.proj_rays = nullptr;
+  a.n_extra = 0; a.remote = 0;
+  for (int k = 0; k < kMaxWorld - 1; ++k) a.out_extra[k] = nullptr;
+  // vector path: 8-byte index loads, 4-byte colour loads, 16-byte record stores (cam_rays is checked by the caller)
+  a.aligned = ((uintptr_t)h % 8 == 0) && ((uintptr_t)v % 8 == 0) && ((uintptr_t)white % 4 == 0);
   a.off32 = ((long long)B * H * W < (1LL << 32)) ? 1 : 0;
   a.tiles_x = (W + kEmitCols - 1) / kEmitCols;
   a.total_tiles = (long long)a.tiles_x * a.bands * B;      // callers reject >= 2^31 (check_emit_size)
@@ -818,9 +824,8 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, pairs, rgb32);
   a.cal = CalibDev();
   a.cal.proj_w = proj_w; a.cal.proj_h = proj_h; a.cal.row0 = 0;
-  int rc = emit_configure();
+  int rc = check_emit_size(a);
   if (rc) return rc;
-  if ((rc = check_emit_size(a))) return rc;
   emit_kernel<kModePairs><<<grid_for(a.total_tiles, kEmitWarps), kEmitWarps * 32, kEmitSmem, st>>>(a);
   count_launch();
   SL_CUDA(cudaGetLastError());
@@ -842,15 +847,19 @@ int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_ra
 
 int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
                       int precision, const float* cam_rays, const float* proj_rays, int B, int H, int W,
-                      const void* ws, float* cloud, cudaStream_t st) {
+                      const void* ws, float* cloud, cudaStream_t st, float* const* extra, int n_extra, int remote,
+                      long long max_points) {
   EmitArgs a = make_emit(h, v, white, B, H, W, ws, cloud, nullptr);
   a.cal = make_calib(calib);
   a.cam_rays = (const float2*)cam_rays; a.proj_rays = (const float2*)proj_rays;
+  if (n_extra < 0 || n_extra > kMaxWorld - 1) { set_error("at most %d clouds per emission", kMaxWorld); return kErrBadArg; }
+  for (int k = 0; k < n_extra; ++k) a.out_extra[k] = extra[k];
+  a.n_extra = n_extra; a.remote = remote;
+  if (max_points > 0) a.off32 = (max_points < (1LL << 32)) ? 1 : 0;     // offsets rebased by the multi-GPU exchange
   const int g = grid_for(a.total_tiles, kEmitWarps);
   const int thr = kEmitWarps * 32;
-  int rc = emit_configure();
+  const int rc = check_emit_size(a);
   if (rc) return rc;
-  if ((rc = check_emit_size(a))) return rc;
   if (cam_rays) {
     if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmemCloud, st>>>(a);
     else SL_CUDA(launch_stage2(emit_kernel<kModeTable32>, g, thr, (size_t)kEmitSmemCloud, st, a));

@@ -1,7 +1,7 @@
 // Stage 1: fused Gray-code decode kernels (sm_100a).
 //
 // K1  decode_tma_kernel     persistent, one CTA per SM (1 producer + 16 consumer warps that claim
-//                           128-px sub-tiles dynamically).  The producer thread streams [F x 1024 px]
+//                           128-px sub-tiles dynamically).  The producer thread streams [F x 512 px]
 //                           tiles into a ring of shared-memory stages, ONE TMA tensor load per
 //                           tile (cp.async.bulk.tensor.3d + mbarrier complete_tx; the stack is
 //                           described as a (pixels/4 x F x B) uint32 tensor); consumer warps read them as
@@ -36,44 +36,25 @@ __global__ void binv_table_kernel() {
 }
 #endif
 
+// Called once per device from the first C-ABI entry on that device (sl_capi.cu: device_gate, under its mutex).
+// The table is filled on a private blocking-free stream and the call returns only when the fill has completed, so
+// no launch on any stream or thread can ever read a partly filled table.  If the calling thread is capturing a
+// CUDA graph, the thread's capture mode is relaxed for the duration: the fill runs immediately, outside the capture.
+static int fill_binv_table() {
 #if defined(SL_BINV_TABLE)
-static bool g_binv_ready[64] = {false};
-#endif
-
-// Called once per device from the first C-ABI entry (sl_capi.cu: device_gate): fill the table on the
-// legacy default stream and wait, so that no later launch on any stream can race with the fill.  If the
-// calling thread is capturing a CUDA graph this is not possible; ensure_binv_table() then fills it in
-// stream order on first use.
-int init_device_tables() {
-#if defined(SL_BINV_TABLE)
-  int dev = 0;
-  SL_CUDA(cudaGetDevice(&dev));
-  if (g_binv_ready[dev & 63]) return kOk;
-  binv_table_kernel<<<256, 256, 0, 0>>>();
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  SL_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+  cudaStream_t st = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   if (e == cudaSuccess) {
-    count_launch();
-    g_binv_ready[dev & 63] = true;
-  } else {
-    (void)cudaGetLastError();       // capture in progress: leave it to the stream-ordered path
-  }
-#endif
-  return kOk;
-}
-
-static int ensure_binv_table(cudaStream_t st) {
-#if defined(SL_BINV_TABLE)
-  int dev = 0;
-  SL_CUDA(cudaGetDevice(&dev));
-  if (!g_binv_ready[dev & 63]) {
     binv_table_kernel<<<256, 256, 0, st>>>();
-    count_launch();
-    SL_CUDA(cudaGetLastError());
-    g_binv_ready[dev & 63] = true;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
   }
-#else
-  (void)st;
+  cudaThreadExchangeStreamCaptureMode(&mode);
+  if (e != cudaSuccess) return cuda_fail(e, "b_inv table initialisation");
+  count_launch();
 #endif
   return kOk;
 }
@@ -95,6 +76,17 @@ constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;   // + 1 producer warp
 constexpr int kMaxStages = SL_MAX_STAGES;
 constexpr int kSmemBudget = 227 * 1024;
 
+// four int16 indices of a quad: one 8-byte store, or four 2-byte stores when scan b's plane is only 2-byte aligned
+// (a batch whose scans hold a number of pixels that is not a multiple of 4)
+__device__ __forceinline__ void store_idx4(int16_t* p, uint32_t lo, uint32_t hi, int vec) {
+  if (vec) {
+    st_global_v2(p, lo, hi);
+  } else {
+    p[0] = (int16_t)(lo & 0xffffu); p[1] = (int16_t)(lo >> 16);
+    p[2] = (int16_t)(hi & 0xffffu); p[3] = (int16_t)(hi >> 16);
+  }
+}
+
 struct DecodeArgs {
   const uint8_t* frames;
   size_t frame_pitch, scan_pitch;
@@ -110,6 +102,7 @@ struct DecodeArgs {
   long long total_tiles; // B * tiles_per_scan
   int tiles_per_scan;
   int n, F, e, stages;
+  int idx_vec;           // every scan's index planes are 8-byte aligned (B == 1 or npix % 4 == 0): vector stores
 };
 
 // Register cap: the decode CTA (544 threads, 188 KB of shared memory) leaves room on the SM for one emit
@@ -215,8 +208,8 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
         *reinterpret_cast<uint32_t*>(dst) = tri;
       };
       const QuadOut o = decode_quad<NB, CODES>(ld, st, n, a.e);
-      st_global_v2(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23);
-      st_global_v2(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23);
+      store_idx4(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23, a.idx_vec);
+      store_idx4(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23, a.idx_vec);
       nib = ((o.valid & kMsb4) * 0x00204081u) >> 28;      // the 4 msb flags gathered into bits 0..3
     }
     if (a.bitmap) {
@@ -336,8 +329,8 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
       auto st = [](int, int, uint32_t) {};
       const long long px = px0 + off;
       const QuadOut o = decode_quad<NB, false>(ld, st, n, a.e);
-      st_global_v2(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23);
-      st_global_v2(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23);
+      store_idx4(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23, a.idx_vec);
+      store_idx4(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23, a.idx_vec);
       nib = ((o.valid & kMsb4) * 0x00204081u) >> 28;
     }
     if (a.bitmap) {
@@ -468,16 +461,13 @@ __global__ void __launch_bounds__(256) codes_to_pixels_kernel(const int8_t* __re
 }
 
 // ------------------------------------------------------------------ launchers
-// SMs the persistent decode kernels leave to other work (sl_set_decode_sm_reserve).  A caller that pipelines
-// independent scans over several streams gets more out of the GPU when the decode grid does not cover every SM:
-// the offsets / emit kernels of the other scans then always find SMs of their own instead of the two CTA slots
+// `sm_reserve` (a launch argument of the C ABI): SMs the persistent decode grid leaves to other work.  A caller that
+// pipelines independent scans over several streams gets more out of the GPU when the decode grid does not cover
+// every SM: the offsets / emit kernels of the other scans then always find SMs of their own instead of the CTA slot
 // beside a resident decode CTA.  Measured on the bench step (4 streams): 34.2 us per scan with 148 CTAs, 33.4 with
-// 145, 32.4 with 140, 32.6 with 138 / 135; a launch on its own gets slower instead (21.9 -> 23.0 us at 140), so the
-// default is 0.
-static std::atomic<int> g_decode_sm_reserve{0};
-int set_decode_sm_reserve(int sms) { return g_decode_sm_reserve.exchange(sms < 0 ? 0 : sms); }
-static int decode_grid_sms(int num_sms) {
-  const int r = g_decode_sm_reserve.load(std::memory_order_relaxed);
+// 145, 32.4 with 140, 32.6 with 138 / 135; a launch on its own gets slower instead (21.9 -> 23.0 us at 140).
+static int decode_grid_sms(int num_sms, int sm_reserve) {
+  const int r = sm_reserve < 0 ? 0 : sm_reserve;
   return num_sms > 2 * r ? num_sms - r : num_sms;
 }
 
@@ -486,20 +476,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static std::atomic<EncodeTiledFn> g_encode_tiled{nullptr};
+
 static int make_frames_tensor_map(CUtensorMap* out, const uint8_t* frames, long long npix4, int F, int B,
                                   size_t frame_pitch, size_t scan_pitch, int bytes_per_px = 1,
                                   int box_words = kTilePx / 4) {
-  static EncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    SL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-    if (q != cudaDriverEntryPointSuccess || !fn) {
-      set_error("cuTensorMapEncodeTiled not available from this driver");
-      return kErrCuda;
-    }
-    encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
+  EncodeTiledFn encode = g_encode_tiled.load(std::memory_order_acquire);
+  if (!encode) { set_error("cuTensorMapEncodeTiled not available (device not initialised)"); return kErrCuda; }
   // tensor of uint32 (4 pixels): dim0 = npix4/4 along a frame, dim1 = frame, dim2 = scan
   const cuuint64_t dims[3] = {(cuuint64_t)(npix4 / 4) * bytes_per_px, (cuuint64_t)F, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)frame_pitch, (cuuint64_t)(B > 1 ? scan_pitch : frame_pitch * F)};
@@ -518,16 +501,7 @@ static int make_frames_tensor_map(CUtensorMap* out, const uint8_t* frames, long 
 
 template <int NB, bool CODES>
 static int launch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
-  auto k = decode_tma_kernel<NB, CODES>;
-  // opt in to > 48 KB dynamic shared memory once per device (not a stream operation, so it is
-  // done outside the launch path and never during CUDA-graph capture replays)
-  static bool configured[64] = {false};
-  int dev = 0;
-  SL_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
-    SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured[dev & 63] = true;
-  }
+  auto k = decode_tma_kernel<NB, CODES>;     // > 48 KB of dynamic shared memory: opted in by decode_device_init
   k<<<grid, kDecodeThreads, smem, st>>>(tmap, a);
   count_launch();
   SL_CUDA(cudaGetLastError());
@@ -549,13 +523,6 @@ static int dispatch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, 
 template <int NB>
 static int launch_bgr_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
   auto k = decode_bgr_tma_kernel<NB>;
-  static bool configured[64] = {false};
-  int dev = 0;
-  SL_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev & 63]) {
-    SL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured[dev & 63] = true;
-  }
   k<<<grid, kDecodeThreads, smem, st>>>(tmap, a);
   count_launch();
   SL_CUDA(cudaGetLastError());
@@ -571,19 +538,49 @@ static int dispatch_bgr_tma(const CUtensorMap& tmap, const DecodeArgs& a, int gr
   }
 }
 
+// Once per device, called by sl_capi.cu's device gate under its mutex: everything the launch path would otherwise
+// initialise lazily (and racily): the b_inv table, the tensor-map encoder, the shared-memory opt-ins.
+template <int NB>
+static int opt_in_smem() {
+  SL_CUDA(cudaFuncSetAttribute(decode_tma_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  SL_CUDA(cudaFuncSetAttribute(decode_tma_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  return kOk;
+}
+template <int NB>
+static int opt_in_smem_bgr() {
+  SL_CUDA(cudaFuncSetAttribute(decode_bgr_tma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+  return kOk;
+}
+
+int decode_device_init() {
+  int rc = fill_binv_table();
+  if (rc) return rc;
+  if (!g_encode_tiled.load(std::memory_order_acquire)) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled not available from this driver");
+      return kErrCuda;
+    }
+    g_encode_tiled.store(reinterpret_cast<EncodeTiledFn>(fn), std::memory_order_release);
+  }
+  if ((rc = opt_in_smem<0>()) || (rc = opt_in_smem<8>()) || (rc = opt_in_smem<9>()) || (rc = opt_in_smem<10>()) ||
+      (rc = opt_in_smem<11>()) || (rc = opt_in_smem<12>())) return rc;
+  if ((rc = opt_in_smem_bgr<0>()) || (rc = opt_in_smem_bgr<10>()) || (rc = opt_in_smem_bgr<11>()) ||
+      (rc = opt_in_smem_bgr<12>())) return rc;
+  return kOk;
+}
+
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                   int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
-                  int num_sms, cudaStream_t st, bool bgr) {
+                  int num_sms, cudaStream_t st, bool bgr, int sm_reserve) {
   const int n = (F - 2) / 4;
-  {
-    const int trc = ensure_binv_table(st);
-    if (trc) return trc;
-  }
   const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
   const bool aligned = ((uintptr_t)frames % 16 == 0) && (frame_pitch % 16 == 0) &&
                        (scan_pitch % 16 == 0) && ((uintptr_t)h_idx % 8 == 0) &&
-                       ((uintptr_t)v_idx % 8 == 0) && (npix % 4 == 0 || B == 1) &&
+                       ((uintptr_t)v_idx % 8 == 0) &&
                        (!h_codes || (((uintptr_t)h_codes % 4 == 0) && ((uintptr_t)v_codes % 4 == 0) &&
                                      npix % 4 == 0));
   long long tma_px = (int_eps && aligned) ? (npix & ~3LL) : 0;
@@ -599,7 +596,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kBgrTilePx - 1) / kBgrTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
-    a.n = n; a.F = F; a.e = (int)eps;
+    a.n = n; a.F = F; a.e = (int)eps; a.idx_vec = (npix % 4 == 0 || B == 1) ? 1 : 0;
     const size_t stage_bytes = (size_t)F * kBgrRowBytes;
     const size_t gray_bytes = (size_t)kConsumerWarps * F * kBgrTilePx;
     int stages = (int)((kSmemBudget - 512 - gray_bytes) / stage_bytes);
@@ -608,7 +605,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
     a.stages = stages;
     const size_t smem = stages * stage_bytes + gray_bytes + (kBgrFullBars + stages) * sizeof(uint64_t) + 16;
-    const int sms = decode_grid_sms(num_sms);
+    const int sms = decode_grid_sms(num_sms, sm_reserve);
     const int grid = (int)(a.total_tiles < sms ? a.total_tiles : sms);
     CUtensorMap tmap;
     int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch, 3, kBgrRowBytes / 4);
@@ -622,7 +619,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
-    a.n = n; a.F = F; a.e = (int)eps;
+    a.n = n; a.F = F; a.e = (int)eps; a.idx_vec = (npix % 4 == 0 || B == 1) ? 1 : 0;
     const size_t stage_bytes = (size_t)F * kTilePx;
     int stages = (int)((kSmemBudget - 256) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -631,7 +628,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
       if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
       a.stages = stages;
       const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16;
-      const int sms = decode_grid_sms(num_sms);
+      const int sms = decode_grid_sms(num_sms, sm_reserve);
       const int grid = (int)(a.total_tiles < sms ? a.total_tiles : sms);
       CUtensorMap tmap;
       int rc = make_frames_tensor_map(&tmap, frames, tma_px, F, B, frame_pitch, scan_pitch);

@@ -7,16 +7,18 @@
 
 namespace sl {
 
+constexpr int kMaxWorld = 16;   // ranks of one multi-GPU exchange (sl_peer.cu); also the destinations of one emission
+
 void count_launch();   // bumps the process-wide kernel launch counter
 
 // ---- stage 1 (sl_decode.cu)
-int init_device_tables();   // once per device: constant look-up tables of the decode kernel
+int decode_device_init();   // once per device (under sl_capi.cu's device mutex): b_inv table, tensor-map encoder, smem opt-ins
+int cloud_device_init();    // once per device: shared-memory opt-ins of the emit kernels (sl_cloud.cu)
 // valid_bitmap (nullable): flat validity bits, scan b at valid_bitmap + b*bitmap_words
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                   int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
-                  int num_sms, cudaStream_t st, bool bgr = false);
-int set_decode_sm_reserve(int sms);   // returns the previous value
+                  int num_sms, cudaStream_t st, bool bgr = false, int sm_reserve = 0);
 int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t frame_pitch, double eps,
                         const double* ld_in, const double* lg_in, double* ld_out, double* lg_out,
                         int8_t* h_codes, int8_t* v_codes, int num_sms, cudaStream_t st);
@@ -54,7 +56,8 @@ int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_ra
                        cudaStream_t st);
 int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
                       int precision, const float* cam_rays, const float* proj_rays, int B, int H, int W,
-                      const void* ws, float* cloud, cudaStream_t st);
+                      const void* ws, float* cloud, cudaStream_t st, float* const* extra = nullptr, int n_extra = 0,
+                      int remote = 0, long long max_points = 0);
 int launch_triangulate_points(const float* cam_pts, const float* proj_pts, long long N,
                               const SlCalib& calib, int precision, double* out, cudaStream_t st);
 size_t filter_workspace_bytes(long long N);

@@ -38,9 +38,8 @@ SIGNATURES = {
     "sl_last_error": (C.c_char_p, []),
     "sl_version": (_i, []),
     "sl_device_check": (_i, [_i]),
-    "sl_set_decode_sm_reserve": (_i, [_i]),
-    "sl_decode_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sl_decode_bgr_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp]),
+    "sl_decode_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sl_decode_bgr_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _i, _vp]),
     "sl_direct_indirect": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp]),
     "sl_is_lit": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _d, _vp, _vp, _vp]),
     "sl_codes_to_pixels": (_i, [_vp, _vp, _i, _i, _i64, _sz, _vp, _vp, _vp]),
@@ -55,7 +54,7 @@ SIGNATURES = {
     "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _vp, _vp, _vp]),
     "sl_emit_cloud": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sl_decode_triangulate_fused": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _vp, _vp,
-                                         _vp, _vp, _vp, _vp]),
+                                         _vp, _vp, _vp, _i, _vp]),
     "sl_triangulate_points": (_i, [_vp, _vp, _i64, C.POINTER(SlCalib), _i, _vp, _vp]),
     "sl_filter_box": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sl_filter_workspace_bytes": (_sz, [_i64]),
@@ -64,10 +63,25 @@ SIGNATURES = {
     "sl_outlier_workspace_bytes": (_sz, [_i64]),
     "sl_pipeline_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "sl_pipeline_destroy": (None, [_vp]),
+    "sl_pipeline_set_sm_reserve": (_i, [_vp, _i]),
     "sl_scan_to_cloud_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(SlCalib), _i, _d, _vp, _vp, _vp, _i64, _vp]),
     "sl_pipeline_submit": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _d, _vp, _i64, _vp]),
     "sl_pipeline_flush": (_i, [_vp]),
     "sl_decode_host": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp]),
+    "sl_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "sl_peer_free": (_i, [_vp]),
+    "sl_peer_export": (_i, [_vp, _vp]),
+    "sl_peer_open": (_i, [_vp, C.POINTER(_vp)]),
+    "sl_peer_close": (_i, [_vp]),
+    "sl_exchange_ctrl_bytes": (_sz, [_i, _i, _i]),
+    "sl_exchange_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(_vp), _i, _i, _d]),
+    "sl_exchange_destroy": (None, [_vp]),
+    "sl_exchange_offsets_by_scan": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sl_exchange_offsets_row_band": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "sl_emit_cloud_multi": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, C.POINTER(_vp), _i, _i64,
+                                _vp]),
+    "sl_exchange_arrive": (_i, [_vp, C.c_uint32, _i, _vp]),
+    "sl_exchange_status": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64)]),
     "sl_launch_count": (_i64, []),
 }
 

@@ -36,12 +36,6 @@ def launch_count() -> int:
     return int(lib().sl_launch_count())
 
 
-def set_decode_sm_reserve(sms: int) -> int:
-    """SMs the persistent decode kernels leave to the kernels of other streams (``sl_set_decode_sm_reserve``);
-    set it (8 on a B200) when independent scans are pipelined over several CUDA streams.  Returns the previous value."""
-    return int(lib().sl_set_decode_sm_reserve(int(sms)))
-
-
 # --------------------------------------------------------------------------- calibration
 @dataclass
 class Calibration:
@@ -119,12 +113,38 @@ def as_u8_stack(images, device=None) -> torch.Tensor:
         return t.to(dev).contiguous()
     if t.dtype == torch.bool:
         raise TypeError("boolean frame stack")
-    t = t.to(dev)
-    u = t.to(torch.uint8) if not t.dtype.is_floating_point else t.clamp(0, 255).to(torch.uint8)
-    if not bool((u.to(t.dtype) == t).all()):
-        raise ValueError("frame stack must hold integer grey levels in 0..255 "
-                         "(the B200 path computes on uint8 samples)")
-    return u.contiguous()
+    # Narrow where the data is: a float64 stack is 8x the bytes of the uint8 samples it holds (763 MB for one 1080p
+    # scan), so a host stack is validated and narrowed frame by frame on the host (torch CPU ops, multi-threaded)
+    # into one pinned uint8 buffer and only that crosses PCIe.
+    u = torch.empty(t.shape, dtype=torch.uint8, device=t.device) if t.is_cuda else _pinned_u8(t.shape)
+    planes = t.reshape(-1, *t.shape[-2:]) if t.dim() >= 3 else t.reshape(1, -1)
+    u_planes = u.reshape(planes.shape)
+    for k in range(planes.shape[0]):
+        src = planes[k]
+        dst = u_planes[k]
+        dst.copy_(src.clamp(0, 255) if src.dtype.is_floating_point else src.clamp(0, 255))
+        if not torch.equal(dst.to(src.dtype), src):
+            raise ValueError("frame stack must hold integer grey levels in 0..255 "
+                             "(the B200 path computes on uint8 samples)")
+    return u.to(dev).contiguous()       # blocking: the pinned staging buffer is reused by the next call
+
+
+_PINNED_STAGE = {}
+
+
+def _pinned_u8(shape) -> torch.Tensor:
+    """Pinned uint8 staging buffer of the drop-in wrappers (one per thread, grown on demand: pinning 95 MB costs
+    tens of milliseconds, a capture loop narrows a stack of the same size every scan)."""
+    import threading
+    n = 1
+    for d in shape:
+        n *= int(d)
+    key = threading.get_ident()
+    buf = _PINNED_STAGE.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+        _PINNED_STAGE[key] = buf
+    return buf[:n].view(*shape)
 
 
 def _stack_dims(frames: torch.Tensor):
@@ -200,7 +220,8 @@ def pair_diff_counts(frames: torch.Tensor, thresh: int = 50) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- stage 1
-def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                  sm_reserve: int = 0):
     """Fused decode: ``(F,H,W)`` / ``(B,F,H,W)`` uint8 -> ``h_pixels, v_pixels`` int16, -1 invalid.
 
     Replaces get_codes + the per-pixel gray_to_decimal loops
@@ -217,7 +238,7 @@ def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[to
     with torch.cuda.device(frames.device):
         fp, sp = _pitches(frames)
         check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
-                                 _ptr(h_idx), _ptr(v_idx), None, None, None, _stream()))
+                                 _ptr(h_idx), _ptr(v_idx), None, None, None, int(sm_reserve), _stream()))
     return h_idx, v_idx
 
 
@@ -244,7 +265,7 @@ def decode_pixels_bgr(frames_bgr: torch.Tensor, eps: float = 1.0):
     v_idx = torch.empty(shape, dtype=torch.int16, device=frames_bgr.device)
     with torch.cuda.device(frames_bgr.device):
         check(lib().sl_decode_bgr_u8(_ptr(frames_bgr), b, f, h, w, fp, sp, float(eps), _ptr(h_idx), _ptr(v_idx),
-                                     None, _stream()))
+                                     None, 0, _stream()))
     return h_idx, v_idx
 
 
@@ -264,7 +285,7 @@ def decode_codes(frames: torch.Tensor, eps: float = 1.0):
     with torch.cuda.device(dev):
         fp, sp = _pitches(frames)
         check(lib().sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
-                                 _ptr(h_idx), _ptr(v_idx), _ptr(h_codes), _ptr(v_codes), None, _stream()))
+                                 _ptr(h_idx), _ptr(v_idx), _ptr(h_codes), _ptr(v_codes), None, 0, _stream()))
     return h_codes, v_codes, h_idx, v_idx
 
 
@@ -552,7 +573,7 @@ class LensTables:
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
                   precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
                   calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None,
-                  row0: int = 0, bgr: bool = False) -> CloudBuffers:
+                  row0: int = 0, bgr: bool = False, sm_reserve: int = 0) -> CloudBuffers:
     """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
     decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
 
@@ -563,6 +584,9 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
 
     ``bgr``: ``frames`` holds the camera's BGR frames ``([B,]F,H,W,3)``; the gray conversion of
     src/3-capture_decode.py:66 happens inside the decode kernel.
+
+    ``sm_reserve``: SMs the persistent decode grid leaves to the kernels of other streams (see ``sl_decode_u8``);
+    8 on a B200 when independent scans are pipelined over several CUDA streams, else 0.
 
     Results are in the returned buffers: ``cloud[:counts[B]]`` (XYZRGB records; ``.xyz`` / ``.rgb``
     views) packed scan after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
@@ -582,7 +606,13 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
             raise TypeError("white_rgb must be a contiguous CUDA uint8 tensor")
         if white_rgb.numel() != b * h * w * 3:
             raise ValueError("white_rgb must be ([B,]H,W,3)")
-    s = calib_struct if calib_struct is not None else calib.struct(row0)
+    if calib_struct is None:
+        s = calib.struct(row0)
+    elif int(calib_struct.cam_row0) != int(row0):
+        s = SlCalib.from_buffer_copy(calib_struct)       # a cached struct is reused for another row band
+        s.cam_row0 = int(row0)
+    else:
+        s = calib_struct
     if tables is not None and (tables.cam_size[0] != w or tables.cam_size[1] < row0 + h
                                or tables.proj_size != tuple(calib.proj_size)):
         raise ValueError("lens tables were built for another image / panel size")
@@ -593,14 +623,15 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     with torch.cuda.device(dev):
         if bgr:
             check(L.sl_decode_bgr_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
-                                     _ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(buffers.ws), st))
+                                     _ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(buffers.ws), int(sm_reserve), st))
             check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
             check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
                                   _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
         else:
             check(L.sl_decode_triangulate_fused(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(white_rgb), C.byref(s),
                                                 _PREC[precision], cam_t, proj_t, _ptr(buffers.h_idx), _ptr(buffers.v_idx),
-                                                _ptr(buffers.ws), _ptr(buffers.cloud), _ptr(buffers.counts), st))
+                                                _ptr(buffers.ws), _ptr(buffers.cloud), _ptr(buffers.counts),
+                                                int(sm_reserve), st))
     return buffers
 
 
@@ -615,6 +646,10 @@ class Pipeline:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self._h = C.c_void_p()
         check(lib().sl_pipeline_create(C.byref(self._h), self.device, self.max_batch, self.f, self.h, self.w))
+
+    def set_sm_reserve(self, sms: int):
+        """SMs this pipeline's decode launches leave to the kernels of its other streams (``sl_pipeline_set_sm_reserve``)."""
+        check(lib().sl_pipeline_set_sm_reserve(self._h, int(sms)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -633,25 +668,65 @@ class Pipeline:
             return C.c_void_p(a.data_ptr())
         return C.c_void_p(a.ctypes.data)
 
+    @staticmethod
+    def _host_check(a, name, dtype, shape=None, min_elems=None, nullable=False):
+        """The C ABI takes raw host pointers: dtype, shape and contiguity are checked here, because a wrong one is a
+        silent misread or an out-of-bounds write by an asynchronous copy.  ``shape`` entries of None are free."""
+        if a is None:
+            if nullable:
+                return None
+            raise TypeError(f"{name} is required")
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                raise TypeError(f"{name}: host buffer expected, got a CUDA tensor")
+            ok_dtype = a.dtype == getattr(torch, dtype)
+            contiguous = a.is_contiguous()
+        elif isinstance(a, np.ndarray):
+            ok_dtype = a.dtype == np.dtype(dtype)
+            contiguous = bool(a.flags["C_CONTIGUOUS"])
+        else:
+            raise TypeError(f"{name}: numpy array or CPU torch tensor expected, got {type(a).__name__}")
+        if not ok_dtype:
+            raise TypeError(f"{name} must be {dtype}, got {a.dtype}")
+        if not contiguous:
+            raise ValueError(f"{name} must be C-contiguous")
+        if shape is not None:
+            got = tuple(a.shape)
+            if len(got) != len(shape) or any(s is not None and int(s) != int(g) for s, g in zip(shape, got)):
+                raise ValueError(f"{name} must have shape {tuple('*' if s is None else s for s in shape)}, got {got}")
+        if min_elems is not None:
+            n = 1
+            for d in a.shape:
+                n *= int(d)
+            if n < min_elems:
+                raise ValueError(f"{name} needs at least {min_elems} elements, got {n}")
+        return a
+
     def scan_to_cloud(self, frames, white_rgb, calib: Calibration, precision="fp32", eps: float = 1.0,
                       cloud=None, counts=None, h_idx=None, v_idx=None):
         """``frames`` host uint8 ``(B,F,H,W)`` (numpy or CPU torch, ideally pinned); the XYZRGB records
         are written into the host tensor ``cloud`` ``(cap,4)`` f32 (allocated pinned when not
         supplied).  Returns ``(cloud[:n], counts)``; ``cloud[:, :3]`` is xyz, ``unpack_rgb(cloud[:, 3])``
         the colours."""
-        shape = tuple(frames.shape)
+        shape = tuple(getattr(frames, "shape", ()))
         if len(shape) == 3:
             shape = (1, *shape)
-        b = shape[0]
-        if shape[1:] != (self.f, self.h, self.w):
+        if len(shape) != 4 or shape[1:] != (self.f, self.h, self.w):
             raise ValueError(f"frames must be (B,{self.f},{self.h},{self.w})")
-        if getattr(frames, "dtype", None) not in (np.uint8, torch.uint8):
-            raise TypeError("frames must be uint8")
+        b = shape[0]
+        self._host_check(frames, "frames", "uint8")
+        self._host_check(white_rgb, "white_rgb", "uint8", min_elems=b * self.h * self.w * 3, nullable=True)
+        if white_rgb is not None and tuple(white_rgb.shape)[-3:] != (self.h, self.w, 3):
+            raise ValueError(f"white_rgb must be ([B,]{self.h},{self.w},3)")
         cap = b * self.h * self.w
         if cloud is None:
             cloud = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
         if counts is None:
             counts = torch.empty(b + 1, dtype=torch.int64)
+        self._host_check(cloud, "cloud", "float32", shape=(None, 4))
+        self._host_check(counts, "counts", "int64", min_elems=b + 1)
+        self._host_check(h_idx, "h_idx", "int16", shape=(b, self.h, self.w), nullable=True)
+        self._host_check(v_idx, "v_idx", "int16", shape=(b, self.h, self.w), nullable=True)
         s = calib.struct()
         check(lib().sl_scan_to_cloud_host(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), b,
                                           C.byref(s), _PREC[precision], float(eps), self._host_ptr(h_idx),
@@ -665,10 +740,10 @@ class Pipeline:
         return; its records go to the host tensor ``cloud`` ``(cap,4)`` f32 and its point count to ``count``
         (int64 host tensor / array of one element).  Results are valid after :meth:`flush`; the buffers must
         stay alive until then."""
-        if tuple(frames.shape) != (self.f, self.h, self.w):
-            raise ValueError(f"frames must be ({self.f},{self.h},{self.w})")
-        if getattr(frames, "dtype", None) not in (np.uint8, torch.uint8):
-            raise TypeError("frames must be uint8")
+        self._host_check(frames, "frames", "uint8", shape=(self.f, self.h, self.w))
+        self._host_check(white_rgb, "white_rgb", "uint8", shape=(self.h, self.w, 3), nullable=True)
+        self._host_check(cloud, "cloud", "float32", shape=(None, 4))
+        self._host_check(count, "count", "int64", min_elems=1)
         s = calib.struct()
         check(lib().sl_pipeline_submit(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), C.byref(s),
                                        _PREC[precision], float(eps), self._host_ptr(cloud), int(cloud.shape[0]),
@@ -680,13 +755,14 @@ class Pipeline:
 
     def decode(self, frames, eps: float = 1.0, codes: bool = False):
         """Host uint8 ``(B,F,H,W)`` -> host int16 ``h_pixels, v_pixels`` [+ int8 tri-state codes]."""
-        shape = tuple(frames.shape)
+        shape = tuple(getattr(frames, "shape", ()))
         squeeze = len(shape) == 3
         if squeeze:
             shape = (1, *shape)
-        b = shape[0]
-        if shape[1:] != (self.f, self.h, self.w):
+        if len(shape) != 4 or shape[1:] != (self.f, self.h, self.w):
             raise ValueError(f"frames must be (B,{self.f},{self.h},{self.w})")
+        b = shape[0]
+        self._host_check(frames, "frames", "uint8")
         n = (self.f - 2) // 4
         h_idx = np.empty((b, self.h, self.w), dtype=np.int16)
         v_idx = np.empty((b, self.h, self.w), dtype=np.int16)

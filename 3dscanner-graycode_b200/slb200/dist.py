@@ -1,12 +1,21 @@
-"""Multi-GPU plumbing: one process per GPU (torch.distributed), scans sharded across ranks.
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), work sharded across ranks.
 
-The path has no inter-pixel dependence, so ranks never talk during decode / triangulation.  The
-only exchange is the final gather of the compacted clouds (all-gather-v over NCCL / NVLink; gloo on
-CPU tensors in the tests).  Row-band sharding of one huge capture is expressed the same way: each
-band is decoded as its own scan and the bands' clouds are merged by `merge_row_bands`.
+The path has no inter-pixel dependence, so ranks never talk during decode / triangulation.  The only
+exchange is the gather of the compacted clouds (BASELINE.json north_star), offered two ways:
+
+* ``CloudExchange`` -- the product path on an NVLink box: every rank's emit kernel writes its records straight
+  into the gathering rank's cloud through a CUDA-IPC peer mapping, at their final packed offsets (the counts are
+  exchanged on the device first, ``sl_exchange_*`` in include/slb200.h).  No host synchronisation, no padding,
+  no concatenation; works for scans sharded over ranks and for row bands of one capture.
+* ``gather_clouds`` -- the same result with NCCL (gloo on CPU tensors in the tests): one all-gather of the counts,
+  then grouped send/recv of every rank's records directly into a pre-sized output at their final offsets.
+
+``merge_row_bands`` is the eager restatement of the row-band merge; the tests use it as the oracle of the
+device-side placement.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -31,43 +40,74 @@ def row_bands(height: int, world: int, align: int = 32) -> List[Tuple[int, int]]
     return out
 
 
-def gather_clouds(cloud: torch.Tensor, counts: torch.Tensor, group=None):
-    """All-gather-v of per-rank packed clouds.
+# --------------------------------------------------------------------------- NCCL / gloo gather
+def gather_clouds(cloud: torch.Tensor, counts: torch.Tensor, group=None, dst: Optional[int] = None,
+                  scans_per_rank: Optional[Sequence[int]] = None, out: Optional[torch.Tensor] = None):
+    """Gather-v of per-rank packed clouds into ONE pre-sized tensor, every rank's records at their final offset.
 
     cloud (n_r, C) (XYZRGB records, C = 4 f32), counts (B_r+1,) int64 with counts[-1] == n_r.
-    Returns (cloud_all, counts_per_rank): clouds concatenated in rank order (scan order is preserved
-    because scans are block-partitioned); counts_per_rank is a list of the per-scan count tensors.
-    Three collectives: sizes, payload (padded to the largest rank), counts.
+    ``dst=None``: all-gather (every rank gets everything); ``dst=r``: only rank r receives (the others return
+    ``(None, counts_per_rank)``).  ``scans_per_rank`` (B_r of every rank, e.g. from ``shard_range``) saves the
+    collective that would otherwise exchange the lengths of the count vectors.
+    Returns (cloud_all, counts_per_rank): clouds in rank order (scan order is preserved because scans are
+    block-partitioned); counts_per_rank is a list of the per-rank count tensors (host, int64, (B_r+1,)).
+    Collectives: one all-gather of the (padded) counts, one grouped send/recv of the payload; one host read of the
+    counts in between (the receive sizes are host arguments of NCCL).
     """
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     dev = cloud.device
-    n_local = torch.tensor([cloud.shape[0], counts.numel()], dtype=torch.int64, device=dev)
-    sizes = [torch.empty_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    n_pts = [int(s[0]) for s in sizes]
-    n_cnt = [int(s[1]) for s in sizes]
-    cap, ccap = max(n_pts), max(n_cnt)
+    if scans_per_rank is None:
+        n_local = torch.tensor([counts.numel() - 1], dtype=torch.int64, device=dev)
+        sizes = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, n_local, group=group)
+        scans_per_rank = [int(v) for v in sizes.tolist()]
+    if len(scans_per_rank) != world or counts.numel() != scans_per_rank[rank] + 1:
+        raise ValueError("scans_per_rank does not match the world size / this rank's count vector")
+    ccap = max(scans_per_rank) + 1
+    mine = torch.zeros(ccap, dtype=torch.int64, device=dev)
+    mine[: counts.numel() - 1] = counts[:-1]
+    mine[ccap - 1] = counts[-1]                                   # the rank's total sits in the last slot
+    cnt_all = torch.empty(world * ccap, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnt_all, mine, group=group)
+    host = cnt_all.cpu().view(world, ccap)                         # the one host read
+    n_pts = [int(host[r, ccap - 1]) for r in range(world)]
+    counts_per_rank = [torch.cat([host[r, : scans_per_rank[r]], host[r, ccap - 1:]]) for r in range(world)]
+    if cloud.shape[0] != n_pts[rank]:
+        raise ValueError("cloud length does not match counts[-1]")
+    offs = [0]
+    for n in n_pts:
+        offs.append(offs[-1] + n)
+    receiver = dst is None or rank == dst
+    tail = tuple(cloud.shape[1:])
+    if receiver:
+        if out is None:
+            out = torch.empty((offs[-1],) + tail, dtype=cloud.dtype, device=dev)
+        elif out.shape[0] < offs[-1] or tuple(out.shape[1:]) != tail or out.dtype != cloud.dtype:
+            raise ValueError("out is too small or of another record type")
+    ops = []
+    for r in range(world):
+        if r == rank:
+            continue
+        if receiver and n_pts[r] > 0:
+            ops.append(dist.P2POp(dist.irecv, out[offs[r]: offs[r + 1]], r if group is None else dist.get_global_rank(group, r), group))
+        if (dst is None or r == dst) and n_pts[rank] > 0:
+            ops.append(dist.P2POp(dist.isend, cloud, r if group is None else dist.get_global_rank(group, r), group))
+    if receiver and n_pts[rank] > 0:
+        out[offs[rank]: offs[rank + 1]].copy_(cloud)
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return (out[: offs[-1]] if receiver else None), counts_per_rank
 
-    def allgather(t, rows):
-        shape = (rows,) + tuple(t.shape[1:])
-        mine = torch.zeros(shape, dtype=t.dtype, device=dev)
-        mine[: t.shape[0]] = t
-        out = torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(out, mine, group=group)
-        return out
 
-    all_pts = allgather(cloud, cap)
-    cloud_cat = torch.cat([all_pts[r * cap: r * cap + n_pts[r]] for r in range(world)])
-    cnt_all = allgather(counts, ccap)
-    counts_per_rank = [cnt_all[r * ccap: r * ccap + n_cnt[r]] for r in range(world)]
-    return cloud_cat, counts_per_rank
-
-
+# --------------------------------------------------------------------------- row-band merge (oracle of the placement)
 def merge_row_bands(band_clouds: Sequence[torch.Tensor], band_cols: Sequence[torch.Tensor]):
     """Merge the clouds of row bands (top to bottom) of ONE capture into the reference's x-major
     order (scanner/triangulation/triangulate.py:52-53): for every camera column, band 0's points,
     then band 1's, ...  band_cols[k] is the int64 (W,) per-column point count of band k (columns in
-    a band's cloud are already x-major).  Returns the merged (N, C) cloud."""
+    a band's cloud are already x-major).  Returns the merged (N, C) cloud.  Eager PyTorch: the tests' oracle of
+    what CloudExchange places on the device."""
     cols = torch.stack(list(band_cols))                        # (K, W)
     k, w = cols.shape
     # destination of each (band, column) run: columns first, bands inside a column
@@ -89,14 +129,9 @@ def merge_row_bands(band_clouds: Sequence[torch.Tensor], band_cols: Sequence[tor
 
 def scan_to_cloud_row_bands(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib, tables,
                             bands: Sequence[Tuple[int, int]], precision="fp32", eps: float = 1.0):
-    """One capture cut into row bands, each decoded + triangulated on its own (this is what every rank
-    of a row-band-sharded job does for its band), then merged back into x-major order.
-
-    On a multi-GPU job call it with the single band of this rank and all-gather the per-band results
-    (`gather_clouds` for the records, `all_gather` for the (W,) column counts) before `merge_row_bands`;
-    with a list of bands on one GPU it is the reference implementation of that flow (tests).
-    Returns (merged cloud (N,4), list of per-band clouds, list of per-band column counts).
-    """
+    """One capture cut into row bands on ONE GPU, each decoded + triangulated on its own and merged with
+    ``merge_row_bands`` -- the single-process restatement of the row-band flow (tests).
+    Returns (merged cloud (N,4), list of per-band clouds, list of per-band column counts)."""
     import slb200
     clouds, cols = [], []
     for (y0, y1) in bands:
@@ -111,3 +146,232 @@ def scan_to_cloud_row_bands(frames: torch.Tensor, white_rgb: Optional[torch.Tens
         clouds.append(bufs.cloud[:n].clone())
         cols.append(bufs.column_counts()[0].to(torch.int64).clone())
     return merge_row_bands(clouds, cols), clouds, cols
+
+
+# --------------------------------------------------------------------------- peer memory (CUDA IPC)
+class _DeviceMemoryView:
+    """``__cuda_array_interface__`` over a raw device allocation, so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerBuffer:
+    """Device memory of THIS process that the other ranks map (``sl_peer_alloc`` / ``sl_peer_export``)."""
+
+    def __init__(self, nbytes: int):
+        from ._lib import check, lib
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib().sl_peer_alloc(self.nbytes, C.byref(p)))
+        self.ptr = int(p.value)
+
+    def handle(self) -> bytes:
+        from ._lib import check, lib
+        buf = C.create_string_buffer(64)
+        check(lib().sl_peer_export(C.c_void_p(self.ptr), buf))
+        return bytes(buf.raw)
+
+    def tensor(self, dtype=torch.uint8) -> torch.Tensor:
+        t = torch.as_tensor(_DeviceMemoryView(self.ptr, self.nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+        return t.view(dtype)
+
+    def free(self):
+        from ._lib import lib
+        if self.ptr:
+            lib().sl_peer_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def _open_peer(handle: bytes) -> int:
+    from ._lib import check, lib
+    p = C.c_void_p()
+    check(lib().sl_peer_open(C.create_string_buffer(handle, 64), C.byref(p)))
+    return int(p.value)
+
+
+class CloudExchange:
+    """Gather of the compacted clouds over NVLink peer memory, fused into the emission.
+
+    One object per process group; every rank constructs it with the same arguments (collective: the IPC handles are
+    exchanged with ``all_gather_object``).  ``gather_to``: the rank that receives the cloud, or ``"all"``.
+    ``max_points``: capacity (records) of the gathered cloud; ``max_scans``: most scans a rank handles per step;
+    ``max_width``: widest image (row-band mode).  All ranks must issue the same sequence of steps, each on one stream.
+
+    After ``scan_to_cloud`` / ``band_to_cloud`` (asynchronous, no host synchronisation) the receiving rank(s) hold
+    ``cloud[:counts_all[-1]]`` = the packed cloud of the whole job, identical to what one GPU produces for the whole
+    batch / the whole image: scan-major, every scan in the reference's x-major order (triangulate.py:52-53).
+    """
+
+    def __init__(self, max_scans: int, max_width: int, max_points: int, group=None, gather_to=0,
+                 timeout_s: float = 20.0):
+        from ._lib import check, lib
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("CloudExchange supports up to 16 ranks")
+        self.max_points = int(max_points)
+        self.max_scans, self.max_width = int(max_scans), int(max_width)
+        self.dsts = list(range(self.world)) if gather_to == "all" else [int(gather_to)]
+        if any(d < 0 or d >= self.world for d in self.dsts):
+            raise ValueError("gather_to outside the group")
+        self.is_dst = self.rank in self.dsts
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        L = lib()
+        nbytes = L.sl_exchange_ctrl_bytes(self.world, self.max_scans, self.max_width)
+        if nbytes == 0:
+            raise ValueError("bad exchange geometry")
+        self._ctrl = PeerBuffer(nbytes)
+        self._cloud = PeerBuffer(self.max_points * 16) if self.is_dst else None
+        mine = {"ctrl": self._ctrl.handle(), "cloud": self._cloud.handle() if self._cloud else None}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._opened = []
+        ctrl_ptrs, cloud_ptrs = [], {}
+        for r, h in enumerate(everyone):
+            if r == self.rank:
+                ctrl_ptrs.append(self._ctrl.ptr)
+                if self._cloud:
+                    cloud_ptrs[r] = self._cloud.ptr
+                continue
+            p = _open_peer(h["ctrl"])
+            self._opened.append(p)
+            ctrl_ptrs.append(p)
+            if r in self.dsts:
+                q = _open_peer(h["cloud"])
+                self._opened.append(q)
+                cloud_ptrs[r] = q
+        # this rank's own cloud first (local stores keep their L2 policy ordering irrelevant; order is free)
+        order = ([self.rank] if self.is_dst else []) + [d for d in self.dsts if d != self.rank]
+        self._cloud_ptr_list = [cloud_ptrs[d] for d in order]
+        self._clouds_c = (C.c_void_p * len(order))(*self._cloud_ptr_list)
+        arr = (C.c_void_p * self.world)(*ctrl_ptrs)
+        self._x = C.c_void_p()
+        check(L.sl_exchange_create(C.byref(self._x), self.rank, self.world, arr, self.max_scans, self.max_width,
+                                   float(timeout_s)))
+        self.dst_mask = 0
+        for d in self.dsts:
+            self.dst_mask |= 1 << d
+        self.counts_all = torch.zeros(max(self.world * self.max_scans, self.world) + 1, dtype=torch.int64, device=self.device)
+        self.cloud = self._cloud.tensor(torch.float32).view(-1, 4) if self._cloud else None
+        dist.barrier(group=group)           # every mapping exists before anyone's first step
+
+    # -- pieces (each asynchronous on the current stream)
+    def offsets_by_scan(self, buffers, b: int, h: int, w: int):
+        from ._lib import check, lib
+        from .api import _ptr, _stream
+        check(lib().sl_exchange_offsets_by_scan(self._x, b, h, w, _ptr(buffers.ws), _ptr(buffers.counts),
+                                                _ptr(self.counts_all), _stream()))
+
+    def offsets_row_band(self, buffers, h: int, w: int):
+        from ._lib import check, lib
+        from .api import _ptr, _stream
+        check(lib().sl_exchange_offsets_row_band(self._x, h, w, _ptr(buffers.ws), _ptr(buffers.counts),
+                                                 _ptr(self.counts_all), _stream()))
+
+    def emit(self, buffers, white_rgb, calib_struct, precision, tables, b: int, h: int, w: int):
+        from ._lib import check, lib
+        from .api import _PREC, _ptr, _stream
+        cam_t = _ptr(tables.cam) if tables is not None else None
+        proj_t = _ptr(tables.proj) if tables is not None else None
+        check(lib().sl_emit_cloud_multi(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
+                                        _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), self._clouds_c,
+                                        len(self._cloud_ptr_list), self.max_points, _stream()))
+
+    def arrive(self):
+        from ._lib import check, lib
+        from .api import _stream
+        check(lib().sl_exchange_arrive(self._x, self.dst_mask, 1 if self.is_dst else 0, _stream()))
+
+    # -- whole steps
+    def scan_to_cloud(self, frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib, precision="fp32",
+                      eps: float = 1.0, buffers=None, calib_struct=None, tables=None, sm_reserve: int = 0):
+        """This rank's block of scans ``(B_r,F,H,W)``: decode -> offsets -> count exchange -> emission into the
+        gathering rank's cloud -> arrival flags.  ``counts_all[:total_scans + 1]`` = per-scan counts + total."""
+        from . import api
+        from ._lib import check, lib
+        api._check_stack(frames)
+        b, f, h, w, _ = api._stack_dims(frames)
+        if b > self.max_scans:
+            raise ValueError(f"{b} scans per step, the exchange was built for {self.max_scans}")
+        fp, sp = api._pitches(frames)
+        if buffers is None:
+            buffers = api.CloudBuffers.allocate(b, h, w, frames.device, cap_points=1)
+        s = calib_struct if calib_struct is not None else calib.struct()
+        L, st = lib(), api._stream()
+        check(L.sl_decode_u8(api._ptr(frames), b, f, h, w, fp, sp, float(eps), api._ptr(buffers.h_idx),
+                             api._ptr(buffers.v_idx), None, None, api._ptr(buffers.ws), int(sm_reserve), st))
+        check(L.sl_compact_offsets_decoded(b, h, w, api._ptr(buffers.ws), api._ptr(buffers.counts), st))
+        self.offsets_by_scan(buffers, b, h, w)
+        self.emit(buffers, white_rgb, s, precision, tables, b, h, w)
+        self.arrive()
+        return buffers
+
+    def band_to_cloud(self, band_frames: torch.Tensor, band_white: Optional[torch.Tensor], calib, row0: int,
+                      precision="fp32", eps: float = 1.0, buffers=None, tables=None, sm_reserve: int = 0):
+        """This rank's band of rows ``(F,H_r,W)`` (rows ``[row0, row0 + H_r)`` of the capture, boundaries multiples
+        of 32 as ``row_bands`` gives them): the merged, x-major cloud of the whole image lands on the gathering
+        rank; ``counts_all[:world + 1]`` = points per band + total.  An empty band still takes part (pass a
+        ``(F,0,W)`` tensor)."""
+        from . import api
+        from ._lib import check, lib
+        f, h, w = band_frames.shape
+        if w > self.max_width:
+            raise ValueError(f"width {w}, the exchange was built for {self.max_width}")
+        L, st = lib(), api._stream()
+        if h == 0:
+            # nothing to decode: publish zero column totals so the other ranks' offsets are right
+            if buffers is None:
+                buffers = api.CloudBuffers.allocate(1, 32, w, band_frames.device, cap_points=1)
+            buffers.ws.zero_()
+            buffers.counts.zero_()
+            self.offsets_row_band(buffers, 32, w)
+            self.arrive()
+            return buffers
+        api._check_stack(band_frames)
+        fp, sp = api._pitches(band_frames)
+        if buffers is None:
+            buffers = api.CloudBuffers.allocate(1, h, w, band_frames.device, cap_points=1)
+        s = calib.struct(row0)
+        check(L.sl_decode_u8(api._ptr(band_frames), 1, f, h, w, fp, sp, float(eps), api._ptr(buffers.h_idx),
+                             api._ptr(buffers.v_idx), None, None, api._ptr(buffers.ws), int(sm_reserve), st))
+        check(L.sl_compact_offsets_decoded(1, h, w, api._ptr(buffers.ws), api._ptr(buffers.counts), st))
+        self.offsets_row_band(buffers, h, w)
+        self.emit(buffers, band_white, s, precision, tables, 1, h, w)
+        self.arrive()
+        return buffers
+
+    def status(self):
+        """Synchronous: raises if a wait for a peer timed out; returns (this rank's first record, total records)
+        of the last step."""
+        from ._lib import check, lib
+        err, base, total = C.c_int(), C.c_int64(), C.c_int64()
+        check(lib().sl_exchange_status(self._x, C.byref(err), C.byref(base), C.byref(total)))
+        if err.value:
+            raise RuntimeError(f"cloud exchange: a wait for a peer rank timed out (stage {err.value})")
+        return int(base.value), int(total.value)
+
+    def close(self):
+        from ._lib import lib
+        L = lib()
+        if getattr(self, "_x", None):
+            torch.cuda.synchronize()
+            try:
+                dist.barrier(group=self.group)      # nobody unmaps while a peer may still write
+            except Exception:
+                pass
+            L.sl_exchange_destroy(self._x)
+            self._x = None
+            self.cloud = None
+            for p in self._opened:
+                L.sl_peer_close(C.c_void_p(p))
+            self._opened = []
+            try:
+                dist.barrier(group=self.group)
+            except Exception:
+                pass
+            self._ctrl.free()
+            if self._cloud:
+                self._cloud.free()

@@ -59,12 +59,6 @@ int sl_version(void);
 /* 0 if `device` (or the current device when < 0) is an sm_100 GPU */
 int sl_device_check(int device);
 
-/* Process-wide tuning option: the persistent decode kernels launch one CTA per SM; `sms` SMs are left out of that
- * grid (default 0).  Worth setting (8 on a B200) by callers that pipeline independent scans over several CUDA
- * streams: the short offsets / emit kernels of the other scans then find SMs of their own (bench step 34.2 -> 32.4 us
- * per 1080p scan); a decode launch running alone gets ~5 % slower.  Returns the previous value. */
-int sl_set_decode_sm_reserve(int sms);
-
 /* ---------------------------------------------------------------- decode (stage 1) */
 
 /* Fused decode of B frame stacks.
@@ -80,10 +74,18 @@ int sl_set_decode_sm_reserve(int sms);
  *   cloud_workspace  nullable device scratch of sl_cloud_workspace_bytes(B,H,W): when given, the
  *               kernel also leaves the per-pixel validity bitmap there, so the compaction can start
  *               from it (sl_compact_offsets_decoded) instead of re-reading the indices
+ *   sm_reserve  launch option, normally 0: the persistent decode kernel runs one CTA per SM; `sm_reserve` SMs are
+ *               left out of that grid.  Worth setting (8 on a B200) by callers that pipeline independent scans over
+ *               several CUDA streams: the short offsets / emit kernels of the other scans then find SMs of their own
+ *               (bench step 34.2 -> 32.4 us per 1080p scan); a decode launch running alone gets ~5 % slower.
+ * Alignment: any; the TMA kernel needs frames, frame_pitch, scan_pitch multiples of 16 bytes and h_idx / v_idx
+ * multiples of 8, anything else is decoded by the (slower) generic kernel with the same results.
+ * The library keeps no mutable process state: every option is an argument, per-device constants are initialised once
+ * under a lock by the first call on that device, and calls from several host threads / streams / devices may overlap.
  */
 int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                 int8_t* v_codes, void* cloud_workspace, void* stream);
+                 int8_t* v_codes, void* cloud_workspace, int sm_reserve, void* stream);
 
 /* The same decode straight from the camera's 8-bit BGR frames: the capture loop's per-frame
  * cv2.cvtColor(frame, COLOR_BGR2GRAY) (src/3-capture_decode.py:66; gray = (3735 B + 19235 G + 9798 R + 16384) >> 15)
@@ -93,7 +95,7 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
  * Other arguments as sl_decode_u8 (the tri-state code planes are not offered here). */
 int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size_t frame_pitch,
                      size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx,
-                     void* cloud_workspace, void* stream);
+                     void* cloud_workspace, int sm_reserve, void* stream);
 
 /* get_direct_indirect (decode_codes.py:90-122): L_d, L_g device f64 [H*W] (NaN where
  * white+black == 0, as in the reference). */
@@ -131,7 +133,7 @@ int sl_pair_diff_counts(const uint8_t* frames, int n_frames, int64_t elems_per_f
 
 /* ---------------------------------------------------------- triangulation (stage 2) */
 
-/* Bytes of device scratch the compaction needs for B scans of H x W. */
+/* Bytes of device scratch the compaction needs for B scans of H x W (the workspace must be 256-byte aligned). */
 size_t sl_cloud_workspace_bytes(int B, int H, int W);
 
 /* Ordered-compaction offsets: counts the valid pixels (h != -1 and v != -1) and prepares
@@ -171,7 +173,9 @@ int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, 
  * cloud (N,4) f32: one 16-byte XYZRGB record per point = [x, y, z, bits(R | G<<8 | B<<16)] (the
  * layout PCL calls PointXYZRGB; colour word 0 when white_rgb is NULL), packed over the batch, each
  * scan in the reference's x-major order.
- * Requires sl_compact_offsets[_decoded] on the same workspace first. */
+ * Requires sl_compact_offsets[_decoded] on the same workspace first.
+ * Alignment: cloud 16 bytes, cam_rays 16, proj_rays 8 (SL_ERR_BAD_ARG otherwise); h_idx / v_idx 8 bytes and white_rgb 4
+ * for the vector loads -- buffers with less (any 2-byte aligned sub-view) take the scalar path, same results. */
 int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
                   const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
                   int B, int H, int W, const void* workspace, float* cloud, void* stream);
@@ -185,7 +189,8 @@ int sl_emit_cloud(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
 int sl_decode_triangulate_fused(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                                 size_t scan_pitch, double eps, const uint8_t* white_rgb, const SlCalib* calib,
                                 int precision, const float* cam_rays, const float* proj_rays, int16_t* h_idx,
-                                int16_t* v_idx, void* workspace, float* cloud, int64_t* counts, void* stream);
+                                int16_t* v_idx, void* workspace, float* cloud, int64_t* counts, int sm_reserve,
+                                void* stream);
 
 /* Triangulate.triangulate (triangulate.py:73-97) on caller-supplied point pairs.
  * cam_pts, proj_pts device f32 (N,2); out device f64 (3,N) like the reference's return. */
@@ -235,6 +240,9 @@ typedef struct SlPipeline SlPipeline;
  * max_batch scans of F frames of H x W are staged per call. */
 int sl_pipeline_create(SlPipeline** out, int device, int max_batch, int F, int H, int W);
 void sl_pipeline_destroy(SlPipeline* p);
+/* sm_reserve (see sl_decode_u8) of this pipeline's decode launches; default 0.  The pipeline entry points select the
+ * pipeline's device for the duration of the call and restore the caller's current device before returning. */
+int sl_pipeline_set_sm_reserve(SlPipeline* p, int sms);
 
 /* Whole path for B (<= max_batch) scans held in HOST memory:
  * H2D of the frame stacks and white images, decode, compaction, triangulation, D2H.
@@ -267,6 +275,73 @@ int sl_pipeline_flush(SlPipeline* p);
 int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
                    int16_t* h_idx_host, int16_t* v_idx_host, int8_t* h_codes_host,
                    int8_t* v_codes_host);
+
+/* ------------------------------------------------- multi-GPU: clouds gathered over NVLink peer memory */
+
+/* BASELINE.json's partitioning (the reference itself is a single process): one process per GPU, independent scans
+ * block-sharded over the ranks (360-degree / turntable batches) or one huge capture cut into bands of rows; the only
+ * exchange is the gather of the compacted clouds.  Because the cloud is an ordered compaction (scan-major, every scan
+ * in the reference's x-major order, scanner/triangulation/triangulate.py:52-53), a rank must know where its records
+ * start in the gathered cloud before it emits.  So the ranks first exchange their counts through small control blocks
+ * in peer-mapped memory (sl_exchange_offsets_*: publishes this rank's counts to every rank, waits for everybody's,
+ * rebases the offsets in this rank's compaction workspace), then sl_emit_cloud_multi writes the records straight into
+ * the gathering rank's cloud through its peer mapping (the transfer rides on the emission, no staging, padding or
+ * concatenation), and sl_exchange_arrive tells the gathering rank(s) that they have landed.
+ * The caller provides the plumbing: one process per GPU, the 64-byte handles carried between the processes by any
+ * means (torch.distributed in slb200/dist.py). */
+#define SL_PEER_HANDLE_BYTES 64
+#define SL_MAX_RANKS 16
+
+/* Device memory other processes can map (cudaMalloc + CUDA IPC), zero-filled.  sl_peer_export writes the 64-byte
+ * handle of an allocation made by sl_peer_alloc in THIS process; sl_peer_open maps another process's allocation into
+ * this one (peer access over NVLink is enabled on first use) and returns its address here; sl_peer_close unmaps. */
+int sl_peer_alloc(size_t bytes, void** ptr);
+int sl_peer_free(void* ptr);
+int sl_peer_export(const void* ptr, void* handle64);
+int sl_peer_open(const void* handle64, void** ptr);
+int sl_peer_close(void* ptr);
+
+typedef struct SlExchange SlExchange;
+
+/* Size of one rank's control block (allocate it with sl_peer_alloc, zero-filled, and open it on every other rank). */
+size_t sl_exchange_ctrl_bytes(int world, int max_scans, int max_width);
+/* ctrl_ptrs[r] = control block of rank r as mapped in this process (ctrl_ptrs[rank] is the local allocation);
+ * max_scans = most scans one rank processes per step, max_width = widest image (row-band mode);
+ * timeout_s: a wait for a peer gives up after this long (<= 0: 20 s) and reports through sl_exchange_status. */
+int sl_exchange_create(SlExchange** out, int rank, int world, void* const* ctrl_ptrs, int max_scans, int max_width,
+                       double timeout_s);
+void sl_exchange_destroy(SlExchange* x);
+
+/* Scans sharded over ranks.  After sl_compact_offsets[_decoded] of this rank's B scans (counts = its int64 [B+1]
+ * output, still on the device): every offset in `workspace` is advanced by the number of points of all lower ranks,
+ * so that the emission writes at the packed position of the whole batch.  counts_all (nullable, device int64
+ * [total scans + 1]): every scan's point count in rank order, then the grand total.  Asynchronous on `stream`;
+ * every rank must make the same sequence of sl_exchange_* calls. */
+int sl_exchange_offsets_by_scan(SlExchange* x, int B, int H, int W, void* workspace, const int64_t* counts,
+                                int64_t* counts_all, void* stream);
+/* One capture cut into row bands, rank r holding the r-th band (H rows here, boundaries multiples of 32 rows, calib
+ * cam_row0 = first row): after sl_compact_offsets[_decoded](1, H, W) the per-column totals of all ranks are exchanged
+ * and the offsets in `workspace` become the positions of this band's runs inside the columns of the whole image.
+ * counts_all (nullable, device int64 [world + 1]): points per rank, then the total. */
+int sl_exchange_offsets_row_band(SlExchange* x, int H, int W, void* workspace, const int64_t* counts,
+                                 int64_t* counts_all, void* stream);
+
+/* sl_emit_cloud writing every record to n_clouds buffers (1..SL_MAX_RANKS; local or peer-mapped, each 16-byte aligned):
+ * clouds[0] = the gathering rank's cloud for a gather, all ranks' clouds for an all-gather.  max_points = capacity of
+ * the gathered cloud in records (the rebased offsets can exceed B*H*W). */
+int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                        const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                        int B, int H, int W, const void* workspace, float* const* clouds, int n_clouds,
+                        int64_t max_points, void* stream);
+
+/* After the emission: tell the ranks in dst_mask (bit r = rank r) that this rank's records of the current step have
+ * landed; with wait != 0 also wait (on the stream, not the host) until every rank has told this one the same --
+ * the gathered cloud is then complete for whatever is queued next on `stream`. */
+int sl_exchange_arrive(SlExchange* x, uint32_t dst_mask, int wait, void* stream);
+
+/* Synchronous: error = 0, or 1 / 2 if a wait in sl_exchange_offsets_* / sl_exchange_arrive timed out (results of that
+ * step are then invalid); rank_base / grand_total (nullable) = this rank's first record and the total of the last step. */
+int sl_exchange_status(SlExchange* x, int* error, int64_t* rank_base, int64_t* grand_total);
 
 /* Number of kernels this library has launched in the calling process (all streams). */
 int64_t sl_launch_count(void);

@@ -57,6 +57,8 @@ def test_ctypes_signatures_match_the_header():
                 assert ctype is C.c_int64, f"{name}: {decl}"
             elif decl.startswith("int "):
                 assert ctype is C.c_int, f"{name}: {decl}"
+            elif decl.startswith("uint32_t"):
+                assert ctype is C.c_uint32, f"{name}: {decl}"
             else:
                 raise AssertionError(f"{name}: unhandled parameter declaration {decl!r}")
         if "*" in ret and "char" in ret:

@@ -58,18 +58,18 @@ def single_scan(name, cam, proj, ring, iters, streams, sm_reserve=8):
     torch.cuda.synchronize()
     res = {}
     for s_ in sorted({1, streams}):
-        slb200.set_decode_sm_reserve(sm_reserve if s_ > 1 else 0)     # pipelined: leave SMs to the other streams' kernels
+        rsv = sm_reserve if s_ > 1 else 0     # pipelined: leave SMs to the other streams' kernels
         fns = [(lambda i=i: slb200.scan_to_cloud(scans[i][0], scans[i][1], calib, buffers=bufs[i % s_], tables=tables,
-                                                 calib_struct=cs)) for i in range(ring)]
+                                                 calib_struct=cs, sm_reserve=rsv)) for i in range(ring)]
         us = time_graphs(fns, iters, s_)
-        dec = [(lambda i=i: slb200.decode_pixels(scans[i][0], out=(bufs[i % s_].h_idx[0], bufs[i % s_].v_idx[0]))) for i in range(ring)]
+        dec = [(lambda i=i: slb200.decode_pixels(scans[i][0], out=(bufs[i % s_].h_idx[0], bufs[i % s_].v_idx[0]),
+                                                 sm_reserve=rsv)) for i in range(ring)]
         dus = time_graphs(dec, iters, s_)
         F = scans[0][0].shape[0]
         mpx = cam[0] * cam[1] / 1e6
         gbs = (F + 4) * cam[0] * cam[1] / (dus * 1e-6) / 1e9
         res[f"streams_{s_}"] = {"us_per_scan": us, "Mpx_per_s": mpx / (us * 1e-6), "scans_per_s": 1e6 / us,
                                 "decode_us": dus, "decode_GBps": gbs, "decode_frac_of_measured_peak": gbs / PEAK}
-    slb200.set_decode_sm_reserve(0)
     res["valid_fraction"] = float(bufs[0].counts[1]) / (cam[0] * cam[1])
     out[name] = res
     del scans, bufs
