@@ -115,6 +115,22 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
                        bitmap, words, ticket, sms, (cudaStream_t)stream, false, sm_reserve);
 }
 
+int sl_decode_u8_stats(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch, size_t scan_pitch,
+                       double eps, int16_t* h_idx, int16_t* v_idx, uint64_t* stats, void* stream) {
+  int rc = check_decode_shape(B, F, H, W);
+  if (rc) return rc;
+  if (!frames || !h_idx || !v_idx || !stats) { set_error("null buffer"); return kErrBadArg; }
+  const long long npix = (long long)H * W;
+  if (frame_pitch < (size_t)npix) { set_error("frame_pitch smaller than H*W"); return kErrBadArg; }
+  if (B > 1 && scan_pitch < frame_pitch * (size_t)F) { set_error("scan_pitch smaller than F*frame_pitch"); return kErrBadArg; }
+  if (!(eps == eps)) { set_error("eps is NaN"); return kErrBadArg; }
+  int sms = 0;
+  if ((rc = device_gate(&sms))) return rc;
+  SL_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), (cudaStream_t)stream));
+  return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr, nullptr, 0,
+                       nullptr, sms, (cudaStream_t)stream, false, 0, (unsigned long long*)stats);
+}
+
 int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size_t frame_pitch,
                      size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx,
                      void* cloud_workspace, int sm_reserve, void* stream) {

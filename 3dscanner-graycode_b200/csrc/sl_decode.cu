@@ -102,6 +102,7 @@ struct DecodeArgs {
   long long total_tiles; // B * tiles_per_scan
   int tiles_per_scan;
   int n, F, e, stages;
+  unsigned long long* stats;   // nullable: [0] += quads decoded, [1] += quads that took the full rule evaluation
   int idx_vec;           // every scan's index planes are 8-byte aligned (B == 1 or npix % 4 == 0): vector stores
 };
 
@@ -123,6 +124,7 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   // bars[0..stages) = full, bars[stages..2*stages) = empty; then the sub-tile claim counter
   unsigned int* next_sub = reinterpret_cast<unsigned int*>(bars + 2 * stages);
+  unsigned int* warp_stats = next_sub + 2;          // [kConsumerWarps][2], only touched when a.stats is given
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -168,6 +170,7 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   // ring slot s / phase ph of iteration `it`, and (scan b, tile in scan) of tile t = blockIdx.x + it * grid
   const uint32_t total = (uint32_t)a.total_tiles, tps = (uint32_t)a.tiles_per_scan, grid = gridDim.x;
   uint32_t it_prev = 0, s = 0, ph = 0, tile = blockIdx.x, b = 0;
+  if (a.stats && lane == 0) { warp_stats[2 * warp] = 0; warp_stats[2 * warp + 1] = 0; }
   for (;;) {
     unsigned int sub = 0;
     if (lane == 0) sub = atomicAdd(next_sub, 1u);
@@ -175,7 +178,13 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
     const uint32_t it = sub / kSubTiles;                 // kSubTiles is a power of two
     const int part = (int)(sub % kSubTiles);
     const uint32_t t = blockIdx.x + it * grid;
-    if (t >= total) break;
+    if (t >= total) {
+      if (a.stats && lane == 0) {
+        atomicAdd(a.stats, (unsigned long long)warp_stats[2 * warp]);
+        atomicAdd(a.stats + 1, (unsigned long long)warp_stats[2 * warp + 1]);
+      }
+      break;
+    }
     const uint32_t delta = it - it_prev;
     it_prev = it;
     s += delta;
@@ -188,7 +197,7 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
     const long long rem = a.npix4 - px0;
     const int cnt = (int)(rem < kTilePx ? rem : kTilePx);
     const int off = part * 128 + off_lane;                                 // pixel offset in tile
-    uint32_t nib = 0;
+    uint32_t nib = 0, slow = 0;
     if (off < cnt) {
 #if !defined(SL_DECODE_GENERIC_LD)
       // explicit ld.shared with a 32-bit address.  Through the lambda the compiler only sees a generic pointer and
@@ -211,6 +220,11 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
       store_idx4(a.h_idx + (size_t)b * a.npix + px, o.h01, o.h23, a.idx_vec);
       store_idx4(a.v_idx + (size_t)b * a.npix + px, o.v01, o.v23, a.idx_vec);
       nib = ((o.valid & kMsb4) * 0x00204081u) >> 28;      // the 4 msb flags gathered into bits 0..3
+      slow = o.slow;
+    }
+    if (a.stats) {
+      const unsigned int m_all = __ballot_sync(0xffffffffu, off < cnt), m_slow = __ballot_sync(0xffffffffu, slow != 0);
+      if (lane == 0) { warp_stats[2 * warp] += __popc(m_all); warp_stats[2 * warp + 1] += __popc(m_slow); }
     }
     if (a.bitmap) {
       // 8 neighbouring lanes hold the 32 validity bits of 32 consecutive pixels
@@ -575,7 +589,7 @@ int decode_device_init() {
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                   int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
-                  int num_sms, cudaStream_t st, bool bgr, int sm_reserve) {
+                  int num_sms, cudaStream_t st, bool bgr, int sm_reserve, unsigned long long* stats) {
   const int n = (F - 2) / 4;
   const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
   const bool aligned = ((uintptr_t)frames % 16 == 0) && (frame_pitch % 16 == 0) &&
@@ -592,7 +606,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = nullptr; a.v_codes = nullptr;
-    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket; a.stats = nullptr;
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kBgrTilePx - 1) / kBgrTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
@@ -615,19 +629,19 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
-    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket; a.stats = stats;
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
     a.n = n; a.F = F; a.e = (int)eps; a.idx_vec = (npix % 4 == 0 || B == 1) ? 1 : 0;
     const size_t stage_bytes = (size_t)F * kTilePx;
-    int stages = (int)((kSmemBudget - 256) / stage_bytes);
+    int stages = (int)((kSmemBudget - 512) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { tma_px = 0; }
     else {
       if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one decode launch"); return kErrBadArg; }
       a.stages = stages;
-      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16;
+      const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t) + 16 + 8 * kConsumerWarps;
       const int sms = decode_grid_sms(num_sms, sm_reserve);
       const int grid = (int)(a.total_tiles < sms ? a.total_tiles : sms);
       CUtensorMap tmap;

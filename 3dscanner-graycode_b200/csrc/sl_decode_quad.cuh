@@ -16,6 +16,7 @@ struct QuadOut {
   uint32_t h01, h23;   // int16 lanes: projector column of pixels {0,1} / {2,3}; 0xffff = -1
   uint32_t v01, v23;   // projector row
   uint32_t valid;      // bit 7 of lane k set iff pixel k decoded on both axes
+  uint32_t slow;       // 1 if the quad needed the full rule evaluation (diagnostics: sl_decode_u8_stats)
 };
 
 // Tri-state bytes (1, 0, 0xff=-1) of one bit for 4 pixels (decode_codes.py:162-182 output).
@@ -167,10 +168,12 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
       finish_axis(hA, hB, kMsb4, n, out.h01, out.h23);
       finish_axis(vA, vB, kMsb4, n, out.v01, out.v23);
       out.valid = kMsb4;
+      out.slow = 0;
       return out;
     }
   }
   full_rules<NB, CODES>(ld, st, n, qt, ek, out);
+  out.slow = 1;
   return out;
 }
 

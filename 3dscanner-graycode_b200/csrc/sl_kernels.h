@@ -18,7 +18,8 @@ int cloud_device_init();    // once per device: shared-memory opt-ins of the emi
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                   int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
-                  int num_sms, cudaStream_t st, bool bgr = false, int sm_reserve = 0);
+                  int num_sms, cudaStream_t st, bool bgr = false, int sm_reserve = 0,
+                  unsigned long long* stats = nullptr);
 int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t frame_pitch, double eps,
                         const double* ld_in, const double* lg_in, double* ld_out, double* lg_out,
                         int8_t* h_codes, int8_t* v_codes, int num_sms, cudaStream_t st);

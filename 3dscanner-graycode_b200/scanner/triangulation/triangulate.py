@@ -41,6 +41,10 @@ class Triangulate(object):
         self.proj_T = proj_T
         self.proj_R = proj_R
         self.image_folder = image_folder
+        # device-side copies of what the previous call returned, keyed by the identity of the NumPy arrays handed
+        # out: src/4-triangulate.py:63-71 chains get_cam_proj_pts -> triangulate -> filter_3d_pts on those very
+        # arrays, so the chain does not re-upload what the GPU just produced
+        self._dev_cache = {}
 
     # -- helpers ---------------------------------------------------------------------------
     def _calibration(self):
@@ -76,18 +80,29 @@ class Triangulate(object):
             # the reference falls off the end with `colors_array` unbound (triangulate.py:66-71)
             raise UnboundLocalError("cannot access local variable 'colors_array': img_white is None")
         colors_array = rgb.cpu().numpy().astype(np.float64) / 255.0
+        self._dev_cache = {"pairs": (cam_pts, proj_pts, cam, proj)}
         return cam_pts, proj_pts, colors_array
 
     def triangulate(self, cam_pts, proj_pts):
         """``(3,N)`` float64 points (reference triangulate.py:73-97)."""
-        pts = slb200.triangulate_points(np.asarray(cam_pts, dtype=np.float32), np.asarray(proj_pts, dtype=np.float32),
-                                        self._calibration(), precision="fp64")
-        return pts.cpu().numpy()
+        hit = self._dev_cache.get("pairs")
+        if hit is not None and hit[0] is cam_pts and hit[1] is proj_pts:
+            cam_dev, proj_dev = hit[2], hit[3]                   # still on the device from get_cam_proj_pts
+        else:
+            cam_dev, proj_dev = np.asarray(cam_pts, dtype=np.float32), np.asarray(proj_pts, dtype=np.float32)
+        pts = slb200.triangulate_points(cam_dev, proj_dev, self._calibration(), precision="fp64")
+        out = pts.cpu().numpy()
+        self._dev_cache["pts"] = (out, pts)
+        return out
 
     def filter_3d_pts(self, Pts, colors, threshold=.5):
         """Strict +-threshold box filter (reference triangulate.py:99-122)."""
         dev = torch.device("cuda", torch.cuda.current_device())
-        p = torch.as_tensor(np.ascontiguousarray(np.asarray(Pts, dtype=np.float64))).to(dev)
+        hit = self._dev_cache.get("pts")
+        if hit is not None and hit[0] is Pts:
+            p = hit[1]                                           # still on the device from triangulate
+        else:
+            p = torch.as_tensor(np.ascontiguousarray(np.asarray(Pts, dtype=np.float64))).to(dev)
         c = torch.as_tensor(np.ascontiguousarray(np.asarray(colors, dtype=np.float64))).to(dev)
         out_p, out_c = slb200.filter_box(p, c, float(threshold))
         return out_p.cpu().numpy(), out_c.cpu().numpy()

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sl_version": (_i, []),
     "sl_device_check": (_i, [_i]),
     "sl_decode_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "sl_decode_u8_stats": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _vp]),
     "sl_decode_bgr_u8": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, _vp, _vp, _i, _vp]),
     "sl_direct_indirect": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp]),
     "sl_is_lit": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _d, _vp, _vp, _vp]),

@@ -242,6 +242,24 @@ def decode_pixels(frames: torch.Tensor, eps: float = 1.0, out: Optional[Tuple[to
     return h_idx, v_idx
 
 
+def decode_stats(frames: torch.Tensor, eps: float = 1.0) -> dict:
+    """Diagnostics of the fused decode on this input (``sl_decode_u8_stats``): how many 4-pixel groups needed the
+    full evaluation of the four rules instead of the single-threshold fast pass.  Synchronises."""
+    _check_stack(frames)
+    b, f, h, w, batched = _stack_dims(frames)
+    shape = (b, h, w) if batched else (h, w)
+    h_idx = torch.empty(shape, dtype=torch.int16, device=frames.device)
+    v_idx = torch.empty(shape, dtype=torch.int16, device=frames.device)
+    stats = torch.zeros(2, dtype=torch.int64, device=frames.device)
+    with torch.cuda.device(frames.device):
+        fp, sp = _pitches(frames)
+        check(lib().sl_decode_u8_stats(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(h_idx), _ptr(v_idx),
+                                       _ptr(stats), _stream()))
+    quads, full = (int(x) for x in stats.tolist())
+    return {"quads": quads, "full_rule_quads": full, "full_rule_fraction": (full / quads) if quads else None,
+            "fast_pass_fraction": (1.0 - full / quads) if quads else None}
+
+
 def _bgr_view(frames_bgr: torch.Tensor):
     """``([B,]F,H,W,3)`` uint8 CUDA -> (b, f, h, w, batched, frame_pitch, scan_pitch); dense frames only."""
     if not (isinstance(frames_bgr, torch.Tensor) and frames_bgr.is_cuda and frames_bgr.dtype == torch.uint8

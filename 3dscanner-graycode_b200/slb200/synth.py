@@ -58,12 +58,16 @@ def pattern_stack(proj_size: Tuple[int, int], device) -> torch.Tensor:
 
 
 def render_scan(cam_size: Tuple[int, int], proj_size: Tuple[int, int], seed: int = 0, device="cpu",
-                patterns: torch.Tensor = None, calib: Calibration = None):
+                patterns: torch.Tensor = None, calib: Calibration = None, scene: str = "plane"):
     """Returns ``frames (F,H,W) uint8``, ``white_rgb (H,W,3) uint8`` on ``device``.
 
     frame = clip(ambient + albedo * 0.85 * pattern[v,u] + N(0,1.5)) where (u,v) is the projector
     pixel the camera ray hits on the plane; pixels that miss the panel see ambient light only; the
     left eighth of the image is a dark noise band that exercises the invalid path.
+
+    ``scene="hard"``: the same geometry under conditions that defeat the decoder's single-threshold fast pass --
+    dark surface (albedo U[0.08, 0.45]), pattern contrast 0.5, an inter-reflection term (0.3 x the 31-pixel
+    box-blurred pattern: light from neighbouring stripes, strongest for the fine patterns) and N(0, 4) noise.
     """
     W, H = cam_size
     pw, ph = proj_size
@@ -98,9 +102,18 @@ def render_scan(cam_size: Tuple[int, int], proj_size: Tuple[int, int], seed: int
     uc, vc = u.clamp(0, pw - 1), v.clamp(0, ph - 1)
     lit = patterns[:, vc, uc].to(torch.float32)                     # (F,H,W)
     lit = lit * inside.to(torch.float32)[None]
-    albedo = 0.3 + 0.7 * torch.rand((H, W), generator=g, device=dev, dtype=torch.float32)
-    noise = 1.5 * torch.randn((F, H, W), generator=g, device=dev, dtype=torch.float32)
-    frames = (10.0 + albedo[None] * 0.85 * lit + noise).round().clamp(0, 255).to(torch.uint8)
+    if scene == "hard":
+        albedo = 0.08 + 0.37 * torch.rand((H, W), generator=g, device=dev, dtype=torch.float32)
+        noise = 4.0 * torch.randn((F, H, W), generator=g, device=dev, dtype=torch.float32)
+        glob = torch.nn.functional.avg_pool2d(lit[None], 31, stride=1, padding=15)[0]
+        frames = (10.0 + albedo[None] * (0.5 * lit + 0.3 * glob) + noise).round().clamp(0, 255).to(torch.uint8)
+        del glob
+    elif scene == "plane":
+        albedo = 0.3 + 0.7 * torch.rand((H, W), generator=g, device=dev, dtype=torch.float32)
+        noise = 1.5 * torch.randn((F, H, W), generator=g, device=dev, dtype=torch.float32)
+        frames = (10.0 + albedo[None] * 0.85 * lit + noise).round().clamp(0, 255).to(torch.uint8)
+    else:
+        raise ValueError("scene must be 'plane' or 'hard'")
     band = W // 8
     frames[:, :, :band] = torch.randint(0, 12, (F, H, band), generator=g, device=dev, dtype=torch.uint8)
     white = frames[1]

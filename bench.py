@@ -5,18 +5,21 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (N=1): BASELINE config[1] -- one 1920x1080 camera scan of a 1920x1080 projector sequence
-(n = 11 bits, F = 46 frames), synthetic textured plane (slb200/synth.py).  A step = one scan through
-decode -> ordered compaction -> undistort + triangulate.  Steps rotate over a ring of resident
-scans larger than L2 so no step finds its input in cache.  N > 1: every rank runs the same
-per-rank workload on its own scans (weak scaling by scan, no data-path collective); the
-all-gather-v of the compacted clouds is timed separately and reported under "gather".
+N = 1 -- BASELINE config[1]: 1920x1080 camera scans of a 1920x1080 projector sequence (n = 11 bits, F = 46 frames),
+synthetic textured plane (slb200/synth.py).  A step = ONE PASS over a ring of 12 resident scans (1.14 GB > L2), each
+scan through decode -> ordered compaction -> undistort + triangulate, independent scans pipelined over 4 CUDA streams.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through
-the host-buffer C-ABI call (sl_scan_to_cloud_host: pinned host frames in, host cloud out), `roofline`
-the fused decode kernel against the measured HBM peak, `cpu_baseline` the oracle port timed on this
-box's host cores.  `--impl reference` times the reference algorithm's CPU port (oracle/) on all
-host cores for the driver's ratio.
+N > 1 -- the multi-GPU configurations north_star names, the cloud gather INSIDE the timed step:
+  config[3]: a 64-view turntable batch of 1080p scans block-sharded over the N ranks; a step = every rank's decode +
+             compaction + emission of its views, the records written straight into rank 0's packed cloud over NVLink
+             peer memory (slb200.dist.CloudExchange), strong scaling.  `value` = 64 views / step time.
+  config[2]: one 3840x2160, F = 50 capture cut into N row bands, the merged x-major cloud on rank 0 (`row_bands`).
+Compute-only and the NCCL gather (slb200.dist.gather_clouds) are timed beside it.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the host-buffer
+C-ABI call (pinned host frames in, host cloud out), `roofline` the fused decode kernel against the measured HBM peak,
+`cpu_baseline` the oracle port timed on this box's host cores (and used to CHECK the GPU result of the timed scans).
+`--impl reference` times the reference algorithm's CPU port (oracle/) on all host cores for the driver's ratio.
 """
 from __future__ import annotations
 
@@ -37,10 +40,25 @@ PROJ_SIZE = (1920, 1080)
 N_BITS = 11
 N_FRAMES = 4 * N_BITS + 2
 MPX = CAM_SIZE[0] * CAM_SIZE[1] / 1e6
+CAM_4K = (3840, 2160)
+PROJ_4K = (3840, 2160)
 METRIC = "Mpx/s decoded+triangulated"
 WORKLOAD = "config[1]: single 1920x1080 camera scan of a 1920x1080 projector Gray sequence (11+11 bits + inverses + white/black)"
+WORKLOAD_MULTI = ("config[3]: 64-view turntable batch of 1080p scans (11+11 bits) block-sharded by scan over the ranks, "
+                  "compacted clouds gathered on rank 0 inside the step")
 RING = 12         # resident scans per rank: 12 x 95.4 MB = 1.14 GB > 126 MB L2
 STREAMS = 4       # independent scans are pipelined over 4 CUDA streams (own buffers each)
+VIEWS = 64        # config[3]
+
+
+def config_n1(ring_n=RING):
+    """`config` of the N = 1 line, identical in both arms (`--impl b200` and `--impl reference`)."""
+    W, H = CAM_SIZE
+    return {"workload": WORKLOAD, "camera": f"{W}x{H}", "projector": f"{PROJ_SIZE[0]}x{PROJ_SIZE[1]}",
+            "frames_per_scan": N_FRAMES, "n_bits": N_BITS,
+            "scene": "synthetic textured plane at ~0.9 m, noise sigma 1.5, dark noise band over the left eighth (slb200/synth.py), ~87.6 % valid pixels",
+            "triangulation_precision": "fp32 on the GPU (1e-4 relative), fp64 in the CPU reference",
+            "l2": f"inputs rotate over a ring of {ring_n} resident scans ({ring_n * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)"}
 
 
 def load_peaks():
@@ -104,128 +122,781 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU side (oracle port)
-def _oracle_calib(calib):
+def _oracle_calib(calib, proj_size=PROJ_SIZE):
     return dict(cam_mtx=calib.cam_mtx, cam_dist=calib.cam_dist, proj_mtx=calib.proj_mtx, proj_dist=calib.proj_dist,
-                proj_R=calib.proj_R, proj_T=calib.proj_T, proj_size=PROJ_SIZE, proj_calib_size=PROJ_SIZE)
+                proj_R=calib.proj_R, proj_T=calib.proj_T, proj_size=proj_size, proj_calib_size=proj_size)
 
 
 def _oracle_band(args):
-    """One bounded sample: rows [y0, y1) of a scan through the oracle's whole path."""
+    """Rows [y0, y0 + rows) of a scan through the oracle's whole path (decode, pair extraction, triangulation with
+    the rows' true image coordinates).  Returns (h_pixels, v_pixels, pts (3,N), colors (N,3)) of the band."""
     import numpy as np
     from oracle import graycode_oracle as oracle
-    frames, white, cal = args
-    h_px, v_px, pts, colors = oracle.scan_to_cloud(frames.astype(np.float64), white, cal)
-    return int(pts.shape[1])
+    frames, white, cal, y0 = args
+    h_px, v_px = oracle.decode_pixels(frames.astype(np.float64))
+    cam, proj, colors = oracle.cam_proj_pairs(h_px, v_px, cal["proj_size"], white)
+    cam = cam + np.array([[0, y0]], dtype=cam.dtype)
+    pm = oracle.scale_proj_mtx(cal["proj_mtx"], cal["proj_size"], cal["proj_calib_size"])
+    pts = oracle.triangulate(cam, proj, cal["cam_mtx"], cal["cam_dist"], pm, cal["proj_dist"], cal["proj_R"], cal["proj_T"])
+    return h_px, v_px, pts, colors
+
+
+def _oracle_band_count(args):
+    return int(_oracle_band(args)[2].shape[1])
 
 
 def ncu_traffic_per_launch():
     """dram__bytes_read + dram__bytes_write of the decode kernel per launch, from the committed ncu launch
-    list of the same workload (profiles/r01_launches.csv); None if the file is missing."""
-    path = os.path.join(ROOT, "profiles", "r01_launches.csv")
-    try:
-        rd = wr = None
-        with open(path) as f:
-            for line in f:
-                if "decode_tma_kernel" not in line:
-                    continue
-                parts = line.strip().split(",")
-                if "dram__bytes_read.sum" in line:
-                    rd = float(parts[-2])
-                elif "dram__bytes_write.sum" in line:
-                    wr = float(parts[-2])
-        return None if rd is None or wr is None else rd + wr
-    except Exception:
-        return None
+    list of the same workload (newest profiles/rNN_launches.csv); None if the file is missing."""
+    for name in ("r02_launches.csv", "r01_launches.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            rd = wr = None
+            with open(path) as f:
+                for line in f:
+                    if "decode_tma_kernel" not in line:
+                        continue
+                    parts = line.strip().split(",")
+                    if "dram__bytes_read.sum" in line:
+                        rd = float(parts[-2])
+                    elif "dram__bytes_write.sum" in line:
+                        wr = float(parts[-2])
+            if rd is not None and wr is not None:
+                return rd + wr, f"profiles/{name}"
+        except Exception:
+            pass
+    return None, None
 
 
-def cpu_baseline_single_core(frames_np, white_np, calib, budget_s=15.0):
-    """Oracle port, one thread, on a bounded sample of the 1080p scan (whole rows)."""
+def cpu_baseline_and_parity(frames_np, white_np, calib, gpu_h, gpu_v, gpu_cloud, budget_s=15.0):
+    """Oracle port, one thread, on bands of whole rows of ring scan 0 -- the CPU baseline -- and, with the very same
+    band results, the parity check of what the GPU produced for that scan in the timed configuration:
+    indices bit-exact, point count / x-major order / colours exact, points within 1e-4 relative (fp32 mode)."""
     import numpy as np
     cal = _oracle_calib(calib)
+    H, W = gpu_h.shape
     rows = 135                                   # 1/8 of the scan per call
+    valid = (gpu_h != -1) & (gpu_v != -1)
+    order = (np.cumsum(valid.T.ravel()) - 1).reshape(W, H)          # x-major position of every valid pixel
+    n_gpu = int(valid.sum())
+    xyz = gpu_cloud[:n_gpu, :3].astype(np.float64)
+    rgb = gpu_cloud[:n_gpu, 3].copy().view(np.uint8).reshape(-1, 4)[:, :3]
+    scale = None
     t0 = time.perf_counter()
-    done_px, calls = 0, 0
+    cpu_s, done_px, calls = 0.0, 0, 0
+    checked_px, max_rel, ok, why = 0, 0.0, True, None
     y = 0
-    while True:
-        band = slice(y, y + rows)
-        _oracle_band((frames_np[:, band], white_np[band], cal))
-        done_px += rows * CAM_SIZE[0]
+    while y < H:
+        y1 = min(H, y + rows)
+        c0 = time.perf_counter()
+        h_px, v_px, pts, colors = _oracle_band((frames_np[:, y:y1], white_np[y:y1], cal, y))
+        cpu_s += time.perf_counter() - c0
+        done_px += (y1 - y) * W
         calls += 1
-        y = (y + rows) % (CAM_SIZE[1] - rows + 1)
-        el = time.perf_counter() - t0
-        if el > budget_s or calls >= 96:
+        # ---- parity of the GPU's full-scan result on these rows
+        if not (np.array_equal(gpu_h[y:y1], h_px) and np.array_equal(gpu_v[y:y1], v_px)):
+            ok, why = False, f"decoded indices differ in rows {y}..{y1}"
+        else:
+            sel = order[:, y:y1][valid.T[:, y:y1]]                   # x-major inside the band == the oracle's order
+            if sel.size != pts.shape[1]:
+                ok, why = False, f"point count differs in rows {y}..{y1}"
+            else:
+                if scale is None:
+                    scale = float(np.abs(pts).max()) if pts.size else 1.0
+                if pts.size:
+                    max_rel = max(max_rel, float(np.abs(xyz[sel] - pts.T).max()) / scale)
+                if not np.array_equal(rgb[sel], np.round(colors * 255).astype(np.uint8)):
+                    ok, why = False, f"colours differ in rows {y}..{y1}"
+        checked_px += (y1 - y) * W
+        y = y1
+        if time.perf_counter() - t0 > budget_s:
             break
-    return {"value": done_px / 1e6 / el, "unit": "Mpx/s", "cores": 1, "kind": "port",
-            "sample": f"{calls} bands of {rows} rows x 1920 px of the 1080p scan ({done_px / 1e6:.2f} Mpx, {el:.1f} s), "
-                      "oracle/graycode_oracle.py scan_to_cloud (NumPy restatement of the reference)"}
+    if max_rel >= 1e-4:
+        ok, why = False, f"points differ by {max_rel:.2e} relative"
+    cpu = {"value": done_px / 1e6 / cpu_s, "unit": "Mpx/s", "cores": 1, "kind": "port",
+           "sample": f"{calls} bands of {rows} rows x {W} px of the 1080p scan ({done_px / 1e6:.2f} Mpx, {cpu_s:.1f} s of CPU), "
+                     "oracle/graycode_oracle.py (vectorised NumPy restatement of the reference, ~25x the reference's own "
+                     "per-pixel Python loops: 0.054 Mpx/s, profiles/r02_reference_faithful.json)"}
+    parity = {"parity_checked": bool(ok), "rows_checked": int(checked_px // W), "of_rows": int(H),
+              "points_max_rel_err": max_rel, "tolerance": 1e-4,
+              "what": "GPU result of ring scan 0 (the timed configuration: fp32, lens tables) vs the oracle on the same rows: "
+                      "h/v indices bit-exact, count + x-major order + colours exact, points relative to the largest coordinate"}
+    if why:
+        parity["failure"] = why
+    return cpu, parity
 
 
 def run_reference(args):
     """`--impl reference`: the reference algorithm's CPU port (oracle/) on all host cores.  The
     reference itself is pure Python (no build) and cannot travel to the GPU box; the oracle is its
-    NumPy restatement, pinned bit-exact against it (tests/test_oracle_*).  Each step = one band of rows
-    of the 1080p scan per worker process."""
+    NumPy restatement, pinned bit-exact against it (tests/test_oracle_*).  Each step = ONE whole 1080p scan
+    (all 1080 rows), cut into bands of rows that the worker processes share."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    import numpy as np
     from slb200 import synth
     cores = os.cpu_count() or 1
     calib = synth.synthetic_calibration(CAM_SIZE, PROJ_SIZE)
     frames, white = synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=0, device="cpu")
     frames_np, white_np = frames.numpy(), white.numpy()
     cal = _oracle_calib(calib)
+    H = CAM_SIZE[1]
+    # bands of ~34 rows: 32 jobs per scan, dealt to the pool (whole scan per step, same config as the GPU arm)
+    n_jobs = max(cores, 32)
+    edges = [round(i * H / n_jobs) for i in range(n_jobs + 1)]
+    jobs = [(frames_np[:, edges[i]:edges[i + 1]], white_np[edges[i]:edges[i + 1]], cal, edges[i]) for i in range(n_jobs)
+            if edges[i + 1] > edges[i]]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        # size the per-step sample so warmup + steps fit in ~100 s
-        probe_rows = 8
+        def step():
+            return sum(pool.map(_oracle_band_count, jobs))
+
         t0 = time.perf_counter()
-        pool.map(_oracle_band, [(frames_np[:, i * probe_rows:(i + 1) * probe_rows], white_np[i * probe_rows:(i + 1) * probe_rows], cal)
-                                for i in range(cores)])
+        step()                                                  # probe: one scan
         probe = time.perf_counter() - t0
-        per_row = probe / probe_rows
-        budget = 100.0 / max(1, args.steps + args.warmup)
-        rows = int(max(2, min(CAM_SIZE[1] // cores, budget / max(per_row, 1e-6))))
-
-        def step(k):
-            jobs = []
-            for i in range(cores):
-                y = ((k * cores + i) * rows) % (CAM_SIZE[1] - rows + 1)
-                jobs.append((frames_np[:, y:y + rows], white_np[y:y + rows], cal))
-            pool.map(_oracle_band, jobs)
-
-        for k in range(args.warmup):
-            step(k)
+        # keep warmup + steps within ~150 s: the driver's K may be larger than the CPU can do; then fewer
+        # timed steps are run and reported as such
+        k = max(1, min(args.steps, int(150.0 / max(probe, 1e-3)) - args.warmup))
+        w = max(0, min(args.warmup, int(40.0 / max(probe, 1e-3))))
+        for _ in range(w):
+            step()
         t0 = time.perf_counter()
-        for k in range(args.steps):
-            step(k)
+        for _ in range(k):
+            pts = step()
         el = time.perf_counter() - t0
-    px = args.steps * cores * rows * CAM_SIZE[0]
-    value = px / 1e6 / el
-    sample = f"per step: {cores} bands of {rows} rows x 1920 px (one per worker process) of the 1080p scan"
+    value = k * MPX / el
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "steps": k, "warmup": w, "ms_per_step": el / k * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": config_n1(max(2, args.ring)),
+        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port",
+                         "sample": f"per step: one whole 1080p scan (1080 rows, {pts} points) cut into {len(jobs)} bands of rows over {cores} "
+                                   "worker processes; oracle/graycode_oracle.py (vectorised NumPy restatement of the reference)"},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
-    global RING
-    RING = max(2, args.ring)
+# --------------------------------------------------------------------------- GPU helpers
+class StreamRing:
+    """CUDA graphs of a per-slot function, slot i on stream i % S; replay / event timing over all streams."""
+
+    def __init__(self, torch, dev, n_streams):
+        self.torch, self.dev = torch, dev
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+        self.main = torch.cuda.current_stream()
+
+    def capture(self, fn, n_slots):
+        torch = self.torch
+        S = len(self.streams)
+        graphs = []
+        for i in range(n_slots):
+            with torch.cuda.stream(self.streams[i % S]):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.streams[i % S]):
+                    fn(i, i % S)
+                graphs.append(g)
+        torch.cuda.synchronize()
+        return graphs
+
+    def replay(self, graphs, n):
+        S = len(self.streams)
+        for i in range(n):
+            k = i % len(graphs)
+            with self.torch.cuda.stream(self.streams[k % S]):
+                graphs[k].replay()
+
+    def timed(self, graphs, n):
+        """n replays bracketed by CUDA events: the start event gates every stream, the end event waits for all."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.main)
+        for st in self.streams:
+            st.wait_event(e0)
+        self.replay(graphs, n)
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.main.wait_event(ev)
+        e1.record(self.main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+
+def chain_us(torch, stream, fn_list, reps):
+    """One CUDA graph holding the launches of fn_list in sequence on one stream (kernel after kernel, nothing else
+    running); microseconds per launch."""
+    with torch.cuda.stream(stream):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for fn in fn_list:
+                fn()
+        g.replay()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        for _ in range(reps):
+            g.replay()
+        d1.record(stream)
+    torch.cuda.synchronize()
+    return d0.elapsed_time(d1) / (reps * len(fn_list)) * 1e3
+
+
+def pcie_ceiling(torch, dev, world, dist, seconds=0.5):
+    """Pinned H2D and D2H copies running at the same time on this rank while every other rank does the same: the
+    link ceiling the host-buffer path can reach on this box at N ranks (GB/s per rank, aggregate)."""
+    n = 256 << 20
+    hx = torch.empty(n, dtype=torch.uint8).pin_memory()
+    hy = torch.empty(n, dtype=torch.uint8).pin_memory()
+    dx = torch.empty(n, dtype=torch.uint8, device=dev)
+    dy = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    out = {}
+    for name, up, down in (("h2d_only", True, False), ("d2h_only", False, True), ("both", True, True)):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        reps = 4
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    dx.copy_(hx, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    hy.copy_(dy, non_blocking=True)
+        torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        gbs = reps * n / float(el.item()) / 1e9
+        out[name] = {"per_rank_each_direction_gbs": gbs, "aggregate_gbs": gbs * world * ((1 if up else 0) + (1 if down else 0))}
+    return out
+
+
+def e2e_pipeline(torch, slb200, dev, local, world, dist, calib, ring_frames, ring_white, K):
+    """The host-buffer C-ABI path: pinned host frames in, host cloud out, one scan per sl_pipeline_submit."""
+    W, H = CAM_SIZE
+    eb = min(12, len(ring_frames))                                   # distinct host scans (pinned), streamed round-robin
+    host_frames = torch.empty((eb, N_FRAMES, H, W), dtype=torch.uint8).pin_memory()
+    host_white = torch.empty((eb, H, W, 3), dtype=torch.uint8).pin_memory()
+    for i in range(eb):
+        host_frames[i].copy_(ring_frames[i]); host_white[i].copy_(ring_white[i])
+    pipe = slb200.Pipeline(N_FRAMES, H, W, max_batch=eb, device=local)
+    cloud_h = torch.empty((eb * H * W, 4), dtype=torch.float32).pin_memory()
+    calls = max(2, min(5, (K + eb - 1) // eb))                       # 24..60 scans streamed
+    cnts = [torch.zeros(1, dtype=torch.int64) for _ in range(eb)]
+    clouds = [cloud_h[i * H * W:(i + 1) * H * W] for i in range(eb)]
+
+    def stream_scans(n):
+        for j in range(n):
+            i = j % eb
+            pipe.submit(host_frames[i], host_white[i], calib, clouds[i], cnts[i])
+        pipe.flush()
+
+    stream_scans(eb)                                                                  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    stream_scans(calls * eb)
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    n_pts = sum(int(c) for c in cnts)
+    pipe.close()
+    return {"value": world * calls * eb * MPX / float(el.item()), "unit": "Mpx/s",
+            "h2d_bytes_per_step": N_FRAMES * H * W + H * W * 3,
+            "d2h_bytes_per_step": int(n_pts / eb * 16 + 16),
+            "scans_per_call": 1, "distinct_host_scans": eb, "steps": calls * eb,
+            "ms_per_scan": float(el.item()) / (calls * eb) * 1e3,
+            "step": "one scan (the e2e path is per scan; `value` is Mpx/s)",
+            "api": "sl_pipeline_submit per scan + sl_pipeline_flush (slb200.Pipeline.submit / flush), pinned host buffers"}
+
+
+def e2e_dropin(torch, calib, frames_u8, white_u8, reps=3):
+    """The reference's own API, NumPy in / NumPy out, as src/3 and src/4 call it (with the two-line patch of
+    INTEGRATION.md for the per-pixel loops): float64 frame stack -> decode_pixels -> Triangulate(...).point_cloud."""
     import numpy as np
+    from scanner.grayCode import decode_codes as dc
+    from scanner.triangulation import Triangulate
+    stack = frames_u8.cpu().numpy().astype(np.float64)             # src/3-capture_decode.py:69: the stack is float64
+    white = white_u8.cpu().numpy()
+    best = None
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        h_pixels, v_pixels = dc.decode_pixels(stack)
+        t1 = time.perf_counter()
+        tri = Triangulate(h_pixels, v_pixels, CAM_SIZE, calib.cam_mtx, calib.cam_dist, PROJ_SIZE, PROJ_SIZE,
+                          calib.proj_mtx.copy(), calib.proj_dist, calib.proj_R, calib.proj_T)
+        pts, colors = tri.point_cloud(white, precision="fp32")
+        t2 = time.perf_counter()
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1, pts.shape[1])
+    return {"value": MPX / best[0], "unit": "Mpx/s", "ms_per_scan": best[0] * 1e3, "decode_ms": best[1] * 1e3,
+            "triangulate_ms": best[2] * 1e3, "points": int(best[3]),
+            "h2d_bytes_per_step": N_FRAMES * CAM_SIZE[0] * CAM_SIZE[1] + 7 * CAM_SIZE[0] * CAM_SIZE[1],
+            "d2h_bytes_per_step": 4 * CAM_SIZE[0] * CAM_SIZE[1] + 16 * int(best[3]),
+            "api": "scanner.grayCode.decode_codes.decode_pixels(float64 (F,H,W) NumPy stack) -> int64 h/v_pixels -> "
+                   "scanner.triangulation.Triangulate(...).point_cloud(white) -> (3,N) f64 + (N,3) f64 NumPy; best of "
+                   f"{reps + 1} calls, host conversions (f64 -> u8 validation, int64 / f64 outputs) inside the time"}
+
+
+# --------------------------------------------------------------------------- N = 1
+def run_single(args, torch, slb200, synth, dev, local):
+    from slb200.api import CloudBuffers
+    import numpy as np
+    ring_n = max(2, args.ring)
+    W, H = CAM_SIZE
+    K, Wm = args.steps, args.warmup
+    calib = synth.synthetic_calibration(CAM_SIZE, PROJ_SIZE)
+    cstruct = calib.struct()
+
+    # ---- synthetic inputs, resident in HBM: a ring of scans
+    pats = synth.pattern_stack(PROJ_SIZE, dev)
+    ring_frames, ring_white = [], []
+    for i in range(ring_n):
+        fr, wh = synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=i, device=dev, patterns=pats, calib=calib)
+        ring_frames.append(fr); ring_white.append(wh)
+    S = max(1, min(args.streams, ring_n))
+    # the persistent decode grid leaves a few SMs to the offsets / emit kernels of the scans in flight on the other
+    # streams (sm_reserve launch argument of sl_decode_u8)
+    sm_reserve = (8 if S > 1 else 0) if args.sm_reserve is None else max(0, args.sm_reserve)
+    bufsets = [CloudBuffers.allocate(1, H, W, dev) for _ in range(S)]
+    bufs = bufsets[0]
+    tables = slb200.LensTables(calib, CAM_SIZE, dev)                 # once per calibration
+    torch.cuda.synchronize()
+
+    def step_fn(lens_tables, rsv):
+        def fn(i, k):
+            slb200.scan_to_cloud(ring_frames[i % ring_n], ring_white[i % ring_n], calib, precision="fp32",
+                                 buffers=bufsets[k], calib_struct=cstruct, tables=lens_tables, sm_reserve=rsv)
+        return fn
+
+    primary_tables = None if args.lens == "iterate" else tables
+    before = slb200.launch_count()
+    step_fn(primary_tables, sm_reserve)(0, 0)
+    kernels_per_scan = slb200.launch_count() - before
+    torch.cuda.synchronize()
+    ring = StreamRing(torch, dev, S)
+    graphs = ring.capture(step_fn(primary_tables, sm_reserve), ring_n)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- timed region: EXACTLY K steps, a step = one pass over the ring (ring_n scans)
+    ring.replay(graphs, Wm * ring_n)
+    torch.cuda.synchronize()
+    ms_total = ring.timed(graphs, K * ring_n)
+    torch.cuda.synchronize()
+    valid_pts = int(bufs.counts[1].item())
+    # results of ring scan 0 in the timed configuration, for the parity check below
+    graphs[0].replay()
+    torch.cuda.synchronize()
+    gpu_h = bufs.h_idx[0].cpu().numpy()
+    gpu_v = bufs.v_idx[0].cpu().numpy()
+    gpu_cloud = bufs.cloud[: int(bufs.counts[1].item())].cpu().numpy()
+
+    # ---- the other lens mode for the same step (north_star names the in-kernel Brown-Conrady iteration)
+    other_tables = tables if primary_tables is None else None
+    graphs_o = ring.capture(step_fn(other_tables, sm_reserve), ring_n)
+    ring.replay(graphs_o, 2 * ring_n)
+    ko = max(2, min(K, 10))
+    ms_other = ring.timed(graphs_o, ko * ring_n) / (ko * ring_n)
+    del graphs_o
+
+    def lens_name(t):
+        return "tables" if t is not None else "iterate"
+    lens_modes = {
+        lens_name(primary_tables): {"us_per_scan": ms_total / (K * ring_n) * 1e3, "Mpx_per_s": K * ring_n * MPX / (ms_total * 1e-3)},
+        lens_name(other_tables): {"us_per_scan": ms_other * 1e3, "Mpx_per_s": MPX / (ms_other * 1e-3)},
+        "tables_is": "exact fp64 rays of both pixel lattices built once per calibration (sl_lens_tables), looked up per valid pixel",
+        "iterate_is": "5 Brown-Conrady fixed-point iterations per valid pixel and lens inside the emit kernel (fp32)",
+    }
+
+    # ---- roofline of the dominant kernel (fused decode): decode-only launches over the same ring, timed
+    # with CUDA events (a) in the configuration the step uses (pipelined over the S streams) and
+    # (b) isolated: back to back on one stream, every launch waiting for the previous one.
+    kr = max(60, min(K * ring_n, 600))
+    dgraphs = ring.capture(lambda i, k: slb200.decode_pixels(ring_frames[i], out=(bufsets[k].h_idx[0], bufsets[k].v_idx[0]),
+                                                             sm_reserve=sm_reserve), ring_n)
+    ring.replay(dgraphs, 10)
+    torch.cuda.synchronize()
+    decode_ms = ring.timed(dgraphs, kr) / kr
+    reps = max(3, kr // ring_n)
+    decode_solo_us = chain_us(torch, ring.streams[0],
+                              [(lambda i=i: slb200.decode_pixels(ring_frames[i], out=(bufs.h_idx[0], bufs.v_idx[0])))
+                               for i in range(ring_n)], reps)
+    peak, peak_src = load_peaks()
+    algo_bytes = (N_FRAMES + 4) * W * H                      # F u8 reads + two int16 writes per pixel
+    achieved = algo_bytes / (decode_ms * 1e-3) / 1e9
+    achieved_solo = algo_bytes / (decode_solo_us * 1e-6) / 1e9
+
+    # ---- stage 2 on its own (offsets + emit of decoded scans), isolated chain on one stream
+    from slb200.api import _ptr, _stream, check, lib, _PREC
+    import ctypes as C
+    L = lib()
+    stage_sets = []
+    for i in range(min(ring_n, 6)):
+        b = CloudBuffers.allocate(1, H, W, dev)
+        slb200.scan_to_cloud(ring_frames[i], ring_white[i], calib, buffers=b, calib_struct=cstruct, tables=tables)
+        stage_sets.append((b, ring_white[i]))
+    torch.cuda.synchronize()
+
+    def offsets_fn(b):
+        return lambda: check(L.sl_compact_offsets_decoded(1, H, W, _ptr(b.ws), _ptr(b.counts), _stream()))
+
+    def emit_fn(b, wh, t):
+        return lambda: check(L.sl_emit_cloud(_ptr(b.h_idx), _ptr(b.v_idx), _ptr(wh), C.byref(cstruct), _PREC["fp32"],
+                                             _ptr(t.cam) if t is not None else None, _ptr(t.proj) if t is not None else None,
+                                             1, H, W, _ptr(b.ws), _ptr(b.cloud), _stream()))
+    off_us = chain_us(torch, ring.streams[0], [offsets_fn(b) for b, _ in stage_sets], 20)
+    emit_us = chain_us(torch, ring.streams[0], [emit_fn(b, wh, tables) for b, wh in stage_sets], 20)
+    emit_it_us = chain_us(torch, ring.streams[0], [emit_fn(b, wh, None) for b, wh in stage_sets], 10)
+    vfrac = valid_pts / (W * H)
+    emit_bytes = (7 + 16 * vfrac) * W * H                    # 4 B indices + 3 B colour read, 16-byte record per valid px
+    stage2 = {
+        "offsets_us": off_us, "emit_tables_us": emit_us, "emit_iterate_us": emit_it_us,
+        "emit_algorithmic_bytes": emit_bytes, "emit_tables_gbs": emit_bytes / (emit_us * 1e-6) / 1e9,
+        "emit_tables_frac_of_peak": emit_bytes / (emit_us * 1e-6) / 1e9 / peak,
+        "timing": "isolated: one CUDA graph of 6 launches back to back on one stream, warm L2 (lens tables resident)",
+    }
+    del stage_sets
+
+    # ---- the harder synthetic scene (low contrast + inter-reflection + more noise): decode only, pipelined
+    hard = None
+    if not args.no_hard:
+        hf = [synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=100 + i, device=dev, patterns=pats, calib=calib, scene="hard")[0]
+              for i in range(ring_n)]
+        hgraphs = ring.capture(lambda i, k: slb200.decode_pixels(hf[i], out=(bufsets[k].h_idx[0], bufsets[k].v_idx[0]),
+                                                                 sm_reserve=sm_reserve), ring_n)
+        ring.replay(hgraphs, 10)
+        hms = ring.timed(hgraphs, kr) / kr
+        hv = slb200.decode_pixels(hf[0])
+        hard_valid = float(((hv[0] != -1) & (hv[1] != -1)).float().mean().item())
+        hard = {"us_per_launch": hms * 1e3, "achieved": algo_bytes / (hms * 1e-3) / 1e9,
+                "frac": algo_bytes / (hms * 1e-3) / 1e9 / peak, "valid_fraction": hard_valid,
+                "full_rule_quads": slb200.decode_stats(hf[0])["full_rule_fraction"],
+                "scene": "albedo U[0.08,0.45], pattern contrast 0.5, inter-reflection term (0.3 x 31-px box-blurred pattern), "
+                         "N(0,4) noise: most quads fail the single-threshold fast pass"}
+        del hf, hgraphs
+    fast = slb200.decode_stats(ring_frames[0])
+    del pats
+
+    # ---- e2e through the host-buffer C-ABI call and through the reference's own API
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_pipeline(torch, slb200, dev, local, 1, None, calib, ring_frames, ring_white, K * ring_n)
+        e2e["ceiling_gbs"] = pcie_ceiling(torch, dev, 1, None)
+        e2e["dropin"] = e2e_dropin(torch, calib, ring_frames[0], ring_white[0])
+    clocks = sampler.stop()
+
+    # ---- the multi-GPU configurations on ONE GPU (the 1-rank reference of their strong scaling)
+    multi = None
+    if not args.no_multi:
+        del graphs, dgraphs
+        torch.cuda.empty_cache()
+        multi = multi_configs(args, torch, slb200, synth, dev, 0, 1, None, tables, calib)
+
+    # ---- CPU baseline (the oracle port on one core) + parity of the timed scan against it
+    cpu, parity = None, None
+    if not args.no_cpu:
+        cpu, parity = cpu_baseline_and_parity(ring_frames[0].cpu().numpy(), ring_white[0].cpu().numpy(), calib,
+                                              gpu_h, gpu_v, gpu_cloud)
+
+    traffic, traffic_src = ncu_traffic_per_launch()
+    line = {
+        "metric": METRIC, "value": K * ring_n * MPX / (ms_total * 1e-3), "unit": "Mpx/s",
+        "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": config_n1(ring_n),
+        "run": {"scans_per_step_per_gpu": ring_n, "step": f"one pass over the ring of {ring_n} resident scans",
+                "valid_fraction": vfrac, "lens": lens_name(primary_tables), "parallelism": "1 GPU",
+                "launch": f"CUDA graph per scan (decode, strip-prefix + column scan, emit: {kernels_per_scan} kernels); independent scans pipelined over {S} CUDA streams",
+                "decode_grid": f"one persistent CTA per SM, {sm_reserve} SMs left to the other streams' kernels"},
+        "us_per_scan": ms_total / (K * ring_n) * 1e3,
+        "scans_per_s": K * ring_n / (ms_total * 1e-3),
+        "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, {traffic_src}",
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": decode_ms * 1e3,
+                     "frac_of_nominal_8000": achieved / 8000.0,
+                     "timing": f"{kr} decode-only launches over the ring, CUDA events, pipelined over {S} streams like the step",
+                     "isolated": {"us_per_launch": decode_solo_us, "achieved": achieved_solo,
+                                  "frac": achieved_solo / peak,
+                                  "timing": "the same launches strictly one after another on one stream (one CUDA graph of RING launches)"},
+                     "fast_pass": fast, "hard_scene": hard},
+        "lens_modes": lens_modes, "stage2": stage2,
+        "cpu_baseline": cpu, "e2e": e2e, "multi": multi, "clocks": clocks,
+        "gpu_launches": int(K * ring_n * kernels_per_scan),
+    }
+    if parity:
+        line.update(parity)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- multi-GPU configurations
+def multi_configs(args, torch, slb200, synth, dev, rank, world, dist, tables, calib):
+    """config[3] (64 views sharded by scan) and config[2] (one 4K capture cut into row bands), every variant timed
+    with CUDA events on every rank, MAX over ranks.  world = 1 gives the single-GPU reference of the same work."""
+    from slb200.api import CloudBuffers
+    from slb200.dist import CloudExchange, gather_clouds, row_bands, shard_range
+    W, H = CAM_SIZE
+    K = max(3, min(args.steps, args.multi_steps))
+    Wm = max(3, min(args.warmup, 5))
+    out = {}
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_steps(fn, k=K, wm=Wm):
+        for _ in range(wm):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ================= config[3]: 64 views by scan
+    lo, hi = shard_range(VIEWS, rank, world)
+    B = hi - lo
+    per_rank = [shard_range(VIEWS, r, world)[1] - shard_range(VIEWS, r, world)[0] for r in range(world)]
+    pats = synth.pattern_stack(PROJ_SIZE, dev)
+    distinct = min(B, 8)
+    frames = torch.empty((B, N_FRAMES, H, W), dtype=torch.uint8, device=dev)
+    white = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    for i in range(distinct):
+        fr, wh = synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=1000 + (lo + i) % 61, device=dev, patterns=pats, calib=calib)
+        for b in range(i, B, distinct):
+            frames[b].copy_(fr); white[b].copy_(wh)
+    del pats
+    cstruct = calib.struct()
+    bufs = CloudBuffers.allocate(B, H, W, dev)
+    slb200.scan_to_cloud(frames, white, calib, buffers=bufs, calib_struct=cstruct, tables=tables)
+    torch.cuda.synchronize()
+    n_local = int(bufs.counts[-1].item())
+    c3 = {"views": VIEWS, "views_per_rank": per_rank, "points_this_rank": n_local,
+          "l2": f"every rank's {B} views = {B * N_FRAMES * W * H / 1e6:.0f} MB of frames per step (> 126 MB L2)"}
+    ms_compute = timed_steps(lambda: slb200.scan_to_cloud(frames, white, calib, buffers=bufs, calib_struct=cstruct, tables=tables))
+    c3["compute_only"] = {"ms_per_step": ms_compute, "Mpx_per_s": VIEWS * MPX / (ms_compute * 1e-3),
+                          "scans_per_s": VIEWS / (ms_compute * 1e-3),
+                          "what": "decode + compaction + emission of the rank's views into its own cloud, no exchange"}
+    best = ("compute_only", ms_compute)
+    # the dominant kernel on this rank: the fused decode of its whole block of views in one launch
+    ms_dec = timed_steps(lambda: slb200.decode_pixels(frames, out=(bufs.h_idx, bufs.v_idx)), k=max(3, K // 2))
+    peak, peak_src = load_peaks()
+    algo = B * (N_FRAMES + 4) * W * H
+    c3["decode_roofline"] = {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": algo / (ms_dec * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": algo / (ms_dec * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "us_per_launch": ms_dec * 1e3,
+                             "timing": f"decode-only launch of the rank's {B} views ({B * N_FRAMES * W * H / 1e6:.0f} MB > L2), CUDA events, slowest rank"}
+    if world > 1:
+        total_pts = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(total_pts)
+        total_pts = int(total_pts.item())
+        c3["points_total"] = total_pts
+        cloud_bytes_in = (total_pts - n_local) * 16 if rank == 0 else 0
+        # ---- (a) peer-memory exchange fused into the emission, gather to rank 0
+        try:
+            ex = CloudExchange(max_scans=max(per_rank), max_width=W, max_points=VIEWS * H * W, gather_to=0)
+            ex_bufs = CloudBuffers.allocate(B, H, W, dev, cap_points=1)
+            ms_p2p = timed_steps(lambda: ex.scan_to_cloud(frames, white, calib, buffers=ex_bufs, calib_struct=cstruct, tables=tables))
+            base, total = ex.status()
+            ingress = (total - n_local) * 16
+            ok = (total == total_pts)
+            if rank == 0:
+                # the gathered cloud's first block is this rank's own cloud, bit for bit
+                ok = ok and torch.equal(ex.cloud[:n_local].view(torch.int32), bufs.cloud[:n_local].view(torch.int32))
+            c3["gather_p2p"] = {"ms_per_step": ms_p2p, "Mpx_per_s": VIEWS * MPX / (ms_p2p * 1e-3),
+                                "scans_per_s": VIEWS / (ms_p2p * 1e-3), "checked": bool(ok),
+                                "root_ingress_bytes": ingress, "root_ingress_gbs": ingress / (ms_p2p * 1e-3) / 1e9,
+                                "nvlink_bound_ms": ingress / 770e9 * 1e3,
+                                "what": "the same step with every rank's emit kernel writing its records straight into rank 0's packed "
+                                        "cloud over NVLink peer memory (counts exchanged on the device first); the step ends when all "
+                                        "records have landed on rank 0"}
+            if ok:
+                best = ("gather_p2p", ms_p2p)
+            # all-gather variant (every rank ends up with the whole cloud)
+            ex.close()
+            del ex, ex_bufs
+            ex = CloudExchange(max_scans=max(per_rank), max_width=W, max_points=VIEWS * H * W, gather_to="all")
+            ex_bufs = CloudBuffers.allocate(B, H, W, dev, cap_points=1)
+            ms_all = timed_steps(lambda: ex.scan_to_cloud(frames, white, calib, buffers=ex_bufs, calib_struct=cstruct, tables=tables))
+            ex.status()
+            c3["allgather_p2p"] = {"ms_per_step": ms_all, "Mpx_per_s": VIEWS * MPX / (ms_all * 1e-3),
+                                   "bus_gbs": (total_pts * 16) * (world - 1) / world / (ms_all * 1e-3) / 1e9,
+                                   "what": "every rank's emit kernel writes its records into ALL ranks' clouds"}
+            ex.close()
+            del ex, ex_bufs
+        except Exception as exc:                                   # keep the line: the NCCL gather below still measures the step
+            c3["gather_p2p"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        # ---- (b) the same step with the NCCL gather (grouped send/recv into a pre-sized cloud at final offsets)
+        out_cloud = torch.empty((total_pts, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+
+        def nccl_step():
+            slb200.scan_to_cloud(frames, white, calib, buffers=bufs, calib_struct=cstruct, tables=tables)
+            gather_clouds(bufs.cloud[:n_local], bufs.counts, dst=0, scans_per_rank=per_rank, out=out_cloud)
+        ms_nccl = timed_steps(nccl_step)
+        c3["gather_nccl"] = {"ms_per_step": ms_nccl, "Mpx_per_s": VIEWS * MPX / (ms_nccl * 1e-3),
+                             "root_ingress_gbs": (total_pts - n_local) * 16 / (ms_nccl * 1e-3) / 1e9 if rank == 0 else None,
+                             "what": "compute, then slb200.dist.gather_clouds(dst=0): all-gather of the counts, one host read of them, "
+                                     "grouped ncclSend/Recv of the records into rank 0's pre-sized cloud at their final offsets"}
+        if best[0] == "compute_only" or ms_nccl < best[1]:
+            best = ("gather_nccl", ms_nccl)
+        # ---- (c) the collective alone: all-gather-v of ONE scan's cloud per rank (29 MB), NCCL
+        one = bufs.cloud[: int(bufs.counts[0].item())]
+        one_counts = torch.stack([bufs.counts[0], bufs.counts[0]])
+        ag_out = torch.empty((world * H * W, 4), dtype=torch.float32, device=dev)
+        ms_ag = timed_steps(lambda: gather_clouds(one, one_counts, scans_per_rank=[1] * world, out=ag_out), k=10)
+        c3["allgather_nccl_one_scan"] = {"ms": ms_ag, "bytes_per_rank": int(one.shape[0]) * 16,
+                                         "bus_gbs": int(one.shape[0]) * 16 * (world - 1) / (ms_ag * 1e-3) / 1e9}
+        del out_cloud, ag_out
+    c3["step_variant"] = best[0]
+    c3["ms_per_step"] = best[1]
+    c3["Mpx_per_s"] = VIEWS * MPX / (best[1] * 1e-3)
+    c3["scans_per_s"] = VIEWS / (best[1] * 1e-3)
+    out["config3_64_views_by_scan"] = c3
+    del frames, white, bufs
+    torch.cuda.empty_cache()
+
+    # ================= config[2]: one 4K capture in row bands
+    W4, H4 = CAM_4K
+    n4 = 12
+    F4 = 4 * n4 + 2
+    calib4 = synth.synthetic_calibration(CAM_4K, PROJ_4K)
+    tables4 = slb200.LensTables(calib4, CAM_4K, dev)
+    y0, y1 = row_bands(H4, world)[rank]
+    ring4 = 3 if world == 1 else 4            # distinct captures: per rank 4 x (415 MB / world) of frames stay above L2 up to 8 ranks... see l2
+    pats4 = synth.pattern_stack(PROJ_4K, dev)
+    bands_f, bands_w = [], []
+    for i in range(ring4):
+        fr, wh = synth.render_scan(CAM_4K, PROJ_4K, seed=2000 + i, device=dev, patterns=pats4, calib=calib4)
+        bands_f.append(fr[:, y0:y1].contiguous()); bands_w.append(wh[y0:y1].contiguous())
+        del fr, wh
+    del pats4
+    torch.cuda.empty_cache()
+    Hb = y1 - y0
+    band_bytes = F4 * Hb * W4
+    c2 = {"capture": "3840x2160 camera, 3840x2160 projector, 12+12 bits, F = 50", "rows_this_rank": [y0, y1],
+          "l2": f"{ring4} distinct captures rotate; this rank's bands = {ring4 * band_bytes / 1e6:.0f} MB of frames"
+                + ("" if ring4 * band_bytes > 126e6 else " (below the 126 MB L2 at this rank count: band inputs are partly L2-resident)")}
+    b4 = [CloudBuffers.allocate(1, Hb, W4, dev) for _ in range(2)]
+    state = {"i": 0}
+
+    def band_local():
+        i = state["i"]; state["i"] += 1
+        slb200.scan_to_cloud(bands_f[i % ring4], bands_w[i % ring4], calib4, buffers=b4[i % 2], tables=tables4, row0=y0)
+    band_local()
+    torch.cuda.synchronize()
+    K4 = max(K, 12)
+    ms_c = timed_steps(band_local, k=K4)
+    mpx4 = W4 * H4 / 1e6
+    c2["compute_only"] = {"ms_per_step": ms_c, "Mpx_per_s": mpx4 / (ms_c * 1e-3),
+                          "what": "every rank decodes + compacts + emits its band into its own cloud, no exchange (single stream)"}
+    best = ("compute_only", ms_c)
+    if world > 1:
+        try:
+            ex = CloudExchange(max_scans=1, max_width=W4, max_points=H4 * W4, gather_to=0)
+            xb = [CloudBuffers.allocate(1, Hb, W4, dev, cap_points=1) for _ in range(2)]
+
+            def band_p2p():
+                i = state["i"]; state["i"] += 1
+                ex.band_to_cloud(bands_f[i % ring4], bands_w[i % ring4], calib4, row0=y0, buffers=xb[i % 2], tables=tables4)
+            ms_p = timed_steps(band_p2p, k=K4)
+            base, total = ex.status()
+            n_band = int(ex.counts_all[rank].item())
+            ingress = (total - n_band) * 16
+            c2["gather_p2p"] = {"ms_per_step": ms_p, "Mpx_per_s": mpx4 / (ms_p * 1e-3), "points_total": total,
+                                "root_ingress_bytes": ingress if rank == 0 else None,
+                                "root_ingress_gbs": ingress / (ms_p * 1e-3) / 1e9 if rank == 0 else None,
+                                "nvlink_bound_ms": ingress / 770e9 * 1e3 if rank == 0 else None,
+                                "what": "per-column counts of all bands exchanged on the device, every rank's emit kernel writes its runs "
+                                        "at their x-major position of the WHOLE image in rank 0's cloud over NVLink peer memory"}
+            best = ("gather_p2p", ms_p)
+            ex.close()
+            del ex, xb
+        except Exception as exc:
+            c2["gather_p2p"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    c2["step_variant"] = best[0]
+    c2["ms_per_step"] = best[1]
+    c2["Mpx_per_s"] = mpx4 / (best[1] * 1e-3)
+    out["config2_4k_row_bands"] = c2
+    out["steps"] = K
+    out["timing"] = "CUDA events around K steps on every rank after a barrier, MAX over ranks"
+    return out
+
+
+# --------------------------------------------------------------------------- N > 1
+def run_multi(args, torch, slb200, synth, dev, local, rank, world, dist):
+    W, H = CAM_SIZE
+    calib = synth.synthetic_calibration(CAM_SIZE, PROJ_SIZE)
+    tables = slb200.LensTables(calib, CAM_SIZE, dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    before = slb200.launch_count()
+    multi = multi_configs(args, torch, slb200, synth, dev, rank, world, dist, tables, calib)
+    launches = slb200.launch_count() - before
+    c3 = multi["config3_64_views_by_scan"]
+
+    # ---- e2e: every rank streams its own scans from pinned host memory through the C-ABI pipeline
+    e2e = None
+    if not args.no_e2e:
+        pats = synth.pattern_stack(PROJ_SIZE, dev)
+        rf, rw = [], []
+        for i in range(6):
+            fr, wh = synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=rank * 6 + i, device=dev, patterns=pats, calib=calib)
+            rf.append(fr); rw.append(wh)
+        del pats
+        e2e = e2e_pipeline(torch, slb200, dev, local, world, dist, calib, rf, rw, 24)
+        e2e["ceiling_gbs"] = pcie_ceiling(torch, dev, world, dist)
+        del rf, rw
+    clocks = sampler.stop()
+    if rank == 0:
+        K = multi["steps"]
+        line = {
+            "metric": METRIC, "value": c3["Mpx_per_s"], "unit": "Mpx/s",
+            "n_gpus": world, "steps": K, "warmup": max(3, min(args.warmup, 5)), "ms_per_step": c3["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD_MULTI, "frames_per_scan": N_FRAMES, "n_bits": N_BITS,
+                       "scans_per_step_per_gpu": c3["views_per_rank"], "step": "the whole 64-view batch: compute on every rank + gather on rank 0",
+                       "step_variant": c3["step_variant"], "triangulation_precision": "fp32", "lens": "tables",
+                       "parallelism": f"scan-sharded x{world}, clouds gathered on rank 0 (NVLink peer stores from the emit kernel, or NCCL send/recv)",
+                       "l2": c3["l2"],
+                       "single_gpu_reference": "bench.py --gpus 1 reports the same batch on one GPU under multi.config3_64_views_by_scan"},
+            "scans_per_s": c3["scans_per_s"],
+            "multi": multi, "e2e": e2e, "clocks": clocks,
+            "roofline": c3.get("decode_roofline"),
+            "nvlink": {"note": "with the gather in the step, the step is bound by rank 0's NVLink ingress (measured 770 GB/s per direction, "
+                               "B200_PROFILING.md): the compacted cloud of one 1080p scan is 29 MB and ONE GPU already emits clouds at ~0.9 TB/s",
+                       "achieved_gbs": (c3.get("gather_p2p") or {}).get("root_ingress_gbs"), "peak_gbs": 770.0,
+                       "frac": ((c3.get("gather_p2p") or {}).get("root_ingress_gbs") or 0.0) / 770.0},
+            "cpu_baseline": None,
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
     import torch
     import torch.distributed as dist
     import slb200
     from slb200 import synth
-    from slb200.api import CloudBuffers
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,224 +909,10 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     slb200.lib()                                           # fail loudly if the extension is missing
-    W, H = CAM_SIZE
-    K, Wm = args.steps, args.warmup
-    calib = synth.synthetic_calibration(CAM_SIZE, PROJ_SIZE)
-    cstruct = calib.struct()
-
-    # ---- synthetic inputs, resident in HBM: a ring of scans (different seeds per rank)
-    pats = synth.pattern_stack(PROJ_SIZE, dev)
-    ring_frames, ring_white = [], []
-    for i in range(RING):
-        fr, wh = synth.render_scan(CAM_SIZE, PROJ_SIZE, seed=rank * RING + i, device=dev, patterns=pats, calib=calib)
-        ring_frames.append(fr); ring_white.append(wh)
-    del pats
-    S = max(1, min(args.streams, RING))
-    # the persistent decode grid leaves a few SMs to the offsets / emit kernels of the scans in flight on the other
-    # streams (sl_set_decode_sm_reserve; launch geometry is fixed when the graphs below are captured)
-    sm_reserve = (8 if S > 1 else 0) if args.sm_reserve is None else max(0, args.sm_reserve)
-    slb200.set_decode_sm_reserve(sm_reserve)
-    bufsets = [CloudBuffers.allocate(1, H, W, dev) for _ in range(S)]
-    bufs = bufsets[0]
-    tables = None if args.lens == "iterate" else slb200.LensTables(calib, CAM_SIZE, dev)   # once per calibration
-    torch.cuda.synchronize()
-
-    def step(i, k):
-        slb200.scan_to_cloud(ring_frames[i % RING], ring_white[i % RING], calib, precision="fp32",
-                             buffers=bufsets[k], calib_struct=cstruct, tables=tables)
-
-    # One CUDA graph per ring slot (the 3 launches of a step replay without host launch latency); slot i
-    # always runs on stream i % S with that stream's buffers, so consecutive scans overlap: the small
-    # compaction / emit kernels of one scan run beside the decode of the next.
-    before = slb200.launch_count()
-    step(0, 0)
-    kernels_per_step = slb200.launch_count() - before
-    torch.cuda.synchronize()
-    streams = [torch.cuda.Stream(dev) for _ in range(S)]
-    graphs = []
-    for i in range(RING):
-        with torch.cuda.stream(streams[i % S]):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=streams[i % S]):
-                step(i, i % S)
-            graphs.append(g)
-    torch.cuda.synchronize()
-    main = torch.cuda.current_stream()
-
-    def replay(graph_list, n):
-        for i in range(n):
-            k = i % RING
-            with torch.cuda.stream(streams[k % S]):
-                graph_list[k].replay()
-
-    def timed(graph_list, n):
-        """n replays bracketed by CUDA events: the start event gates every stream, the end event waits for all."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(main)
-        for st in streams:
-            st.wait_event(e0)
-        replay(graph_list, n)
-        for st in streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main.wait_event(ev)
-        e1.record(main)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
-
-    sampler = ClockSampler(local)
-    sampler.start()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- timed region: EXACTLY K steps
-    replay(graphs, Wm)
-    barrier()
-    ms = torch.tensor([timed(graphs, K)], dtype=torch.float64, device=dev)
-    barrier()
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    valid_pts = int(bufs.counts[1].item())
-
-    # ---- roofline of the dominant kernel (fused decode): decode-only launches over the same ring, timed
-    # with CUDA events (a) in the configuration the step uses (pipelined over the S streams) and
-    # (b) isolated: back to back on one stream, every launch waiting for the previous one.
-    kr = max(60, min(K, 600))
-    dgraphs = []
-    for i in range(RING):
-        with torch.cuda.stream(streams[i % S]):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=streams[i % S]):
-                slb200.decode_pixels(ring_frames[i], out=(bufsets[i % S].h_idx[0], bufsets[i % S].v_idx[0]))
-            dgraphs.append(g)
-    torch.cuda.synchronize()
-    replay(dgraphs, 10)
-    torch.cuda.synchronize()
-    decode_ms = timed(dgraphs, kr) / kr
-    # (b) isolated: ONE graph holding RING decode launches in sequence on one stream (kernel after kernel, no
-    # overlap between launches; the graph only removes the host launch latency).  Nothing else runs, so the
-    # grid covers every SM.
-    slb200.set_decode_sm_reserve(0)
-    with torch.cuda.stream(streams[0]):
-        chain = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(chain, stream=streams[0]):
-            for i in range(RING):
-                slb200.decode_pixels(ring_frames[i], out=(bufs.h_idx[0], bufs.v_idx[0]))
-        chain.replay()
-        reps = max(3, kr // RING)
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(streams[0])
-        for _ in range(reps):
-            chain.replay()
-        d1.record(streams[0])
-    torch.cuda.synchronize()
-    decode_solo_ms = d0.elapsed_time(d1) / (reps * RING)
-    slb200.set_decode_sm_reserve(sm_reserve)
-    peak, peak_src = load_peaks()
-    algo_bytes = (N_FRAMES + 4) * W * H                      # F u8 reads + two int16 writes per pixel
-    achieved = algo_bytes / (decode_ms * 1e-3) / 1e9
-    achieved_solo = algo_bytes / (decode_solo_ms * 1e-3) / 1e9
-
-    # ---- e2e through the host-buffer C-ABI call: pinned host frames in, host cloud out
-    e2e = None
-    if not args.no_e2e:
-        eb = min(12, RING)                                   # distinct host scans (pinned), streamed round-robin
-        host_frames = torch.empty((eb, N_FRAMES, H, W), dtype=torch.uint8).pin_memory()
-        host_white = torch.empty((eb, H, W, 3), dtype=torch.uint8).pin_memory()
-        for i in range(eb):
-            host_frames[i].copy_(ring_frames[i]); host_white[i].copy_(ring_white[i])
-        pipe = slb200.Pipeline(N_FRAMES, H, W, max_batch=eb, device=local)
-        cloud_h = torch.empty((eb * H * W, 4), dtype=torch.float32).pin_memory()
-        cnt_h = torch.empty(eb + 1, dtype=torch.int64)
-        calls = max(2, min(5, (K + eb - 1) // eb))           # 24..60 scans streamed
-        # streaming form of the host API: one scan per call, copies and kernels of consecutive scans overlap on the
-        # pipeline's streams, flush() returns when every cloud is in host memory
-        cnts = [torch.zeros(1, dtype=torch.int64) for _ in range(eb)]
-        clouds = [cloud_h[i * H * W:(i + 1) * H * W] for i in range(eb)]
-
-        def stream_scans(n):
-            for j in range(n):
-                i = j % eb
-                pipe.submit(host_frames[i], host_white[i], calib, clouds[i], cnts[i])
-            pipe.flush()
-
-        stream_scans(eb)                                                                  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        stream_scans(calls * eb)
-        torch.cuda.synchronize()
-        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        cnt_h[eb] = sum(int(c) for c in cnts)
-        n_pts = int(cnt_h[eb])
-        e2e = {"value": world * calls * eb * MPX / float(el.item()), "unit": "Mpx/s",
-               "h2d_bytes_per_step": N_FRAMES * H * W + H * W * 3,
-               "d2h_bytes_per_step": int(n_pts / eb * 16 + 16),
-               "scans_per_call": 1, "distinct_host_scans": eb, "steps": calls * eb, "ms_per_scan": float(el.item()) / (calls * eb) * 1e3,
-               "api": "sl_pipeline_submit per scan + sl_pipeline_flush (slb200.Pipeline.submit / flush), pinned host buffers"}
-        pipe.close()
-
-    # ---- gather of the compacted clouds (the only collective on the path), timed separately
-    gather = None
-    if world > 1:
-        from slb200.dist import gather_clouds
-        cloud = bufs.cloud[:valid_pts]
-        gather_clouds(cloud, bufs.counts)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        reps = 5
-        for _ in range(reps):
-            out = gather_clouds(cloud, bufs.counts)
-        g1.record()
-        torch.cuda.synchronize()
-        gms = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gms.item()), "points_per_rank": valid_pts, "bytes_per_rank": valid_pts * 16,
-                  "what": "all-gather-v (NCCL) of one scan's compacted XYZRGB cloud (16 B records) per rank"}
-    clocks = sampler.stop()
-
-    # ---- CPU baseline (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_single_core(ring_frames[0].cpu().numpy(), ring_white[0].cpu().numpy(), calib)
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": world * K * MPX / (ms_total * 1e-3), "unit": "Mpx/s",
-            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_scan": N_FRAMES, "n_bits": N_BITS,
-                       "scans_per_step_per_gpu": 1, "valid_fraction": valid_pts / (W * H),
-                       "triangulation_precision": "fp32",
-                       "lens": ("exact fp64 ray tables built once per calibration (sl_lens_tables)" if tables is not None
-                                else "5 Brown-Conrady iterations per valid pixel in the emit kernel"),
-                       "parallelism": f"scan-sharded x{world}",
-                       "l2": f"inputs rotate over a ring of {RING} resident scans ({RING * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": f"CUDA graph per scan (decode, strip-prefix + column scan, emit: 3 kernels); independent scans pipelined over {S} CUDA streams",
-                       "decode_grid": f"one persistent CTA per SM, {sm_reserve} SMs left to the other streams' kernels"},
-            "scans_per_s": world * K / (ms_total * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "decode_tma_kernel<11>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_launch(),
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_launches.csv",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": decode_ms * 1e3,
-                         "frac_of_nominal_8000": achieved / 8000.0,
-                         "timing": f"{kr} decode-only launches over the ring, CUDA events, pipelined over {S} streams like the step",
-                         "isolated": {"us_per_launch": decode_solo_ms * 1e3, "achieved": achieved_solo,
-                                      "frac": achieved_solo / peak,
-                                      "timing": "the same launches strictly one after another on one stream (one CUDA graph of RING launches)"}},
-            "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "clocks": clocks,
-            "gpu_launches": int(K * kernels_per_step),
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
+    if world == 1:
+        run_single(args, torch, slb200, synth, dev, local)
+    else:
+        run_multi(args, torch, slb200, synth, dev, local, rank, world, dist)
         dist.barrier()
         dist.destroy_process_group()
 
@@ -463,16 +920,19 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lens", default="tables", choices=["tables", "iterate"])
     ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--sm-reserve", type=int, default=None,
                     help="SMs the decode grid leaves to the other streams' kernels (default: 8 when pipelining, else 0)")
     ap.add_argument("--ring", type=int, default=RING)
+    ap.add_argument("--multi-steps", type=int, default=20, help="timed steps of the multi-GPU configurations")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-multi", action="store_true")
+    ap.add_argument("--no-hard", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

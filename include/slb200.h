@@ -87,6 +87,12 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
                  size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
                  int8_t* v_codes, void* cloud_workspace, int sm_reserve, void* stream);
 
+/* sl_decode_u8 plus a diagnostic: stats (device u64 [2], zeroed by the call) receives the number of 4-pixel groups
+ * the byte-compare kernel decoded and how many of them needed the full evaluation of the four rules
+ * (decode_codes.py:172-182) instead of the single-threshold fast pass -- the kernel's input-dependent cost. */
+int sl_decode_u8_stats(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch, size_t scan_pitch,
+                       double eps, int16_t* h_idx, int16_t* v_idx, uint64_t* stats, void* stream);
+
 /* The same decode straight from the camera's 8-bit BGR frames: the capture loop's per-frame
  * cv2.cvtColor(frame, COLOR_BGR2GRAY) (src/3-capture_decode.py:66; gray = (3735 B + 19235 G + 9798 R + 16384) >> 15)
  * is applied while the frames stream through shared memory, so no gray stack is ever written or re-read.

@@ -201,6 +201,58 @@ def test_full_size_synthetic_scan_vs_oracle(T):
     assert err64.max() < 2e-7, err64.max()
 
 
+def _check_scan_against_oracle_bands(T, cam_size, proj_size, seed, band_rows):
+    """The GPU's full-scan result (fp32, lens tables: the benchmark's configuration) against the oracle run on
+    bands of rows: indices bit-exact, count / x-major order / colours exact, points < 1e-4 relative."""
+    import slb200
+    from slb200 import synth
+    W, H = cam_size
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    frames, white = synth.render_scan(cam_size, proj_size, seed=seed, device="cuda", calib=calib)
+    tables = slb200.LensTables(calib, cam_size, T.device("cuda", T.cuda.current_device()))
+    bufs = slb200.scan_to_cloud(frames, white, calib, precision="fp32", tables=tables)
+    n = int(bufs.counts[1])
+    gpu_h, gpu_v = bufs.h_idx[0].cpu().numpy(), bufs.v_idx[0].cpu().numpy()
+    cloud = bufs.cloud[:n].cpu().numpy()
+    xyz = cloud[:, :3].astype(np.float64)
+    rgb = cloud[:, 3].copy().view(np.uint8).reshape(-1, 4)[:, :3]
+    frames_np, white_np = frames.cpu().numpy(), white.cpu().numpy()
+    del frames, bufs, tables
+    T.cuda.empty_cache()
+    valid = (gpu_h != -1) & (gpu_v != -1)
+    assert int(valid.sum()) == n and n > 0.8 * W * H
+    order = (np.cumsum(valid.T.ravel()) - 1).reshape(W, H)      # x-major position of every valid pixel (triangulate.py:52-53)
+    worst, scale = 0.0, None
+    for y0 in range(0, H, band_rows):
+        y1 = min(H, y0 + band_rows)
+        hp, vp = O.decode_pixels(frames_np[:, y0:y1].astype(np.float64))
+        np.testing.assert_array_equal(gpu_h[y0:y1], hp)
+        np.testing.assert_array_equal(gpu_v[y0:y1], vp)
+        cam, proj, col = O.cam_proj_pairs(hp, vp, proj_size, white_np[y0:y1])
+        cam = cam + np.array([[0, y0]], dtype=cam.dtype)
+        pts = O.triangulate(cam, proj, calib.cam_mtx, calib.cam_dist, calib.proj_mtx, calib.proj_dist, calib.proj_R, calib.proj_T)
+        sel = order[:, y0:y1][valid.T[:, y0:y1]]
+        assert sel.size == pts.shape[1]
+        np.testing.assert_array_equal(rgb[sel], np.round(col * 255).astype(np.uint8))
+        if scale is None:
+            scale = float(np.abs(pts).max())
+        worst = max(worst, float(np.abs(xyz[sel] - pts.T).max()) / scale)
+    assert worst < 1e-4, worst      # tolerance (north_star): 1e-4 relative in fp32
+    return worst
+
+
+def test_bench_config1_1080p_scan_vs_oracle(T):
+    """BASELINE config[1], the benchmark's own workload (1920x1080 camera and projector, n = 11, synthetic plane)."""
+    worst = _check_scan_against_oracle_bands(T, (1920, 1080), (1920, 1080), seed=0, band_rows=135)
+    print(f"config[1] 1080p: max relative point error {worst:.2e}")
+
+
+def test_bench_config2_4k_scan_vs_oracle(T):
+    """BASELINE config[2]'s capture (3840x2160 camera and projector, n = 12, F = 50)."""
+    worst = _check_scan_against_oracle_bands(T, (3840, 2160), (3840, 2160), seed=2000, band_rows=120)
+    print(f"config[2] 4K: max relative point error {worst:.2e}")
+
+
 # ------------------------------------------------------------------ triangulation
 @pytest.mark.parametrize("name", ["a", "b", "c"])
 def test_pairs_and_triangulate_golden(T, golden_dir, name):
@@ -222,17 +274,23 @@ def test_pairs_and_triangulate_golden(T, golden_dir, name):
     if name != "c":      # case c evaluates the projector lens far outside its calibrated domain (chaotic in fp32)
         pts32 = slb200.triangulate_points(k("cam_full"), k("proj_pts"), calib, precision="fp32").cpu().numpy()
         rel = np.linalg.norm(pts32 - ref, axis=0) / np.linalg.norm(ref, axis=0)
-        # The golden pairs are RANDOM correspondences, so many ray pairs are nearly parallel and the
-        # triangle is ill-conditioned (error ~ eps_f32 / sin(gamma)).  The 1e-4 bound (north_star) is
-        # asserted where the intersection angle gamma exceeds 1 degree -- every pixel of a real scan
-        # (baseline 0.2 m at 0.9 m gives ~12 degrees); the rest must still agree to 1e-4 * 0.0175/sin(gamma).
+        # The golden pairs are RANDOM correspondences, so many ray pairs are nearly parallel and the triangle is
+        # ill-conditioned (error ~ eps_f32 / sin(gamma)).  Two stated bounds (north_star: "1e-4 relative in fp32 or
+        # ... a stated absolute tolerance in mm"):
+        #  (1) relative: < 1e-4 wherever the rays intersect at gamma > 1 degree -- every pixel of a real scan
+        #      (baseline 0.2 m at 0.9 m gives ~12 degrees);
+        #  (2) absolute: < 0.01 mm (measured 0.002 mm) for EVERY finite point within 2 m of the camera, ill-conditioned ones included
+        #      (the reference keeps only the +-0.5 m box, triangulate.py:119).
         xp = ref + g["T"]                                   # point seen from the projector
         sin_g = np.linalg.norm(np.cross(ref.T, xp.T), axis=1) / (np.linalg.norm(ref, axis=0) * np.linalg.norm(xp, axis=0))
         good = fin & (sin_g > 0.0175)
         assert good.sum() > 0.5 * fin.sum()
         assert rel[good].max() < 1e-4, rel[good].max()
-        rest = fin & ~good & (sin_g > 1e-4)
-        assert (rel[rest] * sin_g[rest]).max() < 1e-4 * 0.0175
+        near = fin & (np.linalg.norm(ref, axis=0) < 2.0)
+        abs_mm = np.linalg.norm(pts32 - ref, axis=0)[near] * 1e3
+        print(f"golden {name}: fp32 max rel (gamma > 1 deg) {rel[good].max():.2e}, max abs within 2 m {abs_mm.max():.2e} mm "
+              f"({int((near & ~good).sum())} ill-conditioned points among them)")
+        assert abs_mm.max() < 0.01, abs_mm.max()
 
 
 @pytest.mark.parametrize("thr,key", [(.5, "filt"), (1.25, "filt125")])
@@ -338,7 +396,7 @@ def test_row_band_sharding_matches_whole_image(T, world):
     cam_size, proj_size = (256, 200), (1024, 768)
     calib = synth.synthetic_calibration(cam_size, proj_size)
     frames, white = synth.render_scan(cam_size, proj_size, seed=8, device="cuda")
-    tables = slb200.LensTables(calib, cam_size, "cuda")
+    tables = slb200.LensTables(calib, cam_size, T.device("cuda", T.cuda.current_device()))
     for tab in (tables, None):
         whole = slb200.scan_to_cloud(frames, white, calib, tables=tab)
         n = int(whole.counts[1])
@@ -426,7 +484,7 @@ def test_pipeline_host_buffers(T):
     pipe = slb200.Pipeline(frames.shape[1], 200, 320, max_batch=5)
     h_idx = np.empty((5, 200, 320), np.int16); v_idx = np.empty((5, 200, 320), np.int16)
     cloud, counts = pipe.scan_to_cloud(frames, white, calib, h_idx=h_idx, v_idx=v_idx)
-    tables = slb200.LensTables(calib, cam_size, "cuda")      # the pipeline builds the same tables internally
+    tables = slb200.LensTables(calib, cam_size, T.device("cuda", T.cuda.current_device()))      # the pipeline builds the same tables internally
     dev = slb200.scan_to_cloud(frames.cuda(), white.cuda(), calib, tables=tables)
     n = int(dev.counts[-1])
     assert int(counts[-1]) == n and tuple(cloud.shape) == (n, 4)

@@ -1,12 +1,17 @@
-"""Two-rank NCCL run of both sharding modes (needs >= 2 GPUs; skipped otherwise):
-  * by scan: each rank processes its block of scans, all-gather-v of the packed clouds == single-GPU batch;
-  * by row band: each rank decodes + triangulates one band of the same capture, clouds and per-column counts
-    are gathered and merged back into the reference's x-major order == whole-image result."""
+"""Multi-rank runs on real GPUs (2, 4 and 8 ranks where the box has them; skipped below 2 GPUs) of both sharding
+modes, through both gathers:
+  * by scan: each rank processes its block of scans; the gathered cloud == the single-GPU batch, bit for bit
+      - CloudExchange (records emitted straight into the gathering rank's cloud over NVLink peer memory), gather to
+        rank 0 and all-gather, several steps in a row (the control blocks are double-buffered by step parity)
+      - gather_clouds over NCCL (all-gather and gather to rank 0)
+  * by row band: each rank decodes + triangulates one band of the same capture
+      - CloudExchange.band_to_cloud: per-column counts exchanged on the device, records land at their x-major
+        position of the whole image == whole-image result (incl. ranks whose band is empty)
+      - NCCL gather + merge_row_bands (the eager oracle of that placement)."""
 import os
 import socket
 import sys
 
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -27,63 +32,125 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     import slb200
     from slb200 import synth
-    from slb200.dist import gather_clouds, merge_row_bands, row_bands, shard_range
+    from slb200.dist import CloudExchange, gather_clouds, merge_row_bands, row_bands, shard_range
+    fails = []
+
+    def expect(cond, what):
+        if not bool(cond):
+            fails.append(what)
+
+    def same(a, b):
+        return a.shape == b.shape and torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
     cam_size, proj_size = (256, 200), (1024, 768)
+    W, H = cam_size
     calib = synth.synthetic_calibration(cam_size, proj_size)
     tables = slb200.LensTables(calib, cam_size, dev)
-    ok = True
-    # ---- by scan
-    n_scans = 5
-    scans = [synth.render_scan(cam_size, proj_size, seed=s, device="cpu") for s in range(n_scans)]
+    n_scans = 2 * world + 1                      # uneven blocks
+    scans = [synth.render_scan(cam_size, proj_size, seed=s, device="cpu") for s in range(n_scans + 2)]
+    per_rank = [shard_range(n_scans, r, world)[1] - shard_range(n_scans, r, world)[0] for r in range(world)]
     lo, hi = shard_range(n_scans, rank, world)
-    frames = torch.stack([scans[i][0] for i in range(lo, hi)]).to(dev)
-    white = torch.stack([scans[i][1] for i in range(lo, hi)]).to(dev)
-    mine = slb200.scan_to_cloud(frames, white, calib, tables=tables)
+
+    def batch(shift):                            # this rank's block / the whole batch, inputs rotated by `shift`
+        ids = [(i + shift) % len(scans) for i in range(n_scans)]
+        fr = torch.stack([scans[i][0] for i in ids]).to(dev)
+        wh = torch.stack([scans[i][1] for i in ids]).to(dev)
+        return fr, wh
+
+    # ---- by scan, peer-memory exchange: gather to rank 0, then all-gather; 3 steps each
+    for mode in (0, "all"):
+        ex = CloudExchange(max_scans=max(per_rank), max_width=W, max_points=n_scans * H * W, gather_to=mode)
+        for step in range(3):
+            fr, wh = batch(step)
+            ex.scan_to_cloud(fr[lo:hi].contiguous(), wh[lo:hi].contiguous(), calib, tables=tables)
+            torch.cuda.synchronize()
+            base, total = ex.status()
+            ref = slb200.scan_to_cloud(fr, wh, calib, tables=tables)
+            nr = int(ref.counts[-1])
+            expect(total == nr, f"exchange[{mode}] step {step}: total {total} != {nr}")
+            expect(base == int(ref.counts[:lo].sum()), f"exchange[{mode}] step {step}: rank base")
+            expect(torch.equal(ex.counts_all[: n_scans + 1], ref.counts), f"exchange[{mode}] step {step}: counts_all")
+            if ex.is_dst:
+                expect(same(ex.cloud[:nr], ref.cloud[:nr]), f"exchange[{mode}] step {step}: gathered cloud != single-GPU batch")
+            dist.barrier()                       # the reference run above must not overlap the next step's writes
+        ex.close()
+
+    # ---- by scan, NCCL
+    fr, wh = batch(0)
+    ref = slb200.scan_to_cloud(fr, wh, calib, tables=tables)
+    nr = int(ref.counts[-1])
+    mine = slb200.scan_to_cloud(fr[lo:hi].contiguous(), wh[lo:hi].contiguous(), calib, tables=tables)
     n = int(mine.counts[-1])
-    cloud_all, counts = gather_clouds(mine.cloud[:n], mine.counts)
-    if rank == 0:
-        ref = slb200.scan_to_cloud(torch.stack([s[0] for s in scans]).to(dev), torch.stack([s[1] for s in scans]).to(dev),
-                                   calib, tables=tables)
-        nr = int(ref.counts[-1])
-        ok &= cloud_all.shape[0] == nr and torch.equal(cloud_all.view(torch.int32), ref.cloud[:nr].view(torch.int32))
-        got = [int(c) for r in counts for c in r[:-1]]
-        ok &= got == [int(c) for c in ref.counts[:-1]]
+    for dst in (None, 0):
+        for spr in (None, per_rank):
+            cloud_all, counts = gather_clouds(mine.cloud[:n], mine.counts, dst=dst, scans_per_rank=spr)
+            got = [int(c) for r in counts for c in r[:-1]]
+            expect(got == [int(c) for c in ref.counts[:-1]], f"nccl dst={dst}: per-scan counts")
+            if dst is None or rank == dst:
+                expect(same(cloud_all, ref.cloud[:nr]), f"nccl dst={dst}: gathered cloud != single-GPU batch")
+            else:
+                expect(cloud_all is None, "non-receiving rank got a cloud")
+
     # ---- by row band
     frames1, white1 = scans[0][0].to(dev), scans[0][1].to(dev)
-    y0, y1 = row_bands(cam_size[1], world)[rank]
-    band = slb200.scan_to_cloud(frames1[:, y0:y1], white1[y0:y1].contiguous(), calib, tables=tables, row0=y0)
-    nb = int(band.counts[-1])
-    cols = band.column_counts()[0].to(torch.int64).contiguous()
+    whole = slb200.scan_to_cloud(frames1, white1, calib, tables=tables)
+    nw = int(whole.counts[-1])
+    y0, y1 = row_bands(H, world)[rank]
+    ex = CloudExchange(max_scans=1, max_width=W, max_points=H * W, gather_to=0)
+    for step in range(2):
+        ex.band_to_cloud(frames1[:, y0:y1], white1[y0:y1].contiguous(), calib, row0=y0, tables=tables)
+        torch.cuda.synchronize()
+        base, total = ex.status()
+        expect(total == nw, f"row bands step {step}: total {total} != {nw}")
+        if rank == 0:
+            expect(same(ex.cloud[:nw], whole.cloud[:nw]), f"row bands step {step}: placed cloud != whole-image cloud")
+            if step == 0:
+                ex.cloud.zero_()
+        dist.barrier()
+    ex.close()
+    # NCCL + eager merge (the oracle of the placement)
+    if y1 > y0:
+        band = slb200.scan_to_cloud(frames1[:, y0:y1], white1[y0:y1].contiguous(), calib, tables=tables, row0=y0)
+        nb = int(band.counts[-1])
+        cols = band.column_counts()[0].to(torch.int64).contiguous()
+        bcloud, bcounts = band.cloud[:nb], band.counts
+    else:
+        cols = torch.zeros(W, dtype=torch.int64, device=dev)
+        bcloud, bcounts = torch.zeros((0, 4), dtype=torch.float32, device=dev), torch.zeros(2, dtype=torch.int64, device=dev)
     all_cols = [torch.empty_like(cols) for _ in range(world)]
     dist.all_gather(all_cols, cols)
-    cloud_cat, _ = gather_clouds(band.cloud[:nb], band.counts)
+    cloud_cat, _ = gather_clouds(bcloud, bcounts)
     sizes = [int(c.sum()) for c in all_cols]
     parts, start = [], 0
     for s_ in sizes:
         parts.append(cloud_cat[start:start + s_]); start += s_
     merged = merge_row_bands(parts, all_cols)
-    if rank == 0:
-        whole = slb200.scan_to_cloud(frames1, white1, calib, tables=tables)
-        nw = int(whole.counts[-1])
-        ok &= merged.shape[0] == nw and torch.equal(merged.view(torch.int32), whole.cloud[:nw].view(torch.int32))
-    q.put((rank, bool(ok)))
+    expect(same(merged, whole.cloud[:nw]), "row bands over NCCL + merge_row_bands != whole-image cloud")
+
+    q.put((rank, fails))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_nccl_sharding():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_sharding(world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    try:
+        res = [q.get(timeout=600) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=120)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=120)
         assert p.exitcode == 0
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, []) for r in range(world)], res
