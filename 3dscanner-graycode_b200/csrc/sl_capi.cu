@@ -262,13 +262,15 @@ int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
                            (cudaStream_t)stream);
 }
 
-int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, int precision, float* cam_rays, float* proj_rays,
                    void* stream) {
   if (!calib || !cam_rays || !proj_rays) { set_error("null buffer"); return kErrBadArg; }
+  if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  if ((uintptr_t)cam_rays % 16 || (uintptr_t)proj_rays % 8) { set_error("cam_rays must be 16-byte aligned, proj_rays 8-byte"); return kErrBadArg; }
   if (cam_w < 1 || cam_h < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
   int sms = 0, rc;
   if ((rc = device_gate(&sms))) return rc;
-  return launch_lens_tables(*calib, cam_w, cam_h, cam_rays, proj_rays, (cudaStream_t)stream);
+  return launch_lens_tables(*calib, cam_w, cam_h, precision, cam_rays, proj_rays, (cudaStream_t)stream);
 }
 
 static int emit_cloud_checked(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
@@ -402,6 +404,7 @@ struct SlPipeline {
   int8_t* v_codes = nullptr;
   // lens tables of the last calibration seen (rebuilt when the calibration changes)
   SlCalib table_calib;
+  int table_precision = -1;
   bool have_tables = false;
   float* cam_rays = nullptr;
   float* proj_rays = nullptr;
@@ -469,6 +472,28 @@ int sl_pipeline_set_sm_reserve(SlPipeline* p, int sms) {
   return kOk;
 }
 
+// lens tables of the pipeline: (re)built when the calibration or the precision changes; all slots must be idle then
+static int pipeline_tables(SlPipeline* p, const SlCalib* calib, int precision) {
+  const size_t npix = (size_t)p->H * p->W;
+  if (calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad projector size"); return kErrBadArg; }
+  if (p->have_tables && p->table_precision == precision && memcmp(&p->table_calib, calib, sizeof(SlCalib)) == 0) return kOk;
+  for (auto& s : p->slot) SL_CUDA(cudaStreamSynchronize(s.stream));
+  const size_t pe = (size_t)calib->proj_w * calib->proj_h * 2;
+  if (!p->cam_rays) SL_CUDA(cudaMalloc(&p->cam_rays, npix * 2 * sizeof(float)));
+  if (pe > p->proj_rays_elems) {
+    cudaFree(p->proj_rays); p->proj_rays = nullptr; p->proj_rays_elems = 0;
+    SL_CUDA(cudaMalloc(&p->proj_rays, pe * sizeof(float)));
+    p->proj_rays_elems = pe;
+  }
+  const int trc = launch_lens_tables(*calib, p->W, p->H, precision, p->cam_rays, p->proj_rays, p->slot[0].stream);
+  if (trc) return trc;
+  SL_CUDA(cudaStreamSynchronize(p->slot[0].stream));
+  p->table_calib = *calib;
+  p->table_precision = precision;
+  p->have_tables = true;
+  return kOk;
+}
+
 // Scan i goes through slot i % kSlots: H2D -> decode -> offsets -> emit -> D2H(count).  The cloud
 // D2H needs the count (packed host output), so it is issued one step later, after the slot's
 // `counted` event, while the next scans' copies and kernels are already queued on other streams.
@@ -487,22 +512,9 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
   const size_t npix = (size_t)p->H * p->W;
   const size_t stack = (size_t)p->F * npix;
   const int S = SlPipeline::kSlots;
-  if (calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad projector size"); return kErrBadArg; }
-  if (!p->have_tables || memcmp(&p->table_calib, calib, sizeof(SlCalib)) != 0) {
-    // (re)build the lens tables for this calibration; all slots must be idle while they change
-    for (auto& s : p->slot) SL_CUDA(cudaStreamSynchronize(s.stream));
-    const size_t pe = (size_t)calib->proj_w * calib->proj_h * 2;
-    if (!p->cam_rays) SL_CUDA(cudaMalloc(&p->cam_rays, npix * 2 * sizeof(float)));
-    if (pe > p->proj_rays_elems) {
-      cudaFree(p->proj_rays); p->proj_rays = nullptr; p->proj_rays_elems = 0;
-      SL_CUDA(cudaMalloc(&p->proj_rays, pe * sizeof(float)));
-      p->proj_rays_elems = pe;
-    }
-    int trc = launch_lens_tables(*calib, p->W, p->H, p->cam_rays, p->proj_rays, p->slot[0].stream);
+  {
+    const int trc = pipeline_tables(p, calib, precision);
     if (trc) return trc;
-    SL_CUDA(cudaStreamSynchronize(p->slot[0].stream));
-    p->table_calib = *calib;
-    p->have_tables = true;
   }
   long long total = 0;
   bool overflow = false;
@@ -563,26 +575,6 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
 }
 
 // ---- streaming: scans are submitted one at a time and complete in the background ----------------------------
-static int pipeline_tables(SlPipeline* p, const SlCalib* calib) {
-  const size_t npix = (size_t)p->H * p->W;
-  if (calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad projector size"); return kErrBadArg; }
-  if (p->have_tables && memcmp(&p->table_calib, calib, sizeof(SlCalib)) == 0) return kOk;
-  for (auto& s : p->slot) SL_CUDA(cudaStreamSynchronize(s.stream));
-  const size_t pe = (size_t)calib->proj_w * calib->proj_h * 2;
-  if (!p->cam_rays) SL_CUDA(cudaMalloc(&p->cam_rays, npix * 2 * sizeof(float)));
-  if (pe > p->proj_rays_elems) {
-    cudaFree(p->proj_rays); p->proj_rays = nullptr; p->proj_rays_elems = 0;
-    SL_CUDA(cudaMalloc(&p->proj_rays, pe * sizeof(float)));
-    p->proj_rays_elems = pe;
-  }
-  const int trc = launch_lens_tables(*calib, p->W, p->H, p->cam_rays, p->proj_rays, p->slot[0].stream);
-  if (trc) return trc;
-  SL_CUDA(cudaStreamSynchronize(p->slot[0].stream));
-  p->table_calib = *calib;
-  p->have_tables = true;
-  return kOk;
-}
-
 // the scan occupying `s` is on its way out: its count is read, its cloud copy queued on the slot's stream
 static int pipeline_retire(SlPipeline* p, SlPipeline::Slot& s) {
   if (!s.pending) return kOk;
@@ -602,7 +594,7 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
   DeviceGuard guard;
   SL_CUDA(cudaSetDevice(p->device));
-  int rc = pipeline_tables(p, calib);
+  int rc = pipeline_tables(p, calib, precision);
   if (rc) return rc;
   const size_t npix = (size_t)p->H * p->W;
   const size_t stack = (size_t)p->F * npix;

@@ -396,24 +396,48 @@ __device__ __forceinline__ void rays_to_point_fp32(float cx, float cy, float px,
   X = cx * s; Y = cy * s; Z = s;
 }
 
+// The same point from the camera ray c = (cx, cy, 1) and the projector entry (bn, tp) = (|T x p|, T.p):
+//   |T x c|^2 = |T|^2 |c|^2 - (T.c)^2   (no cross product),   P = c * |T|^2 bn / (|T x c| tp - (T.c) bn)
+// 10 FFMA/FMUL + 2 MUFU per point.  The subtraction cancels only when the camera ray runs along the baseline, where the
+// triangle is degenerate anyway; measured against the fp64 reference on the synthetic scans: 5.0e-7 relative, the same
+// as the cross-product form.
+__device__ __forceinline__ void rays_to_point_fp32_bt(float cx, float cy, float bn, float tp, float t0, float t1,
+                                                      float t2, float t_len2, float& X, float& Y, float& Z) {
+  const float tc = fmaf(t0, cx, fmaf(t1, cy, t2));
+  const float c2 = fmaf(cx, cx, fmaf(cy, cy, 1.0f));
+  const float an = sqrt_approx(fmaf(t_len2, c2, -tc * tc));
+  const float s = t_len2 * bn * rcp_approx(fmaf(an, tp, -tc * bn));
+  X = cx * s; Y = cy * s; Z = s;
+}
+
 // Lens table: the undistorted, normalised ray of every lattice point (u, v) in [0,w) x [0,h),
 // computed ONCE per calibration with the exact fp64 iteration (bit-identical to
 // cv2.undistortPoints, triangulate.py:84-85).  The camera pixel grid and the projector pixel grid
 // never change between scans, so the per-scan kernels look the rays up instead of iterating.
+// BT: store (|T x p|, T.p) of the exact ray instead of the ray (projector table of the fp32 mode).
+template <bool BT>
 __global__ void __launch_bounds__(256) lens_table_kernel(const Lens<double> lens, int w, int h,
-                                                         float2* __restrict__ table) {
+                                                         float2* __restrict__ table, float t0, float t1, float t2) {
   const long long n = (long long)w * h;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const int y = (int)(i / w), x = (int)(i - (long long)y * w);
     float ox, oy;
     undistort_fp64((float)x, (float)y, lens, ox, oy);
-    table[i] = make_float2(ox, oy);
+    if (BT) {
+      const float bx = t1 - t2 * oy, by = t2 * ox - t0, bz = t0 * oy - t1 * ox;     // T x (px, py, 1)
+      table[i] = make_float2(sqrt_approx(bx * bx + by * by + bz * bz), t0 * ox + t1 * oy + t2);
+    } else {
+      table[i] = make_float2(ox, oy);
+    }
   }
 }
 
 // ------------------------------------------------------------------ K2 emit
-enum { kModePairs = 0, kModeCloud32 = 1, kModeCloud64 = 2, kModeTable32 = 3, kModeTable64 = 4 };
+enum { kModePairs = 0, kModeCloud32 = 1, kModeCloud64 = 2, kModeTable64 = 4, kModeTableBT32 = 5 };
+// kModeTableBT32 is the throughput path: the projector table holds, per panel pixel, (|T x p|, T.p) of its exact ray p --
+// everything the fp32 formula needs from the projector side (sl_lens_tables with SL_PREC_FP32); kModeTable64 looks the
+// exact rays themselves up and mirrors the reference's dtype flow (tables built with SL_PREC_FP64).
 
 struct EmitArgs {
   const int16_t* h;
@@ -480,7 +504,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
   const size_t cell = ((size_t)b * a.bands + band) * a.W + x0;       // (scan, band, column x0)
   const bool has_rgb = a.white != nullptr;
   const bool vec = ((a.W & 3) == 0) && cols == kEmitCols && a.aligned;
-  constexpr bool kTable = (MODE == kModeTable32 || MODE == kModeTable64);
+  constexpr bool kTable = (MODE == kModeTable64 || MODE == kModeTableBT32);
 
   // lane c <-> column x0+c: packed output offset of the column's first point in this band, and its bits
   long long my_base = 0;
@@ -506,8 +530,8 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
       double dx, dy, dz;
       triangulate_fp64(u, w, (float)hc, (float)vc, a.cal, dx, dy, dz);
       X = (float)dx; Y = (float)dy; Z = (float)dz;
-    } else if (MODE == kModeTable32) {
-      rays_to_point_fp32(cray.x, cray.y, pray.x, pray.y, a.cal, X, Y, Z);
+    } else if (MODE == kModeTableBT32) {
+      rays_to_point_fp32_bt(cray.x, cray.y, pray.x, pray.y, a.cal.Tf[0], a.cal.Tf[1], a.cal.Tf[2], a.cal.t_len2f, X, Y, Z);
     } else {
       double dx, dy, dz;
       rays_to_point_fp64(cray.x, cray.y, pray.x, pray.y, a.cal, dx, dy, dz);
@@ -521,7 +545,72 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
   // L2 policy: the lens tables are re-read by every scan (keep them: evict_last); indices, colours and
   // the cloud stream through once (evict_first)
   const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
-  if (vec) {
+  if (MODE == kModeTableBT32 && vec) {
+    // Throughput path.  Everything per pixel is straight-line code: packed 16-bit clamps, the gathers predicated on the
+    // validity bit, the 12-instruction point formula evaluated for all 16 pixels of the lane (no branch per pixel; an
+    // invalid pixel computes garbage that is never stored), one predicated 16-byte shared-memory store per pixel.
+    const float t0 = a.cal.Tf[0], t1 = a.cal.Tf[1], t2 = a.cal.Tf[2], tl2 = a.cal.t_len2f;
+    const uint32_t pw1 = (uint32_t)(a.cal.proj_w - 1), ph1 = (uint32_t)(a.cal.proj_h - 1);
+    const uint32_t pwx2 = pw1 | (pw1 << 16), phx2 = ph1 | (ph1 << 16);
+    const uint32_t pw = (uint32_t)a.cal.proj_w;
+    uint32_t cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
+    const uint32_t rec_base = smem_u32(&tile.rec[c4 * kRunPitch]);
+#pragma unroll 1
+    for (int it0 = 0; it0 < 4; it0 += kEmitGroup) {
+      uint2 h2[kEmitGroup], v2[kEmitGroup];
+      uint32_t w0[kEmitGroup], w1[kEmitGroup], w2[kEmitGroup];
+      float4 r0[kEmitGroup], r1[kEmitGroup];
+#pragma unroll
+      for (int j = 0; j < kEmitGroup; ++j) {
+        const int r = min(rr + 8 * (it0 + j), rows - 1);        // rows past the image repeat the last one (never valid)
+        const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+        h2[j] = ldg_u2_hint(a.h + g, stream);
+        v2[j] = ldg_u2_hint(a.v + g, stream);
+        if (has_rgb) {
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);      // 12 bytes = 4 RGB pixels
+          w0[j] = ldg_u32_hint(wp, stream); w1[j] = ldg_u32_hint(wp + 1, stream); w2[j] = ldg_u32_hint(wp + 2, stream);
+        } else {
+          w0[j] = w1[j] = w2[j] = 0;
+        }
+        const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
+        r0[j] = ldg_f4_hint(rp, keep); r1[j] = ldg_f4_hint(rp + 1, keep);
+      }
+      float2 bt[kEmitGroup][4];
+#pragma unroll
+      for (int j = 0; j < kEmitGroup; ++j) {
+        const int r = rr + 8 * (it0 + j);
+        // triangulate.py:60-61: min(proj_w - 1, h), min(proj_h - 1, v) on both 16-bit halves at once (-1 = 0xffff clamps too)
+        const uint32_t hx = __vminu2(h2[j].x, pwx2), hy = __vminu2(h2[j].y, pwx2);
+        const uint32_t vx = __vminu2(v2[j].x, phx2), vy = __vminu2(v2[j].y, phx2);
+        const uint32_t idx[4] = {(vx & 0xffffu) * pw + (hx & 0xffffu), (vx >> 16) * pw + (hx >> 16),
+                                 (vy & 0xffffu) * pw + (hy & 0xffffu), (vy >> 16) * pw + (hy >> 16)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          bt[j][k] = make_float2(0.f, 0.f);
+          if ((cb[k] >> r) & 1u) bt[j][k] = ldg_f2_hint(a.proj_rays + idx[k], keep);        // triangulate.py:56
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kEmitGroup; ++j) {
+        const int r = rr + 8 * (it0 + j);
+        const uint32_t below = (1u << r) - 1u;
+        const uint32_t col[4] = {w0[j] & 0xffffffu, (w0[j] >> 24) | ((w1[j] & 0xffffu) << 8),
+                                 (w1[j] >> 16) | ((w2[j] & 0xffu) << 16), w2[j] >> 8};   // triangulate.py:64
+        const float cx[4] = {r0[j].x, r0[j].z, r1[j].x, r1[j].z}, cy[4] = {r0[j].y, r0[j].w, r1[j].y, r1[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float X, Y, Z;
+          rays_to_point_fp32_bt(cx[k], cy[k], bt[j][k].x, bt[j][k].y, t0, t1, t2, tl2, X, Y, Z);
+          if ((cb[k] >> r) & 1u) {
+            const uint32_t slot = rec_base + (uint32_t)(k * kRunPitch + __popc(cb[k] & below)) * 16u;
+            sts_u4(slot, __float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), col[k]);
+          }
+        }
+      }
+    }
+  } else if (vec) {
     uint32_t cb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
@@ -792,7 +881,7 @@ int cloud_device_init() {
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModePairs>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
-  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTableBT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   return kOk;
 }
@@ -832,14 +921,19 @@ int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, 
   return kOk;
 }
 
-int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, int precision, float* cam_rays, float* proj_table,
                        cudaStream_t st) {
   const CalibDev cal = make_calib(calib);
   auto blocks = [](long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); };
-  lens_table_kernel<<<blocks((long long)cam_w * cam_h), 256, 0, st>>>(cal.cam_d, cam_w, cam_h, (float2*)cam_rays);
+  lens_table_kernel<false><<<blocks((long long)cam_w * cam_h), 256, 0, st>>>(cal.cam_d, cam_w, cam_h, (float2*)cam_rays,
+                                                                             0.f, 0.f, 0.f);
   count_launch();
-  lens_table_kernel<<<blocks((long long)cal.proj_w * cal.proj_h), 256, 0, st>>>(cal.proj_d, cal.proj_w, cal.proj_h,
-                                                                               (float2*)proj_rays);
+  const int pb = blocks((long long)cal.proj_w * cal.proj_h);
+  if (precision == SL_PREC_FP64)
+    lens_table_kernel<false><<<pb, 256, 0, st>>>(cal.proj_d, cal.proj_w, cal.proj_h, (float2*)proj_table, 0.f, 0.f, 0.f);
+  else
+    lens_table_kernel<true><<<pb, 256, 0, st>>>(cal.proj_d, cal.proj_w, cal.proj_h, (float2*)proj_table, cal.Tf[0],
+                                                cal.Tf[1], cal.Tf[2]);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
@@ -862,7 +956,7 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   if (rc) return rc;
   if (cam_rays) {
     if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmemCloud, st>>>(a);
-    else SL_CUDA(launch_stage2(emit_kernel<kModeTable32>, g, thr, (size_t)kEmitSmemCloud, st, a));
+    else SL_CUDA(launch_stage2(emit_kernel<kModeTableBT32>, g, thr, (size_t)kEmitSmemCloud, st, a));
   } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmemCloud, st>>>(a);
   else emit_kernel<kModeCloud32><<<g, thr, kEmitSmemCloud, st>>>(a);
   count_launch();

@@ -53,7 +53,7 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
 uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned int** ticket);
 int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
                       int proj_w, int proj_h, const void* ws, float* pairs, uint32_t* rgb32, cudaStream_t st);
-int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, int precision, float* cam_rays, float* proj_table,
                        cudaStream_t st);
 int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
                       int precision, const float* cam_rays, const float* proj_rays, int B, int H, int W,

@@ -52,7 +52,7 @@ SIGNATURES = {
     "sl_compact_offsets_decoded": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "sl_workspace_col_totals": (_vp, [_vp, _i, _i, _i]),
     "sl_emit_pairs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _vp, _vp, _vp]),
+    "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _i, _vp, _vp, _vp]),
     "sl_emit_cloud": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sl_decode_triangulate_fused": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _d, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _vp, _vp,
                                          _vp, _vp, _vp, _i, _vp]),

@@ -575,17 +575,32 @@ class CloudBuffers:
 
 class LensTables:
     """Undistorted rays of the camera and projector pixel lattices for one calibration
-    (``sl_lens_tables``); build once, reuse for every scan."""
+    (``sl_lens_tables``); build once, reuse for every scan.  ``cam``: the camera rays (rotated by R);
+    ``proj``: the exact projector rays (what the fp64 mode looks up); ``proj_bt``: ``(|T x p|, T.p)`` of those rays
+    (what the fp32 mode looks up).  ``precision`` restricts the build to one mode's projector table."""
 
-    def __init__(self, calib: Calibration, cam_size: Tuple[int, int], device):
+    def __init__(self, calib: Calibration, cam_size: Tuple[int, int], device, precision=None):
         w, h = int(cam_size[0]), int(cam_size[1])
         pw, ph = calib.proj_size
         self.cam_size, self.proj_size = (w, h), (pw, ph)
         self.cam = torch.empty((h, w, 2), dtype=torch.float32, device=device)
-        self.proj = torch.empty((ph, pw, 2), dtype=torch.float32, device=device)
+        self.proj = self.proj_bt = None
         s = calib.struct()
+        want = (SL_PREC_FP64, SL_PREC_FP32) if precision is None else (_PREC[precision],)
         with torch.cuda.device(device):
-            check(lib().sl_lens_tables(C.byref(s), w, h, _ptr(self.cam), _ptr(self.proj), _stream()))
+            for prec in want:
+                t = torch.empty((ph, pw, 2), dtype=torch.float32, device=device)
+                check(lib().sl_lens_tables(C.byref(s), w, h, prec, _ptr(self.cam), _ptr(t), _stream()))
+                if prec == SL_PREC_FP64:
+                    self.proj = t
+                else:
+                    self.proj_bt = t
+
+    def projector_table(self, precision) -> torch.Tensor:
+        t = self.proj if _PREC[precision] == SL_PREC_FP64 else self.proj_bt
+        if t is None:
+            raise ValueError("lens tables were built for the other triangulation precision")
+        return t
 
 
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
@@ -637,7 +652,7 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     L = lib()
     st = _stream()
     cam_t = _ptr(tables.cam) if tables is not None else None
-    proj_t = _ptr(tables.proj) if tables is not None else None
+    proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
     with torch.cuda.device(dev):
         if bgr:
             check(L.sl_decode_bgr_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),

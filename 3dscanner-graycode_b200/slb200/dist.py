@@ -275,7 +275,7 @@ class CloudExchange:
         from ._lib import check, lib
         from .api import _PREC, _ptr, _stream
         cam_t = _ptr(tables.cam) if tables is not None else None
-        proj_t = _ptr(tables.proj) if tables is not None else None
+        proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
         check(lib().sl_emit_cloud_multi(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
                                         _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), self._clouds_c,
                                         len(self._cloud_ptr_list), self.max_points, _stream()))

@@ -551,7 +551,7 @@ def run_single(args, torch, slb200, synth, dev, local):
 
     def emit_fn(b, wh, t):
         return lambda: check(L.sl_emit_cloud(_ptr(b.h_idx), _ptr(b.v_idx), _ptr(wh), C.byref(cstruct), _PREC["fp32"],
-                                             _ptr(t.cam) if t is not None else None, _ptr(t.proj) if t is not None else None,
+                                             _ptr(t.cam) if t is not None else None, _ptr(t.proj_bt) if t is not None else None,
                                              1, H, W, _ptr(b.ws), _ptr(b.cloud), _stream()))
     off_us = chain_us(torch, ring.streams[0], [offsets_fn(b) for b, _ in stage_sets], 20)
     emit_us = chain_us(torch, ring.streams[0], [emit_fn(b, wh, tables) for b, wh in stage_sets], 20)

@@ -167,14 +167,18 @@ int sl_emit_pairs(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* whi
 /* Lens tables: the undistorted normalised ray of every camera pixel (rotated by R) and of every
  * projector pixel -- cv2.undistortPoints (triangulate.py:84-85: 5 Brown-Conrady fixed-point
  * iterations, fp64 arithmetic, f32 result) evaluated once per calibration on the two pixel
- * lattices, which never change between scans.  cam_rays device f32 [cam_h][cam_w][2],
- * proj_rays device f32 [proj_h][proj_w][2]. */
-int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, float* cam_rays, float* proj_rays,
+ * lattices, which never change between scans.  cam_rays device f32 [cam_h][cam_w][2] (16-byte aligned);
+ * proj_table device f32 [proj_h][proj_w][2] (8-byte aligned), its content depends on `precision`:
+ *   SL_PREC_FP64  the exact ray (x, y) of the panel pixel -- the fp64 mode mirrors the reference's dtype flow from it;
+ *   SL_PREC_FP32  (|T x p|, T.p) of that exact ray p = (x, y, 1): all the fp32 point formula needs from the projector
+ *                 side, so the per-point arithmetic is 12 instructions.
+ * sl_emit_cloud must be given tables built with the precision it is called with. */
+int sl_lens_tables(const SlCalib* calib, int cam_w, int cam_h, int precision, float* cam_rays, float* proj_table,
                    void* stream);
 
 /* Fused get_cam_proj_pts + triangulate (triangulate.py:39-97): undistortion of both sides,
  * law-of-sines depth, ordered compaction.  With cam_rays/proj_rays (from sl_lens_tables, same
- * calibration and sizes) the rays are looked up; with both NULL the 5 Brown-Conrady iterations
+ * calibration, sizes and precision) the rays are looked up; with both NULL the 5 Brown-Conrady iterations
  * run in the kernel for every valid pixel (fp32 or fp64 per `precision`).
  * cloud (N,4) f32: one 16-byte XYZRGB record per point = [x, y, z, bits(R | G<<8 | B<<16)] (the
  * layout PCL calls PointXYZRGB; colour word 0 when white_rgb is NULL), packed over the batch, each

@@ -19,7 +19,7 @@ for i in range(a.ring):
 torch.cuda.synchronize()
 s = calib.struct(); L = lib(); H, W = cam[1], cam[0]
 def offsets(b): check(L.sl_compact_offsets_decoded(1, H, W, _ptr(b.ws), _ptr(b.counts), _stream()))
-def emit(b, wh): check(L.sl_emit_cloud(_ptr(b.h_idx), _ptr(b.v_idx), _ptr(wh), C.byref(s), 0, _ptr(tables.cam), _ptr(tables.proj), 1, H, W, _ptr(b.ws), _ptr(b.cloud), _stream()))
+def emit(b, wh): check(L.sl_emit_cloud(_ptr(b.h_idx), _ptr(b.v_idx), _ptr(wh), C.byref(s), 0, _ptr(tables.cam), _ptr(tables.proj_bt), 1, H, W, _ptr(b.ws), _ptr(b.cloud), _stream()))
 def timeit(fn, name):
     sts = [torch.cuda.Stream(dev) for _ in range(a.streams)]; graphs = []
     for i, (b, wh) in enumerate(sets):
