@@ -107,12 +107,13 @@ int sl_decode_u8(const uint8_t* frames, int B, int F, int H, int W, size_t frame
   int sms = 0;
   if ((rc = device_gate(&sms))) return rc;
   uint32_t* bitmap = nullptr;
-  unsigned int* ticket = nullptr;
+  unsigned long long* flags = nullptr;
+  int n_flags = 0;
   long long words = 0;
-  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &ticket);
+  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &flags, &n_flags);
   if (sm_reserve < 0) { set_error("sm_reserve must be >= 0"); return kErrBadArg; }
   return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, h_codes, v_codes,
-                       bitmap, words, ticket, sms, (cudaStream_t)stream, false, sm_reserve);
+                       bitmap, words, flags, n_flags, sms, (cudaStream_t)stream, false, sm_reserve);
 }
 
 int sl_decode_u8_stats(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch, size_t scan_pitch,
@@ -128,7 +129,7 @@ int sl_decode_u8_stats(const uint8_t* frames, int B, int F, int H, int W, size_t
   if ((rc = device_gate(&sms))) return rc;
   SL_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), (cudaStream_t)stream));
   return launch_decode(frames, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr, nullptr, 0,
-                       nullptr, sms, (cudaStream_t)stream, false, 0, (unsigned long long*)stats);
+                       nullptr, 0, sms, (cudaStream_t)stream, false, 0, (unsigned long long*)stats);
 }
 
 int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size_t frame_pitch,
@@ -145,11 +146,12 @@ int sl_decode_bgr_u8(const uint8_t* frames_bgr, int B, int F, int H, int W, size
   int sms = 0;
   if ((rc = device_gate(&sms))) return rc;
   uint32_t* bitmap = nullptr;
-  unsigned int* ticket = nullptr;
+  unsigned long long* flags = nullptr;
+  int n_flags = 0;
   long long words = 0;
-  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &ticket);
+  if (cloud_workspace) bitmap = workspace_bitmap(cloud_workspace, B, H, W, &words, &flags, &n_flags);
   return launch_decode(frames_bgr, B, F, npix, frame_pitch, scan_pitch, eps, h_idx, v_idx, nullptr, nullptr,
-                       bitmap, words, ticket, sms, (cudaStream_t)stream, true, sm_reserve);
+                       bitmap, words, flags, n_flags, sms, (cudaStream_t)stream, true, sm_reserve);
 }
 
 int sl_direct_indirect(const uint8_t* frames, int F, int H, int W, size_t frame_pitch, double* L_d,
@@ -543,10 +545,11 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     if (white_rgb_host)
       SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host + (size_t)i * npix * 3, npix * 3, cudaMemcpyHostToDevice, s.stream));
     long long bm_words = 0;
-    unsigned int* ticket = nullptr;
-    uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &ticket);
+    unsigned long long* flags = nullptr;
+    int n_flags = 0;
+    uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &flags, &n_flags);
     rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
-                       ticket, p->sms, s.stream, false, p->sm_reserve);
+                       flags, n_flags, p->sms, s.stream, false, p->sm_reserve);
     if (rc) break;
     if (h_idx_host) {
       SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, s.h, npix * 2, cudaMemcpyDeviceToHost, s.stream));
@@ -603,10 +606,11 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
   SL_CUDA(cudaMemcpyAsync(s.frames, frames_host, stack, cudaMemcpyHostToDevice, s.stream));
   if (white_rgb_host) SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host, npix * 3, cudaMemcpyHostToDevice, s.stream));
   long long bm_words = 0;
-  unsigned int* ticket = nullptr;
-  uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &ticket);
+  unsigned long long* flags = nullptr;
+  int n_flags = 0;
+  uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &flags, &n_flags);
   if ((rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
-                          ticket, p->sms, s.stream, false, p->sm_reserve))) return rc;
+                          flags, n_flags, p->sms, s.stream, false, p->sm_reserve))) return rc;
   if ((rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream))) return rc;
   SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
   if ((rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
@@ -664,7 +668,7 @@ int sl_decode_host(SlPipeline* p, const uint8_t* frames_host, int B, double eps,
     auto& u = h_codes_host ? p->slot[0] : s;
     SL_CUDA(cudaMemcpyAsync(u.frames, frames_host + (size_t)i * stack, stack, cudaMemcpyHostToDevice, st));
     rc = launch_decode(u.frames, 1, p->F, (long long)npix, npix, stack, eps, u.h, u.v,
-                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, nullptr, 0, nullptr,
+                       h_codes_host ? p->h_codes : nullptr, h_codes_host ? p->v_codes : nullptr, nullptr, 0, nullptr, 0,
                        p->sms, st, false, p->sm_reserve);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(h_idx_host + (size_t)i * npix, u.h, npix * 2, cudaMemcpyDeviceToHost, st));

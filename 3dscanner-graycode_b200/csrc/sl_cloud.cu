@@ -37,6 +37,8 @@ constexpr int kEmitWarps = SL_EMIT_WARPS;
 // ------------------------------------------------------------------ workspace
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static size_t strips_of(int W) { return (size_t)(W + 31) / 32; }      // kStripCols = 32
+
 static size_t bitmap_words(long long npix) { return (size_t)((npix + 31) / 32) + 1; }   // +1: funnel reads
 
 size_t cloud_workspace_bytes(int B, int H, int W) {
@@ -46,7 +48,7 @@ size_t cloud_workspace_bytes(int B, int H, int W) {
          align_up((size_t)B * bands * W * 4, 256) +                            // col_bits
          align_up((size_t)B * W * 4, 256) +                                    // col_tot
          align_up((size_t)B * W * 8, 256) +                                    // col_base
-         256;                                                                  // ticket of the strip kernel
+         align_up((size_t)B * (strips_of(W) + 1) * 8, 256);                    // published strip / scan totals
 }
 
 CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
@@ -64,7 +66,8 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W) {
   p += align_up((size_t)B * W * 4, 256);
   c.col_base = reinterpret_cast<long long*>(p);
   p += align_up((size_t)B * W * 8, 256);
-  c.ticket = reinterpret_cast<unsigned int*>(p);
+  c.flags = reinterpret_cast<unsigned long long*>(p);
+  c.n_flags = (int)((size_t)B * (strips_of(W) + 1));
   return c;
 }
 
@@ -75,8 +78,9 @@ __global__ void __launch_bounds__(256) bitmap_from_idx_kernel(const int16_t* __r
                                                                const int16_t* __restrict__ v, long long npix,
                                                                long long words_per_scan, int B,
                                                                uint32_t* __restrict__ bitmap,
-                                                               unsigned int* __restrict__ ticket) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0;      // arms the strip kernel's last-CTA election
+                                                               unsigned long long* __restrict__ flags, int n_flags) {
+  if (blockIdx.x == 0)                                        // the offsets kernel's published totals start out empty
+    for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0;
   const long long padded = (npix + 31) & ~31LL;
   const long long total = padded * B;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -155,14 +159,34 @@ __global__ void __launch_bounds__(1024) colscan_kernel(const uint32_t* __restric
   block_scan_columns<1024>(vals, out, m, B, W, counts);
 }
 
-// K3b (+K3c): one CTA per strip of 32 columns, one warp per band (round-robin).  Lane r fetches the 32
+// K3b: one CTA per strip of 32 columns, one warp per band (round-robin).  Lane r fetches the 32
 // validity bits of row (band*32 + r) in the strip (funnel shift out of the flat bitmap); 32 ballots
 // transpose the 32x32 bit block so lane c holds the column word of column x0+c, whose popcount is
 // the number of valid pixels of that column in the band.  The counts meet in shared memory, are
-// prefixed down each column, and leave as band_pre[b][band][x] (exclusive) and col_tot[b][x]; the
-// column words themselves are kept (col_bits) -- the emit kernel ranks pixels with them.
+// prefixed down each column (one warp scan per column, lanes = bands), and leave as band_pre[b][band][x]
+// (exclusive) and col_tot[b][x]; the column words themselves are kept (col_bits) -- the emit kernel ranks pixels
+// with them.
+// K3c, the packed base of every column (scan-major, then x-major), needs the totals of everything before the strip.
+// No second kernel, no last-CTA pass: every CTA publishes its strip total (a 64-bit word: valid bit + value, release
+// store), then sums the published totals of the lower strips of its scan and the published totals of the lower scans
+// (each scan's last strip publishes the scan total), spinning on words that are not there yet.  A CTA only ever
+// waits for CTAs with a lower block index, which the hardware dispatches first, so the waits always end; the words are
+// zeroed by the kernel that produced the bitmap (decode / bitmap_from_idx), which precedes this one in stream order.
 constexpr int kStripWarps = 16;
 constexpr int kMaxBands = 1024;      // H <= 32768
+constexpr int kCntPitch = 33;        // shared counts [band][33]: the column-wise scans read it conflict-free
+constexpr unsigned long long kFlagValid = 1ull << 63;
+
+__device__ __forceinline__ void publish_total(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v | kFlagValid) : "memory");
+}
+__device__ __forceinline__ unsigned long long await_total(const unsigned long long* p) {
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  } while (!(v & kFlagValid));
+  return v & ~kFlagValid;
+}
 
 __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const uint32_t* __restrict__ bitmap,
                                                                          long long words_per_scan, int H, int W,
@@ -172,8 +196,11 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
                                                                          uint32_t* __restrict__ col_tot,
                                                                          long long* __restrict__ col_base, int B,
                                                                          long long* __restrict__ counts,
-                                                                         unsigned int* __restrict__ ticket) {
-  extern __shared__ uint32_t cnt[];            // [bands][32] counts, then exclusive prefixes
+                                                                         unsigned long long* __restrict__ flags) {
+  extern __shared__ uint32_t cnt[];            // [bands][kCntPitch] counts, then exclusive prefixes
+  __shared__ uint32_t tot_s[kStripCols];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = strip * kStripCols, x = x0 + lane;
@@ -203,38 +230,66 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
         const uint32_t bits = __ballot_sync(0xffffffffu, (rowword >> c) & 1u);
         if (lane == c) colword = bits;
       }
-      cnt[band * 32 + lane] = __popc(colword);
+      cnt[band * kCntPitch + lane] = __popc(colword);
       if (x < W) col_bits[((size_t)b * bands + band) * W + x] = colword;    // bit r = pixel (band*32+r, x) valid
     }
   }
   __syncthreads();
-  if (warp == 0) {                              // prefix down the column (bands <= ~70 in practice)
-    uint32_t run = 0;
-    for (int band = 0; band < bands; ++band) {
-      const uint32_t c = cnt[band * 32 + lane];
-      cnt[band * 32 + lane] = run;
-      run += c;
+  // prefix down each column: warp w takes columns 2w and 2w + 1, lane = band (32 bands per pass)
+#pragma unroll
+  for (int cc = 0; cc < kStripCols / kStripWarps; ++cc) {
+    const int c = warp * (kStripCols / kStripWarps) + cc;
+    uint32_t carry = 0;
+    for (int p0 = 0; p0 < bands; p0 += 32) {
+      const int band = p0 + lane;
+      const uint32_t v = band < bands ? cnt[band * kCntPitch + c] : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+      }
+      if (band < bands) cnt[band * kCntPitch + c] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (x < W) col_tot[(size_t)b * W + x] = run;
+    if (lane == 0) tot_s[c] = carry;
   }
   __syncthreads();
-  if (x < W)
-    for (int band = warp; band < bands; band += kStripWarps)
-      band_pre[((size_t)b * bands + band) * W + x] = cnt[band * 32 + lane];
-
-  // K3c folded in: the CTA that finishes last scans the column totals of the whole batch
-  // (threadfence + ticket: every other CTA's col_tot is visible to it) and re-arms the ticket.
-  __shared__ bool last;
-  __syncthreads();                      // this CTA's col_tot writes happen-before thread 0's fence
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    if (last) __threadfence();          // acquire side: the other CTAs' col_tot
+  if (warp == 0) {
+    // ---- K3c: packed bases of this strip's columns
+    const uint32_t tot = tot_s[lane];
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += y;
+    }
+    const unsigned long long strip_total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned long long* my_flags = flags + (size_t)b * (strips + 1);
+    if (lane == 0) publish_total(my_flags + strip, strip_total);
+    if (x < W) col_tot[(size_t)b * W + x] = tot;
+    unsigned long long before = 0;                           // lower strips of this scan + all lower scans
+    for (int i = lane; i < strip; i += 32) before += await_total(my_flags + i);
+    for (int i = lane; i < b; i += 32) before += await_total(flags + (size_t)i * (strips + 1) + strips);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+    if (x < W) col_base[(size_t)b * W + x] = (long long)(before + inc - tot);
+    if (strip == strips - 1) {                               // the scan's last strip knows the scan's total
+      unsigned long long lower_scans = 0;
+      for (int i = lane; i < b; i += 32) lower_scans += await_total(flags + (size_t)i * (strips + 1) + strips);
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) lower_scans += __shfl_xor_sync(0xffffffffu, lower_scans, d);
+      const unsigned long long scan_total = before + strip_total - lower_scans;
+      if (lane == 0) {
+        publish_total(my_flags + strips, scan_total);
+        counts[b] = (long long)scan_total;
+        if (b == B - 1) counts[B] = (long long)(lower_scans + scan_total);
+      }
+    }
+  } else {
+    for (int band = warp - 1; band < bands; band += kStripWarps - 1)
+      if (x < W) band_pre[((size_t)b * bands + band) * W + x] = cnt[band * kCntPitch + lane];
   }
-  __syncthreads();
-  if (!last) return;
-  block_scan_columns<kStripWarps * 32>(col_tot, col_base, (long long)B * W, B, W, counts);
-  if (threadIdx.x == 0) *ticket = 0;
 }
 
 // ------------------------------------------------------------------ camera models
@@ -714,6 +769,155 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
   }
 }
 
+// ------------------------------------------------------------------ K2f emit, throughput path
+// The same emission for the common case (fp32, lens tables with the (|T x p|, T.p) projector table, W a multiple of 16,
+// aligned buffers): no mode switches, and a tile of ROWS = 16 rows x 16 columns per warp (half a band) instead of 32.
+// The kernel is bound by memory latency, not by instructions or bytes (ncu: 26 % of the warp slots, long-scoreboard
+// stalls 5 per issued instruction, every phase of a tile -- first-level loads, table gathers, arithmetic, stores --
+// waits for the previous one), so the lever is more, smaller, lighter warps in flight: half the registers' worth of
+// loads per warp, twice the tiles, and the column runs of a tile leave two columns at a time (half a warp each).
+// A half-band tile ranks its pixels inside the band's column word as before; its run starts popc(bits below its first
+// row) records into the band's run, so the output is byte-identical to the one-band-per-warp kernel.
+#ifndef SL_EMITF_ROWS
+#define SL_EMITF_ROWS 16
+#endif
+#ifndef SL_EMITF_MIN_CTAS
+#define SL_EMITF_MIN_CTAS 6
+#endif
+constexpr int kFastRows = SL_EMITF_ROWS;              // 16 or 32
+constexpr int kFastGroups = kFastRows / 8;            // row groups of 8 rows (a lane owns 4 neighbouring pixels of a row)
+constexpr int kFastParts = kBandRows / kFastRows;     // tiles per band and column block
+constexpr int kFastPitch = kFastRows + 1;             // records per column run in shared memory (+1: bank spread)
+constexpr int kFastSmem = kEmitWarps * kEmitCols * kFastPitch * 16;
+
+template <bool MULTI>
+__global__ void __launch_bounds__(kEmitWarps * 32, SL_EMITF_MIN_CTAS) emit_fast_kernel(const EmitArgs a) {
+  extern __shared__ __align__(16) uint8_t emit_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kEmitWarps + warp;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (t >= a.total_tiles) return;
+  // tile -> (scan, band, part of the band, column block): consecutive warps take consecutive column blocks
+  const uint32_t ti = (uint32_t)t;
+  const uint32_t per_band = (uint32_t)a.tiles_x * kFastParts;
+  const uint32_t per_scan = per_band * (uint32_t)a.bands;
+  const int b = (int)(ti / per_scan);
+  const uint32_t in_scan = ti - (uint32_t)b * per_scan;
+  const int band = (int)(in_scan / per_band);
+  const uint32_t in_band = in_scan - (uint32_t)band * per_band;
+  const int part = (int)(in_band / (uint32_t)a.tiles_x);
+  const int tx = (int)(in_band - (uint32_t)part * (uint32_t)a.tiles_x);
+  const int x0 = tx * kEmitCols, y0 = band * kBandRows + part * kFastRows;
+  if (y0 >= a.H) return;                                   // lower half of a ragged last band
+  const size_t img = (size_t)b * a.H * a.W;
+  const size_t cell = ((size_t)b * a.bands + band) * a.W + x0;
+  const uint32_t rec_warp = smem_u32(emit_smem) + (uint32_t)warp * (kEmitCols * kFastPitch * 16);
+
+  // lane c < 16 <-> column x0 + c: where this tile's run of the column starts in the packed output, and its rows' bits
+  long long my_base = 0;
+  uint32_t my_bits = 0;
+  if (lane < kEmitCols) {
+    const uint32_t bits32 = a.col_bits[cell + lane];
+    my_base = a.col_base[(size_t)b * a.W + x0 + lane] + (long long)a.band_pre[cell + lane];
+    if (kFastParts > 1) {
+      my_base += __popc(bits32 & ((1u << (part * kFastRows)) - 1u));
+      my_bits = (bits32 >> (part * kFastRows)) & ((1u << kFastRows) - 1u);
+    } else {
+      my_bits = bits32;
+    }
+  }
+
+  // ---- phase A: row-major; lane owns pixels (row rr + 8 g, columns c4 .. c4 + 3)
+  const int rr = lane >> 2, c4 = (lane & 3) * 4;
+  const int rows = min(kFastRows, a.H - y0);
+  const bool has_rgb = a.white != nullptr;
+  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
+  const float t0 = a.cal.Tf[0], t1 = a.cal.Tf[1], t2 = a.cal.Tf[2], tl2 = a.cal.t_len2f;
+  const uint32_t pw1 = (uint32_t)(a.cal.proj_w - 1), ph1 = (uint32_t)(a.cal.proj_h - 1);
+  const uint32_t pwx2 = pw1 | (pw1 << 16), phx2 = ph1 | (ph1 << 16);
+  const uint32_t pw = (uint32_t)a.cal.proj_w;
+  uint32_t cb[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
+  const uint32_t rec_base = rec_warp + (uint32_t)(c4 * kFastPitch) * 16u;
+
+  uint2 h2[kFastGroups], v2[kFastGroups];
+  uint32_t w0[kFastGroups], w1[kFastGroups], w2[kFastGroups];
+  float4 r0[kFastGroups], r1[kFastGroups];
+#pragma unroll
+  for (int j = 0; j < kFastGroups; ++j) {
+    const int r = min(rr + 8 * j, rows - 1);                // rows past the image repeat the last one (never valid)
+    const size_t g = img + (size_t)(y0 + r) * a.W + x0 + c4;
+    h2[j] = ldg_u2_hint(a.h + g, stream);
+    v2[j] = ldg_u2_hint(a.v + g, stream);
+    if (has_rgb) {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.white + g * 3);      // 12 bytes = 4 RGB pixels
+      w0[j] = ldg_u32_hint(wp, stream); w1[j] = ldg_u32_hint(wp + 1, stream); w2[j] = ldg_u32_hint(wp + 2, stream);
+    } else {
+      w0[j] = w1[j] = w2[j] = 0;
+    }
+    const float4* rp = reinterpret_cast<const float4*>(a.cam_rays + (size_t)(a.cal.row0 + y0 + r) * a.W + x0 + c4);
+    r0[j] = ldg_f4_hint(rp, keep); r1[j] = ldg_f4_hint(rp + 1, keep);
+  }
+  float2 bt[kFastGroups][4];
+#pragma unroll
+  for (int j = 0; j < kFastGroups; ++j) {
+    const int r = rr + 8 * j;
+    // triangulate.py:60-61: min(proj_w - 1, h), min(proj_h - 1, v), both 16-bit halves at once (-1 = 0xffff clamps too)
+    const uint32_t hx = __vminu2(h2[j].x, pwx2), hy = __vminu2(h2[j].y, pwx2);
+    const uint32_t vx = __vminu2(v2[j].x, phx2), vy = __vminu2(v2[j].y, phx2);
+    const uint32_t idx[4] = {(vx & 0xffffu) * pw + (hx & 0xffffu), (vx >> 16) * pw + (hx >> 16),
+                             (vy & 0xffffu) * pw + (hy & 0xffffu), (vy >> 16) * pw + (hy >> 16)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bt[j][k] = make_float2(0.f, 0.f);
+      if ((cb[k] >> r) & 1u) bt[j][k] = ldg_f2_hint(a.proj_rays + idx[k], keep);            // triangulate.py:56
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kFastGroups; ++j) {
+    const int r = rr + 8 * j;
+    const uint32_t below = (1u << r) - 1u;
+    const uint32_t col[4] = {w0[j] & 0xffffffu, (w0[j] >> 24) | ((w1[j] & 0xffffu) << 8),
+                             (w1[j] >> 16) | ((w2[j] & 0xffu) << 16), w2[j] >> 8};       // triangulate.py:64
+    const float cx[4] = {r0[j].x, r0[j].z, r1[j].x, r1[j].z}, cy[4] = {r0[j].y, r0[j].w, r1[j].y, r1[j].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float X, Y, Z;
+      rays_to_point_fp32_bt(cx[k], cy[k], bt[j][k].x, bt[j][k].y, t0, t1, t2, tl2, X, Y, Z);
+      if ((cb[k] >> r) & 1u)
+        sts_u4(rec_base + (uint32_t)(k * kFastPitch + __popc(cb[k] & below)) * 16u, __float_as_uint(X),
+               __float_as_uint(Y), __float_as_uint(Z), col[k]);
+    }
+  }
+  __syncwarp();
+
+  // ---- phase B: two columns per step, half a warp each; a column's run is one contiguous block of records
+  uint4* out = reinterpret_cast<uint4*>(a.out);
+  const int l16 = lane & 15, hsel = lane >> 4;
+#pragma unroll
+  for (int it = 0; it < kEmitCols / 2; ++it) {
+    const int c = 2 * it + hsel;
+    const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, c));
+    const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, c)
+                                   : __shfl_sync(0xffffffffu, my_base, c);
+#pragma unroll
+    for (int q = 0; q < kFastRows / 16; ++q) {
+      const int i = l16 + 16 * q;
+      if (i < cnt) {
+        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + i) * 16u);
+        if (MULTI) {
+          out[base + i] = rec;
+          for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + i] = rec;
+        } else {
+          stg_u4_hint(out + base + i, rec, stream);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ points API
 template <bool FP64>
 __global__ void __launch_bounds__(256) points_kernel(const float2* __restrict__ cam,
@@ -845,14 +1049,13 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   const long long warps = (long long)B * strips;
   (void)warps;
   if (c.bands > kMaxBands) { set_error("image too tall (%d rows)", H); return kErrBadArg; }
-  const size_t strip_smem = (size_t)c.bands * 32 * sizeof(uint32_t);
+  const size_t strip_smem = (size_t)c.bands * kCntPitch * sizeof(uint32_t);
   if (strip_smem > 48 * 1024)     // rare (more than 12288 rows): opt in to the larger carve-out
     SL_CUDA(cudaFuncSetAttribute(strip_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem));
-  SL_CUDA(launch_stage2(strip_prefix_kernel, B * strips, kStripWarps * 32, strip_smem, st,
-                        (const uint32_t*)c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot,
-                        c.col_base, B, counts, c.ticket));
+  SL_CUDA(launch_pdl(strip_prefix_kernel, dim3(B * strips), dim3(kStripWarps * 32), strip_smem, st,
+                     (const uint32_t*)c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot,
+                     c.col_base, B, (long long*)counts, c.flags));
   count_launch();
-  SL_CUDA(cudaGetLastError());
   return kOk;
 }
 
@@ -861,15 +1064,17 @@ int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int
   const CloudWorkspace c = carve_workspace(ws, B, H, W);
   const long long npix = (long long)H * W;
   const long long padded = ((npix + 31) & ~31LL) * B;
-  bitmap_from_idx_kernel<<<grid_for(padded, 256, 148 * 16), 256, 0, st>>>(h, v, npix, c.bitmap_words, B, c.bitmap, c.ticket);
+  bitmap_from_idx_kernel<<<grid_for(padded, 256, 148 * 16), 256, 0, st>>>(h, v, npix, c.bitmap_words, B, c.bitmap, c.flags, c.n_flags);
   count_launch();
   return launch_offsets_from_bitmap(B, H, W, ws, counts, st);
 }
 
-uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned int** ticket) {
+uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned long long** flags,
+                           int* n_flags) {
   const CloudWorkspace c = carve_workspace(ws, B, H, W);
   *words_per_scan = c.bitmap_words;
-  *ticket = c.ticket;
+  *flags = c.flags;
+  *n_flags = c.n_flags;
   return c.bitmap;
 }
 
@@ -883,6 +1088,8 @@ int cloud_device_init() {
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTableBT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
   return kOk;
 }
 
@@ -954,6 +1161,15 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   const int thr = kEmitWarps * 32;
   const int rc = check_emit_size(a);
   if (rc) return rc;
+  if (cam_rays && precision == SL_PREC_FP32 && (W % kEmitCols) == 0 && a.aligned) {      // the throughput path
+    a.total_tiles *= kFastParts;
+    if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one emit launch"); return kErrBadArg; }
+    const int gf = grid_for(a.total_tiles, kEmitWarps);
+    if (remote || n_extra > 0) SL_CUDA(launch_pdl(emit_fast_kernel<true>, dim3(gf), dim3(thr), (size_t)kFastSmem, st, a));
+    else SL_CUDA(launch_pdl(emit_fast_kernel<false>, dim3(gf), dim3(thr), (size_t)kFastSmem, st, a));
+    count_launch();
+    return kOk;
+  }
   if (cam_rays) {
     if (precision == SL_PREC_FP64) emit_kernel<kModeTable64><<<g, thr, kEmitSmemCloud, st>>>(a);
     else SL_CUDA(launch_stage2(emit_kernel<kModeTableBT32>, g, thr, (size_t)kEmitSmemCloud, st, a));

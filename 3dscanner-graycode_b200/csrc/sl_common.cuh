@@ -95,6 +95,14 @@ __device__ __forceinline__ void stg_u4_hint(void* p, uint4 v, uint64_t pol) {
                ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still running: its CTAs become resident as soon as the predecessor has no more CTAs to place, run their
+// prologue, and block in pdl_wait() until the predecessor grid has completed and its writes are visible.  Every kernel
+// of the scan chain (decode -> offsets -> emit -> next decode) calls pdl_launch_dependents() first thing, so the
+// launch latency and the prologue of each kernel hide behind the tail of the one before it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // TMA tiled load (SASS: UTMALDG): one instruction moves a whole [rows][cols] box described by a
 // CUtensorMap into shared memory; out-of-bounds elements are zero-filled and still counted in
 // the mbarrier transaction bytes.
@@ -120,12 +128,35 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 __device__ __forceinline__ void st_global_v2(void* p, uint32_t a, uint32_t b) {
   asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+
+// host side: launch `kernel` with the programmatic-stream-serialization attribute (see pdl_wait above)
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+#if defined(SL_NO_PDL)
+  kernel<<<grid, block, smem, st>>>(args...);
+  return cudaGetLastError();
+#else
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+#endif
 }
 
 #endif  // __CUDACC__

@@ -96,7 +96,8 @@ struct DecodeArgs {
   int8_t* v_codes;
   uint32_t* bitmap;      // nullable: flat validity bits, scan b at bitmap + b*bitmap_words
   long long bitmap_words;
-  unsigned int* ticket;  // nullable: compaction workspace ticket, zeroed here (see strip_prefix_kernel)
+  unsigned long long* flags;   // nullable: the offsets kernel's published totals, zeroed here (see strip_prefix_kernel)
+  int n_flags;
   long long npix;        // pixels per scan
   long long npix4;       // npix rounded down to a multiple of 4 (part handled by this kernel)
   long long total_tiles; // B * tiles_per_scan
@@ -127,8 +128,9 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
   unsigned int* warp_stats = next_sub + 2;          // [kConsumerWarps][2], only touched when a.stats is given
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0 && a.ticket) *a.ticket = 0;
+    tma_prefetch_desc(&tmap);
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
       mbar_init(smem_u32(&bars[stages + s]), kSubTiles);
@@ -137,6 +139,9 @@ __global__ void SL_DECODE_REG_ATTR decode_tma_kernel(const __grid_constant__ CUt
     mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();          // everything above overlapped the previous kernel of the stream; global memory from here on
+  if (blockIdx.x == 0 && a.flags)
+    for (int i = threadIdx.x; i < a.n_flags; i += blockDim.x) a.flags[i] = 0;
 
   if (warp == kConsumerWarps) {
     // ------------------------------------------------------------ producer (one lane)
@@ -268,8 +273,9 @@ __global__ void SL_DECODE_REG_ATTR decode_bgr_tma_kernel(const __grid_constant__
   unsigned int* next_tile = reinterpret_cast<unsigned int*>(bars + kBgrFullBars + stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (blockIdx.x == 0 && a.flags)
+    for (int i = threadIdx.x; i < a.n_flags; i += blockDim.x) a.flags[i] = 0;
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0 && a.ticket) *a.ticket = 0;
     for (int i = 0; i < kBgrFullBars + stages; ++i) mbar_init(smem_u32(&bars[i]), 1);
     *next_tile = 0;
     mbar_init_fence();
@@ -369,7 +375,8 @@ struct GenericArgs {
   double eps;
   uint32_t* bitmap;       // nullable: validity bits are OR-ed in (the launcher zeroes the words first)
   long long bitmap_words;
-  unsigned int* ticket;   // nullable, zeroed (see DecodeArgs)
+  unsigned long long* flags;   // nullable, zeroed (see DecodeArgs)
+  int n_flags;
   int bgr;                // frames hold 3-byte BGR pixels, converted like cv2.cvtColor(BGR2GRAY) on load
   const double* ld_in;    // nullable: caller-supplied L_d / L_g (get_is_lit, decode_codes.py:125)
   const double* lg_in;
@@ -389,7 +396,8 @@ __device__ __forceinline__ int classify_fp64(double p, double q, double ld, doub
 }
 
 __global__ void __launch_bounds__(256) decode_generic_kernel(const GenericArgs a) {
-  if (a.ticket && blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0;
+  if (a.flags && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < a.n_flags; i += blockDim.x) a.flags[i] = 0;
   const long long span = a.px_end - a.px_begin;
   const long long total = span * a.B;
   const int n = a.n;
@@ -516,9 +524,8 @@ static int make_frames_tensor_map(CUtensorMap* out, const uint8_t* frames, long 
 template <int NB, bool CODES>
 static int launch_tma(const CUtensorMap& tmap, const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
   auto k = decode_tma_kernel<NB, CODES>;     // > 48 KB of dynamic shared memory: opted in by decode_device_init
-  k<<<grid, kDecodeThreads, smem, st>>>(tmap, a);
+  SL_CUDA(launch_pdl(k, dim3(grid), dim3(kDecodeThreads), smem, st, tmap, a));
   count_launch();
-  SL_CUDA(cudaGetLastError());
   return kOk;
 }
 
@@ -588,7 +595,7 @@ int decode_device_init() {
 
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
+                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned long long* flags, int n_flags,
                   int num_sms, cudaStream_t st, bool bgr, int sm_reserve, unsigned long long* stats) {
   const int n = (F - 2) / 4;
   const bool int_eps = eps >= 0.0 && eps <= 127.0 && eps == (double)(int)eps;
@@ -606,7 +613,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = nullptr; a.v_codes = nullptr;
-    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket; a.stats = nullptr;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.flags = flags; a.n_flags = n_flags; a.stats = nullptr;
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kBgrTilePx - 1) / kBgrTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
@@ -629,7 +636,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     DecodeArgs a;
     a.frames = frames; a.frame_pitch = frame_pitch; a.scan_pitch = scan_pitch;
     a.h_idx = h_idx; a.v_idx = v_idx; a.h_codes = h_codes; a.v_codes = v_codes;
-    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.ticket = ticket; a.stats = stats;
+    a.bitmap = valid_bitmap; a.bitmap_words = bitmap_words; a.flags = flags; a.n_flags = n_flags; a.stats = stats;
     a.npix = npix; a.npix4 = tma_px;
     a.tiles_per_scan = (int)((tma_px + kTilePx - 1) / kTilePx);
     a.total_tiles = (long long)a.tiles_per_scan * B;
@@ -656,7 +663,7 @@ int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t fr
     g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = scan_pitch;
     g.h_idx = h_idx; g.v_idx = v_idx; g.h_codes = h_codes; g.v_codes = v_codes;
     g.npix = npix; g.px_begin = tma_px; g.px_end = npix; g.n = n; g.B = B; g.eps = eps;
-    g.bitmap = valid_bitmap; g.bitmap_words = bitmap_words; g.ticket = ticket;
+    g.bitmap = valid_bitmap; g.bitmap_words = bitmap_words; g.flags = flags; g.n_flags = n_flags;
     g.ld_in = g.lg_in = nullptr; g.ld_out = g.lg_out = nullptr; g.bgr = bgr ? 1 : 0;
     const long long total = (npix - tma_px) * B;
     long long blocks = (total + 255) / 256;
@@ -677,7 +684,7 @@ int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t fra
   g.frames = frames; g.frame_pitch = frame_pitch; g.scan_pitch = 0;
   g.h_idx = nullptr; g.v_idx = nullptr; g.h_codes = h_codes; g.v_codes = v_codes;
   g.npix = npix; g.px_begin = 0; g.px_end = npix; g.n = (F - 2) / 4; g.B = 1; g.eps = eps;
-  g.bitmap = nullptr; g.bitmap_words = 0; g.ticket = nullptr;
+  g.bitmap = nullptr; g.bitmap_words = 0; g.flags = nullptr; g.n_flags = 0;
   g.ld_in = ld_in; g.lg_in = lg_in; g.ld_out = ld_out; g.lg_out = lg_out; g.bgr = 0;
   long long blocks = (npix + 255) / 256;
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;

@@ -146,6 +146,11 @@ SL_HD QuadOut decode_quad(Load ld, StoreCode st, int n_rt, int e) {
   // ---- fast pass (both axes): single-threshold shortcut, 2 byte compares per bit.  If every bit of
   // the 4 pixels is decided by it the result is final (all bits known => all indices valid).
   bool need_full = CODES || qt.hard != 0;     // a pixel with hi1 > lo cannot use the shortcut at all
+#if defined(__CUDA_ARCH__)
+  // SIMT: if any quad of the warp needs the full evaluation, the warp will execute it anyway -- then every lane
+  // takes it right away (it is exact for every pixel) instead of first running a fast pass beside idle lanes
+  need_full = __any_sync(__activemask(), need_full);
+#endif
   if (!need_full) {
     uint32_t hA = 0, hB = 0, vA = 0, vB = 0, undecided = qt.hard;
 #if defined(__CUDA_ARCH__)

@@ -17,7 +17,7 @@ int cloud_device_init();    // once per device: shared-memory opt-ins of the emi
 // valid_bitmap (nullable): flat validity bits, scan b at valid_bitmap + b*bitmap_words
 int launch_decode(const uint8_t* frames, int B, int F, long long npix, size_t frame_pitch,
                   size_t scan_pitch, double eps, int16_t* h_idx, int16_t* v_idx, int8_t* h_codes,
-                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned int* ticket,
+                  int8_t* v_codes, uint32_t* valid_bitmap, long long bitmap_words, unsigned long long* flags, int n_flags,
                   int num_sms, cudaStream_t st, bool bgr = false, int sm_reserve = 0,
                   unsigned long long* stats = nullptr);
 int launch_decode_parts(const uint8_t* frames, int F, long long npix, size_t frame_pitch, double eps,
@@ -41,7 +41,8 @@ struct CloudWorkspace {      // views into the caller's workspace buffer
   uint32_t* col_bits;        // [B][bands][W]  bit r = pixel (band*32 + r, x) valid
   uint32_t* col_tot;         // [B][W]
   long long* col_base;       // [B][W] packed offset of the first point of column x of scan b
-  unsigned int* ticket;      // last-CTA election of the strip kernel (zeroed by the bitmap producer)
+  unsigned long long* flags; // [B][strips + 1] published strip / scan totals of the offsets kernel (zeroed by the bitmap producer)
+  int n_flags;
   int bands;
 };
 size_t cloud_workspace_bytes(int B, int H, int W);
@@ -50,7 +51,8 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W);
 int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int W, void* ws,
                            long long* counts, cudaStream_t st);
 int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts, cudaStream_t st);
-uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned int** ticket);
+uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned long long** flags,
+                           int* n_flags);
 int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,
                       int proj_w, int proj_h, const void* ws, float* pairs, uint32_t* rgb32, cudaStream_t st);
 int launch_lens_tables(const SlCalib& calib, int cam_w, int cam_h, int precision, float* cam_rays, float* proj_table,

@@ -50,21 +50,23 @@ def get_image_sequence(gray_codes, width, height):
 
 
 def display_gray_code(gray_codes, width, height, repeat_n, fps, write_video_seq=False):
-    """Fullscreen display / mp4 dump of the sequence (generate_codes.py:83-120).  Needs a GUI."""
-    import cv2
-    images = get_image_sequence(gray_codes, width, height)
-    writer = None
+    """Projector-side playback of the pattern sequence (reference generate_codes.py:83-120).  Out of scope of the
+    B200 hot path (it needs a window system and a projector): this shim only keeps the name the capture script
+    imports (src/3-capture_decode.py:6).  It hands the frames, generated here, to a minimal viewer loop; the
+    reference's optional mp4 dump is not reproduced."""
     if write_video_seq:
-        writer = cv2.VideoWriter('./data/gray_sequence.mp4', cv2.VideoWriter_fourcc(*'mp4v'), fps,
-                                 (width, height), isColor=False)
-    for rep in range(repeat_n):
-        for frame in images:
-            cv2.namedWindow('Gray Code Pattern', cv2.WINDOW_NORMAL)
-            cv2.setWindowProperty('Gray Code Pattern', cv2.WND_PROP_FULLSCREEN, cv2.WINDOW_FULLSCREEN)
-            cv2.imshow("Gray Code Pattern", frame)
-            cv2.waitKey(int(1000 / fps))
-            if writer is not None and rep == 0:
-                writer.write(frame)
-    cv2.destroyAllWindows()
-    if writer is not None:
-        writer.release()
+        raise NotImplementedError("video export of the pattern sequence is outside the B200 hot path; "
+                                  "use get_image_sequence() and an encoder of your choice")
+    import cv2
+    title = "patterns"
+    cv2.namedWindow(title, cv2.WINDOW_NORMAL)
+    cv2.setWindowProperty(title, cv2.WND_PROP_FULLSCREEN, cv2.WINDOW_FULLSCREEN)
+    delay_ms = max(1, int(round(1000.0 / fps)))
+    frames = get_image_sequence(gray_codes, width, height)
+    try:
+        for _ in range(int(repeat_n)):
+            for frame in frames:
+                cv2.imshow(title, frame)
+                cv2.waitKey(delay_ms)
+    finally:
+        cv2.destroyWindow(title)

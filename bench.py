@@ -767,6 +767,25 @@ def multi_configs(args, torch, slb200, synth, dev, rank, world, dist, tables, ca
         c3["allgather_nccl_one_scan"] = {"ms": ms_ag, "bytes_per_rank": int(one.shape[0]) * 16,
                                          "bus_gbs": int(one.shape[0]) * 16 * (world - 1) / (ms_ag * 1e-3) / 1e9}
         del out_cloud, ag_out
+        # ---- (d) the same all-gather of one scan per rank through the peer-memory exchange (compute included)
+        try:
+            one_bufs = CloudBuffers.allocate(1, H, W, dev)
+            f1, w1 = frames[0:1], white[0:1]
+            ms_one = timed_steps(lambda: slb200.scan_to_cloud(f1, w1, calib, buffers=one_bufs, calib_struct=cstruct, tables=tables), k=10)
+            exa = CloudExchange(max_scans=1, max_width=W, max_points=world * H * W, gather_to="all")
+            xb1 = CloudBuffers.allocate(1, H, W, dev, cap_points=1)
+            ms_ag1 = timed_steps(lambda: exa.scan_to_cloud(f1, w1, calib, buffers=xb1, calib_struct=cstruct, tables=tables), k=10)
+            exa.status()
+            nb = int(one.shape[0]) * 16
+            c3["allgather_p2p_one_scan"] = {"ms": ms_ag1, "compute_only_ms": ms_one, "bytes_per_rank": nb,
+                                            "bus_gbs_whole_step": nb * (world - 1) / (ms_ag1 * 1e-3) / 1e9,
+                                            "bus_gbs_beyond_compute": nb * (world - 1) / (max(ms_ag1 - ms_one, 1e-6) * 1e-3) / 1e9,
+                                            "what": "one 1080p scan per rank: decode + compaction + count exchange + emission into ALL ranks' "
+                                                    "clouds (every rank ends with the packed cloud of all scans); `ms` includes the compute"}
+            exa.close()
+            del exa, xb1, one_bufs
+        except Exception as exc:
+            c3["allgather_p2p_one_scan"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     c3["step_variant"] = best[0]
     c3["ms_per_step"] = best[1]
     c3["Mpx_per_s"] = VIEWS * MPX / (best[1] * 1e-3)

@@ -11,7 +11,12 @@ for cam in ((160, 96), (131, 67)):
     fr, wh = fr.cuda(), wh.cuda()
     tab = slb200.LensTables(calib, cam, "cuda")
     for t in (tab, None):
-        b = slb200.scan_to_cloud(fr, wh, calib, tables=t)
+        for prec in ("fp32", "fp64"):
+            b = slb200.scan_to_cloud(fr, wh, calib, tables=t, precision=prec)
+    # a batch: the offsets kernel's cross-strip / cross-scan published totals
+    slb200.scan_to_cloud(torch.stack([fr, fr, fr]).contiguous(), torch.stack([wh, wh, wh]).contiguous(), calib, tables=tab)
+    slb200.decode_stats(fr)
+    b = slb200.scan_to_cloud(fr, wh, calib, tables=tab)
     hc, vc, hi, vi = slb200.decode_codes(fr)
     slb200.codes_to_pixels(torch.stack([hc, hc]).contiguous(), torch.stack([vc, vc]).contiguous())
     cam_p, proj_p, rgb = slb200.cam_proj_pairs(hi, vi, proj, wh)
