@@ -199,8 +199,6 @@ __global__ void __launch_bounds__(kStripWarps * 32) strip_prefix_kernel(const ui
                                                                          unsigned long long* __restrict__ flags) {
   extern __shared__ uint32_t cnt[];            // [bands][kCntPitch] counts, then exclusive prefixes
   __shared__ uint32_t tot_s[kStripCols];
-  pdl_launch_dependents();
-  pdl_wait();
   const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = strip * kStripCols, x = x0 + lane;
@@ -795,8 +793,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMITF_MIN_CTAS) emit_fast_
   extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
-  pdl_launch_dependents();
-  pdl_wait();
   if (t >= a.total_tiles) return;
   // tile -> (scan, band, part of the band, column block): consecutive warps take consecutive column blocks
   const uint32_t ti = (uint32_t)t;
@@ -1052,10 +1048,11 @@ int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts,
   const size_t strip_smem = (size_t)c.bands * kCntPitch * sizeof(uint32_t);
   if (strip_smem > 48 * 1024)     // rare (more than 12288 rows): opt in to the larger carve-out
     SL_CUDA(cudaFuncSetAttribute(strip_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem));
-  SL_CUDA(launch_pdl(strip_prefix_kernel, dim3(B * strips), dim3(kStripWarps * 32), strip_smem, st,
-                     (const uint32_t*)c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot,
-                     c.col_base, B, (long long*)counts, c.flags));
+  SL_CUDA(launch_stage2(strip_prefix_kernel, B * strips, kStripWarps * 32, strip_smem, st,
+                        (const uint32_t*)c.bitmap, c.bitmap_words, H, W, c.bands, strips, c.band_cnt, c.col_bits, c.col_tot,
+                        c.col_base, B, counts, c.flags));
   count_launch();
+  SL_CUDA(cudaGetLastError());
   return kOk;
 }
 
@@ -1165,9 +1162,10 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
     a.total_tiles *= kFastParts;
     if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one emit launch"); return kErrBadArg; }
     const int gf = grid_for(a.total_tiles, kEmitWarps);
-    if (remote || n_extra > 0) SL_CUDA(launch_pdl(emit_fast_kernel<true>, dim3(gf), dim3(thr), (size_t)kFastSmem, st, a));
-    else SL_CUDA(launch_pdl(emit_fast_kernel<false>, dim3(gf), dim3(thr), (size_t)kFastSmem, st, a));
+    if (remote || n_extra > 0) emit_fast_kernel<true><<<gf, thr, kFastSmem, st>>>(a);
+    else SL_CUDA(launch_stage2(emit_fast_kernel<false>, gf, thr, (size_t)kFastSmem, st, a));
     count_launch();
+    SL_CUDA(cudaGetLastError());
     return kOk;
   }
   if (cam_rays) {

@@ -97,9 +97,10 @@ __device__ __forceinline__ void stg_u4_hint(void* p, uint4 v, uint64_t pol) {
 
 // Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may start while its predecessor in the
 // stream is still running: its CTAs become resident as soon as the predecessor has no more CTAs to place, run their
-// prologue, and block in pdl_wait() until the predecessor grid has completed and its writes are visible.  Every kernel
-// of the scan chain (decode -> offsets -> emit -> next decode) calls pdl_launch_dependents() first thing, so the
-// launch latency and the prologue of each kernel hide behind the tail of the one before it.
+// prologue, and block in pdl_wait() until the predecessor grid has completed and its writes are visible.  Only the
+// decode kernels use it (decode after decode: batches of calls, sl_decode_host): measured on the whole chain
+// decode -> offsets -> emit it costs more than it saves (4K scan 149 -> 177 us, 64-view batch 2.03 -> 2.06 ms: the
+// early-resident CTAs of the next kernel hold registers and shared memory while they wait).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -128,8 +128,9 @@ class Triangulate(object):
             check(lib().sl_emit_cloud(_ptr(bufs.h_idx), _ptr(bufs.v_idx), _ptr(white), C.byref(s), _PREC[precision],
                                       None, None, 1, self.cam_h, self.cam_w, _ptr(bufs.ws), _ptr(bufs.cloud), _stream()))
         n = int(bufs.counts[1].item())
+        # widen on the device (IEEE fp64 division: the same values as the reference's uint8 / 255, triangulate.py:69)
         pts = bufs.xyz[:n].to(torch.float64).t().contiguous().cpu().numpy()
-        colors = bufs.rgb[:n].cpu().numpy().astype(np.float64) / 255.0
+        colors = (bufs.rgb[:n].to(torch.float64) / 255.0).cpu().numpy()
         return pts, colors
 
 

@@ -122,8 +122,8 @@ def as_u8_stack(images, device=None) -> torch.Tensor:
     for k in range(planes.shape[0]):
         src = planes[k]
         dst = u_planes[k]
-        dst.copy_(src.clamp(0, 255) if src.dtype.is_floating_point else src.clamp(0, 255))
-        if not torch.equal(dst.to(src.dtype), src):
+        dst.copy_(src)          # plain cast: a value that is not an integer in 0..255 (NaN, 300, -1, 0.5) fails the
+        if not torch.equal(dst.to(src.dtype), src):        # round trip below whatever the cast made of it
             raise ValueError("frame stack must hold integer grey levels in 0..255 "
                              "(the B200 path computes on uint8 samples)")
     return u.to(dev).contiguous()       # blocking: the pinned staging buffer is reused by the next call

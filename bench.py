@@ -470,31 +470,39 @@ def run_single(args, torch, slb200, synth, dev, local):
     tables = slb200.LensTables(calib, CAM_SIZE, dev)                 # once per calibration
     torch.cuda.synchronize()
 
+    G = max(1, args.scans_per_graph)             # scans replayed by one graph launch (consecutive ring slots, one stream)
+    n_graphs = ring_n // G
+    if n_graphs * G != ring_n:
+        raise SystemExit("--ring must be a multiple of --scans-per-graph")
+
     def step_fn(lens_tables, rsv):
         def fn(i, k):
-            slb200.scan_to_cloud(ring_frames[i % ring_n], ring_white[i % ring_n], calib, precision="fp32",
-                                 buffers=bufsets[k], calib_struct=cstruct, tables=lens_tables, sm_reserve=rsv)
+            for g in range(G):
+                j = (i * G + g) % ring_n
+                slb200.scan_to_cloud(ring_frames[j], ring_white[j], calib, precision="fp32",
+                                     buffers=bufsets[k], calib_struct=cstruct, tables=lens_tables, sm_reserve=rsv)
         return fn
 
     primary_tables = None if args.lens == "iterate" else tables
     before = slb200.launch_count()
     step_fn(primary_tables, sm_reserve)(0, 0)
-    kernels_per_scan = slb200.launch_count() - before
+    kernels_per_scan = (slb200.launch_count() - before) // G
     torch.cuda.synchronize()
     ring = StreamRing(torch, dev, S)
-    graphs = ring.capture(step_fn(primary_tables, sm_reserve), ring_n)
+    graphs = ring.capture(step_fn(primary_tables, sm_reserve), n_graphs)
 
     sampler = ClockSampler(local)
     sampler.start()
 
     # ---- timed region: EXACTLY K steps, a step = one pass over the ring (ring_n scans)
-    ring.replay(graphs, Wm * ring_n)
+    ring.replay(graphs, Wm * n_graphs)
     torch.cuda.synchronize()
-    ms_total = ring.timed(graphs, K * ring_n)
+    ms_total = ring.timed(graphs, K * n_graphs)
     torch.cuda.synchronize()
     valid_pts = int(bufs.counts[1].item())
     # results of ring scan 0 in the timed configuration, for the parity check below
-    graphs[0].replay()
+    slb200.scan_to_cloud(ring_frames[0], ring_white[0], calib, precision="fp32", buffers=bufsets[0],
+                         calib_struct=cstruct, tables=primary_tables, sm_reserve=sm_reserve)
     torch.cuda.synchronize()
     gpu_h = bufs.h_idx[0].cpu().numpy()
     gpu_v = bufs.v_idx[0].cpu().numpy()
@@ -502,10 +510,10 @@ def run_single(args, torch, slb200, synth, dev, local):
 
     # ---- the other lens mode for the same step (north_star names the in-kernel Brown-Conrady iteration)
     other_tables = tables if primary_tables is None else None
-    graphs_o = ring.capture(step_fn(other_tables, sm_reserve), ring_n)
-    ring.replay(graphs_o, 2 * ring_n)
+    graphs_o = ring.capture(step_fn(other_tables, sm_reserve), n_graphs)
+    ring.replay(graphs_o, 2 * n_graphs)
     ko = max(2, min(K, 10))
-    ms_other = ring.timed(graphs_o, ko * ring_n) / (ko * ring_n)
+    ms_other = ring.timed(graphs_o, ko * n_graphs) / (ko * ring_n)
     del graphs_o
 
     def lens_name(t):
@@ -947,6 +955,7 @@ def main():
     ap.add_argument("--sm-reserve", type=int, default=None,
                     help="SMs the decode grid leaves to the other streams' kernels (default: 8 when pipelining, else 0)")
     ap.add_argument("--ring", type=int, default=RING)
+    ap.add_argument("--scans-per-graph", type=int, default=1, help="consecutive ring scans replayed by one CUDA graph launch")
     ap.add_argument("--multi-steps", type=int, default=20, help="timed steps of the multi-GPU configurations")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--streams", type=int, default=4); ap.add_argument("--scans", type=int, default=48)
 ap.add_argument("--ring", type=int, default=12); ap.add_argument("--sm-reserve", type=int, default=8)
 ap.add_argument("--what", default="step", choices=["step", "decode", "stage2"])
+ap.add_argument("--graphs", action="store_true", help="replay pre-captured CUDA graphs inside the range (the decode launch encodes a tensor map, which range replay cannot capture)")
 a = ap.parse_args()
 cam, proj = (1920, 1080), (1920, 1080); dev = torch.device("cuda", 0)
 calib = synth.synthetic_calibration(cam, proj); pats = synth.pattern_stack(proj, dev)
@@ -35,6 +36,22 @@ def one(i):
             check(L.sl_emit_cloud(_ptr(b.h_idx), _ptr(b.v_idx), _ptr(wh), C.byref(cs), 0, _ptr(tables.cam), _ptr(tables.proj_bt), 1, H, W, _ptr(b.ws), _ptr(b.cloud), _stream()))
 for i in range(2 * a.ring): one(i)
 torch.cuda.synchronize()
+if a.graphs:
+    graphs = []
+    for i in range(a.ring):
+        k = i % a.streams
+        with torch.cuda.stream(sts[k]):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=sts[k]):
+                one(i)
+            graphs.append(g)
+    torch.cuda.synchronize()
+    plain = one
+    def one(i):
+        with torch.cuda.stream(sts[i % a.ring % a.streams]):
+            graphs[i % a.ring].replay()
+    for i in range(a.ring): one(i)
+    torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.profiler.start()
 e0.record()

@@ -1,8 +1,7 @@
-# A/B of library build variants on the bench step: SLB200_LIB selects the build
+# A/B of library build variants: the bench step + isolated stage-2 timings; SLB200_LIB selects the build
 V=3dscanner-graycode_b200/lib/variants
-run() { python bench.py --steps 60 --no-multi --no-cpu --no-e2e --no-hard "$@" 2>/dev/null | python -c "
+run() { python bench.py --steps 100 --no-multi --no-cpu --no-e2e --no-hard "$@" 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['us_per_scan'],2),'us/scan  decode',round(d['roofline']['us_per_launch'],2),'iso',round(d['roofline']['isolated']['us_per_launch'],2),'off',round(d['stage2']['offsets_us'],2),'emit',round(d['stage2']['emit_tables_us'],2))"; }
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for r in 0 8; do echo "default reserve=$r: $(run --sm-reserve $r)"; done
-for f in $V/*.so; do for r in 0 8; do echo "$(basename $f) reserve=$r: $(SLB200_LIB=$PWD/$f run --sm-reserve $r)"; done; done
+echo "default: $(run)"
+for f in $V/*.so; do echo "$(basename $f): $(SLB200_LIB=$PWD/$f run)"; done
