@@ -184,3 +184,45 @@ def test_gray_formula_matches_cv2_golden(golden_dir):
     bgr = g["gray_bgr"].astype(np.uint32)
     gray = (3735 * bgr[..., 0] + 19235 * bgr[..., 1] + 9798 * bgr[..., 2] + 16384) >> 15
     np.testing.assert_array_equal(gray.astype(np.float64), g["gray_out"])
+
+
+def test_pipeline_host_buffer_validation():
+    """the host-buffer wrappers hand raw pointers to the C ABI, so dtype / shape / contiguity are checked
+    in Python first (a wrong one would be a silent misread or an out-of-bounds write by an asynchronous copy)."""
+    import torch
+    from slb200.api import Pipeline
+    chk = Pipeline._host_check
+    ok = np.zeros((4, 4), np.float32)
+    assert chk(ok, "cloud", "float32", shape=(None, 4)) is ok
+    assert chk(None, "white_rgb", "uint8", nullable=True) is None
+    with pytest.raises(TypeError):
+        chk(None, "cloud", "float32")
+    with pytest.raises(TypeError):
+        chk(np.zeros((4, 4), np.float64), "cloud", "float32", shape=(None, 4))          # dtype
+    with pytest.raises(ValueError):
+        chk(np.zeros((4, 3), np.float32), "cloud", "float32", shape=(None, 4))          # columns
+    with pytest.raises(ValueError):
+        chk(np.zeros((8, 4), np.float32)[::2], "cloud", "float32", shape=(None, 4))     # strided view
+    with pytest.raises(TypeError):
+        chk(np.zeros(3, np.int32), "counts", "int64", min_elems=3)                      # int32 counts
+    with pytest.raises(ValueError):
+        chk(np.zeros(2, np.int64), "counts", "int64", min_elems=3)                      # too short
+    with pytest.raises(TypeError):
+        chk([1, 2, 3], "counts", "int64")                                               # not an array
+    t = torch.zeros((6, 4), dtype=torch.float32)
+    assert chk(t, "cloud", "float32", shape=(None, 4)) is t
+    with pytest.raises(ValueError):
+        chk(t.t(), "cloud", "float32")                                                  # non-contiguous torch view
+    with pytest.raises(ValueError):
+        chk(np.zeros((2, 5, 4, 4), np.uint8), "h_idx", "uint8", shape=(2, 5, 4, 3))
+
+
+def test_exchange_geometry_and_peer_symbols():
+    """The multi-GPU entry points are exported and their size query behaves (no GPU needed)."""
+    import slb200
+    L = slb200.lib()
+    assert L.sl_exchange_ctrl_bytes(8, 8, 3840) > 8 * 2 * (32 + 8 * 8 + 3840 * 4)
+    assert L.sl_exchange_ctrl_bytes(17, 8, 3840) == 0          # more than SL_MAX_RANKS
+    assert L.sl_exchange_ctrl_bytes(0, 8, 3840) == 0
+    assert L.sl_exchange_ctrl_bytes(8, 0, 3840) == 0
+    assert not hasattr(slb200, "set_decode_sm_reserve")        # options are launch arguments now, no process-wide setter
