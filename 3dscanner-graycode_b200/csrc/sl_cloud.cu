@@ -776,20 +776,20 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
 // loads per warp, twice the tiles, and the column runs of a tile leave two columns at a time (half a warp each).
 // A half-band tile ranks its pixels inside the band's column word as before; its run starts popc(bits below its first
 // row) records into the band's run, so the output is byte-identical to the one-band-per-warp kernel.
-#ifndef SL_EMITF_ROWS
-#define SL_EMITF_ROWS 16
-#endif
+// ROWS = 16 for local clouds; ROWS = 32 (whole bands, runs of up to 512 bytes) when the records go to peer-mapped
+// clouds: NVLink write requests are 128 bytes, a 16-byte-aligned run of 256 bytes wastes 1 request in 3, one of 512
+// bytes 1 in 5 (measured on 2 GPUs: 398 GB/s into the gathering rank with 16-row tiles, 434 GB/s with 32-row tiles).
 #ifndef SL_EMITF_MIN_CTAS
 #define SL_EMITF_MIN_CTAS 6
 #endif
-constexpr int kFastRows = SL_EMITF_ROWS;              // 16 or 32
-constexpr int kFastGroups = kFastRows / 8;            // row groups of 8 rows (a lane owns 4 neighbouring pixels of a row)
-constexpr int kFastParts = kBandRows / kFastRows;     // tiles per band and column block
-constexpr int kFastPitch = kFastRows + 1;             // records per column run in shared memory (+1: bank spread)
-constexpr int kFastSmem = kEmitWarps * kEmitCols * kFastPitch * 16;
+constexpr int fast_smem(int rows) { return kEmitWarps * kEmitCols * (rows + 1) * 16; }
 
-template <bool MULTI>
-__global__ void __launch_bounds__(kEmitWarps * 32, SL_EMITF_MIN_CTAS) emit_fast_kernel(const EmitArgs a) {
+template <int ROWS, bool MULTI>
+__global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTAS : 5) emit_fast_kernel(const EmitArgs a) {
+  constexpr int kFastRows = ROWS;                       // 16 or 32
+  constexpr int kFastGroups = kFastRows / 8;            // row groups of 8 rows (a lane owns 4 neighbouring pixels of a row)
+  constexpr int kFastParts = kBandRows / kFastRows;     // tiles per band and column block
+  constexpr int kFastPitch = kFastRows + 1;             // records per column run in shared memory (+1: bank spread)
   extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMITF_MIN_CTAS) emit_fast_
     my_base = a.col_base[(size_t)b * a.W + x0 + lane] + (long long)a.band_pre[cell + lane];
     if (kFastParts > 1) {
       my_base += __popc(bits32 & ((1u << (part * kFastRows)) - 1u));
-      my_bits = (bits32 >> (part * kFastRows)) & ((1u << kFastRows) - 1u);
+      my_bits = (bits32 >> (part * kFastRows)) & (kFastRows >= 32 ? 0xffffffffu : ((1u << (kFastRows & 31)) - 1u));
     } else {
       my_bits = bits32;
     }
@@ -1085,8 +1085,8 @@ int cloud_device_init() {
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeCloud64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTableBT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
   SL_CUDA(cudaFuncSetAttribute(emit_kernel<kModeTable64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem));
-  SL_CUDA(cudaFuncSetAttribute(emit_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
-  SL_CUDA(cudaFuncSetAttribute(emit_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem));
+  SL_CUDA(cudaFuncSetAttribute(emit_fast_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem(16)));
+  SL_CUDA(cudaFuncSetAttribute(emit_fast_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem(32)));
   return kOk;
 }
 
@@ -1159,11 +1159,12 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
   const int rc = check_emit_size(a);
   if (rc) return rc;
   if (cam_rays && precision == SL_PREC_FP32 && (W % kEmitCols) == 0 && a.aligned) {      // the throughput path
-    a.total_tiles *= kFastParts;
+    const bool peer = remote || n_extra > 0;
+    a.total_tiles *= peer ? 1 : 2;                       // whole bands for peer-mapped clouds, half bands otherwise
     if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one emit launch"); return kErrBadArg; }
     const int gf = grid_for(a.total_tiles, kEmitWarps);
-    if (remote || n_extra > 0) emit_fast_kernel<true><<<gf, thr, kFastSmem, st>>>(a);
-    else SL_CUDA(launch_stage2(emit_fast_kernel<false>, gf, thr, (size_t)kFastSmem, st, a));
+    if (peer) emit_fast_kernel<32, true><<<gf, thr, fast_smem(32), st>>>(a);
+    else SL_CUDA(launch_stage2(emit_fast_kernel<16, false>, gf, thr, (size_t)fast_smem(16), st, a));
     count_launch();
     SL_CUDA(cudaGetLastError());
     return kOk;

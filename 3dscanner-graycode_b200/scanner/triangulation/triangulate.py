@@ -128,9 +128,10 @@ class Triangulate(object):
             check(lib().sl_emit_cloud(_ptr(bufs.h_idx), _ptr(bufs.v_idx), _ptr(white), C.byref(s), _PREC[precision],
                                       None, None, 1, self.cam_h, self.cam_w, _ptr(bufs.ws), _ptr(bufs.cloud), _stream()))
         n = int(bufs.counts[1].item())
-        # widen on the device (IEEE fp64 division: the same values as the reference's uint8 / 255, triangulate.py:69)
+        # widen on the device.  Colours: an IEEE fp64 division by a TENSOR 255 (torch turns a division by a Python
+        # scalar into a multiplication by its reciprocal, which is not the reference's uint8 / 255, triangulate.py:69)
         pts = bufs.xyz[:n].to(torch.float64).t().contiguous().cpu().numpy()
-        colors = (bufs.rgb[:n].to(torch.float64) / 255.0).cpu().numpy()
+        colors = torch.div(bufs.rgb[:n].to(torch.float64), torch.full((1, 1), 255.0, dtype=torch.float64, device=dev)).cpu().numpy()
         return pts, colors
 
 

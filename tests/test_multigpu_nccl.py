@@ -75,6 +75,34 @@ def _worker(rank, world, port, q):
             dist.barrier()                       # the reference run above must not overlap the next step's writes
         ex.close()
 
+    # ---- two exchanges on two streams, batches alternating between them (the gather of one batch beside the compute of
+    # the next): both gathered clouds are complete and exact
+    exs = [CloudExchange(max_scans=max(per_rank), max_width=W, max_points=n_scans * H * W, gather_to=0) for _ in range(2)]
+    sts = [torch.cuda.Stream(dev) for _ in range(2)]
+    refs = []
+    for step in range(4):
+        fr, wh = batch(step)
+        refs.append(slb200.scan_to_cloud(fr, wh, calib, tables=tables))
+    torch.cuda.synchronize()
+    for step in range(4):
+        fr, wh = batch(step)
+        sts[step & 1].wait_stream(torch.cuda.current_stream())       # the inputs were produced on the default stream
+        with torch.cuda.stream(sts[step & 1]):
+            exs[step & 1].scan_to_cloud(fr[lo:hi].contiguous(), wh[lo:hi].contiguous(), calib, tables=tables)
+            fr.record_stream(sts[step & 1]); wh.record_stream(sts[step & 1])
+        if step >= 1 and step % 2 == 1:          # after every pair: both exchanges hold a finished batch
+            torch.cuda.synchronize()
+            for k in range(2):
+                ref = refs[step - 1 + k]
+                nr = int(ref.counts[-1])
+                base, total = exs[k].status()
+                expect(total == nr, f"two-stream exchange step {step - 1 + k}: total")
+                if rank == 0:
+                    expect(same(exs[k].cloud[:nr], ref.cloud[:nr]), f"two-stream exchange step {step - 1 + k}: cloud")
+            dist.barrier()
+    for e_ in exs:
+        e_.close()
+
     # ---- by scan, NCCL
     fr, wh = batch(0)
     ref = slb200.scan_to_cloud(fr, wh, calib, tables=tables)
