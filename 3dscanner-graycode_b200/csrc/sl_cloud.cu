@@ -889,25 +889,41 @@ __global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTA
   }
   __syncwarp();
 
-  // ---- phase B: two columns per step, half a warp each; a column's run is one contiguous block of records
+  // ---- phase B: a column's run is one contiguous block of records.  Half-band tiles: two columns per step, half a warp
+  // each (runs of <= 16 records).  Whole-band tiles (peer-mapped clouds): one column per step, the whole warp on one run
+  // of up to 512 contiguous bytes -- the larger the contiguous store, the fewer partial 128-byte NVLink write requests.
   uint4* out = reinterpret_cast<uint4*>(a.out);
-  const int l16 = lane & 15, hsel = lane >> 4;
+  if (kFastRows == 16) {
+    const int l16 = lane & 15, hsel = lane >> 4;
 #pragma unroll
-  for (int it = 0; it < kEmitCols / 2; ++it) {
-    const int c = 2 * it + hsel;
-    const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, c));
-    const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, c)
-                                   : __shfl_sync(0xffffffffu, my_base, c);
-#pragma unroll
-    for (int q = 0; q < kFastRows / 16; ++q) {
-      const int i = l16 + 16 * q;
-      if (i < cnt) {
-        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + i) * 16u);
+    for (int it = 0; it < kEmitCols / 2; ++it) {
+      const int c = 2 * it + hsel;
+      const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, c));
+      const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, c)
+                                     : __shfl_sync(0xffffffffu, my_base, c);
+      if (l16 < cnt) {
+        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + l16) * 16u);
         if (MULTI) {
-          out[base + i] = rec;
-          for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + i] = rec;
+          out[base + l16] = rec;
+          for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + l16] = rec;
         } else {
-          stg_u4_hint(out + base + i, rec, stream);
+          stg_u4_hint(out + base + l16, rec, stream);
+        }
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int c = 0; c < kEmitCols; ++c) {
+      const int cnt = __popc(__shfl_sync(0xffffffffu, my_bits, c));
+      const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, c)
+                                     : __shfl_sync(0xffffffffu, my_base, c);
+      if (lane < cnt) {
+        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + lane) * 16u);
+        if (MULTI) {
+          out[base + lane] = rec;
+          for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + lane] = rec;
+        } else {
+          stg_u4_hint(out + base + lane, rec, stream);
         }
       }
     }
