@@ -194,3 +194,33 @@ def test_row0_with_a_cached_calibration_struct(T):
     n = int(a.counts[1])
     assert int(b.counts[1]) == n and T.equal(a.cloud[:n].view(T.int32), b.cloud[:n].view(T.int32))
     assert cached.cam_row0 == 0
+
+
+def test_offsets_kernel_many_scans_more_ctas_than_fit(T):
+    """The offsets kernel publishes strip / scan totals and waits for lower-indexed CTAs: a batch with far more CTAs
+    than can be resident at once (B x strips = 1760 CTAs of 512 threads) must complete and match per-scan results."""
+    import slb200
+    rng = np.random.default_rng(11)
+    B, H, W = 160, 40, 330                       # 11 strips per scan (the last one ragged), 2 bands (the last one ragged)
+    hp = rng.integers(-1, 60, (B, H, W)).astype(np.int16)
+    vp = rng.integers(-1, 60, (B, H, W)).astype(np.int16)
+    hp[3] = -1                                    # an empty scan in the middle
+    h_idx, v_idx = T.from_numpy(hp).cuda(), T.from_numpy(vp).cuda()
+    from slb200.api import _Offsets, _ptr, _stream, check, lib
+    off = _Offsets(h_idx, v_idx)
+    T.cuda.synchronize()
+    counts = off.counts.cpu().numpy()
+    valid = (hp != -1) & (vp != -1)
+    want = valid.reshape(B, -1).sum(axis=1)
+    np.testing.assert_array_equal(counts[:B], want)
+    assert counts[B] == want.sum()
+    # pairs emitted for the whole batch == every scan's own x-major pairs, packed scan after scan
+    pairs = T.empty((int(counts[B]), 4), dtype=T.float32, device="cuda")
+    check(lib().sl_emit_pairs(_ptr(h_idx), _ptr(v_idx), None, B, H, W, 64, 64, _ptr(off.ws), _ptr(pairs), None, _stream()))
+    got = pairs.cpu().numpy()
+    start = 0
+    for b in (0, 1, 3, 77, 159):
+        start = int(want[:b].sum())
+        cam, proj, _ = O.cam_proj_pairs(hp[b].astype(np.int64), vp[b].astype(np.int64), (64, 64), None)
+        np.testing.assert_array_equal(got[start:start + int(want[b]), :2], cam)
+        np.testing.assert_array_equal(got[start:start + int(want[b]), 2:], proj)
