@@ -61,6 +61,19 @@ def config_n1(ring_n=RING):
             "l2": f"inputs rotate over a ring of {ring_n} resident scans ({ring_n * N_FRAMES * W * H / 1e6:.0f} MB > 126 MB L2)"}
 
 
+def config_multi(world):
+    """`config` of the N > 1 line, identical in both arms."""
+    W, H = CAM_SIZE
+    per_rank = [(VIEWS // world) + (1 if r < VIEWS % world else 0) for r in range(world)]
+    return {"workload": WORKLOAD_MULTI, "camera": f"{W}x{H}", "projector": f"{PROJ_SIZE[0]}x{PROJ_SIZE[1]}",
+            "frames_per_scan": N_FRAMES, "n_bits": N_BITS, "views": VIEWS, "scans_per_step_per_gpu": per_rank,
+            "step": "the whole 64-view batch: compute on every rank + the compacted clouds gathered on rank 0",
+            "scene": "synthetic textured plane at ~0.9 m, noise sigma 1.5, dark noise band over the left eighth (slb200/synth.py), ~87.6 % valid pixels",
+            "triangulation_precision": "fp32 on the GPU (1e-4 relative), fp64 in the CPU reference",
+            "parallelism": f"scan-sharded x{world}, clouds gathered on rank 0",
+            "l2": f"every rank's views = {max(per_rank) * N_FRAMES * W * H / 1e6:.0f} MB of frames per step (> 126 MB L2)"}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -269,8 +282,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": k, "warmup": w, "ms_per_step": el / k * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_n1(max(2, args.ring)),
+        "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_n1(max(2, args.ring)) if args.gpus <= 1 else config_multi(args.gpus),
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port",
                          "sample": f"per step: one whole 1080p scan (1080 rows, {pts} points) cut into {len(jobs)} bands of rows over {cores} "
                                    "worker processes; oracle/graycode_oracle.py (vectorised NumPy restatement of the reference)"},
@@ -945,12 +958,11 @@ def run_multi(args, torch, slb200, synth, dev, local, rank, world, dist):
             "metric": METRIC, "value": c3["Mpx_per_s"], "unit": "Mpx/s",
             "n_gpus": world, "steps": K, "warmup": max(3, min(args.warmup, 5)), "ms_per_step": c3["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD_MULTI, "frames_per_scan": N_FRAMES, "n_bits": N_BITS,
-                       "scans_per_step_per_gpu": c3["views_per_rank"], "step": "the whole 64-view batch: compute on every rank + gather on rank 0",
-                       "step_variant": c3["step_variant"], "triangulation_precision": "fp32", "lens": "tables",
-                       "parallelism": f"scan-sharded x{world}, clouds gathered on rank 0 (NVLink peer stores from the emit kernel, or NCCL send/recv)",
-                       "l2": c3["l2"],
-                       "single_gpu_reference": "bench.py --gpus 1 reports the same batch on one GPU under multi.config3_64_views_by_scan"},
+            "config": config_multi(world),
+            "run": {"step_variant": c3["step_variant"], "lens": "tables",
+                    "gather": "NVLink peer stores from the emit kernel (slb200.dist.CloudExchange) or NCCL send/recv (gather_clouds); "
+                              "the faster one is the step, all variants are under multi.config3_64_views_by_scan",
+                    "single_gpu_reference": "bench.py --gpus 1 reports the same batch on one GPU under multi.config3_64_views_by_scan"},
             "scans_per_s": c3["scans_per_s"],
             "multi": multi, "e2e": e2e, "clocks": clocks,
             "roofline": c3.get("decode_roofline"),
