@@ -780,16 +780,20 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SL_EMIT_MIN_CTAS) emit_kernel
 // clouds: NVLink write requests are 128 bytes, a 16-byte-aligned run of 256 bytes wastes 1 request in 3, one of 512
 // bytes 1 in 5 (measured on 2 GPUs: 398 GB/s into the gathering rank with 16-row tiles, 434 GB/s with 32-row tiles).
 #ifndef SL_EMITF_MIN_CTAS
-#define SL_EMITF_MIN_CTAS 6
+#define SL_EMITF_MIN_CTAS 7      // <= 73 registers: 7 CTAs (28 warps) per SM; measured 15.0 us against 16.1 us with 6
 #endif
-constexpr int fast_smem(int rows) { return kEmitWarps * kEmitCols * (rows + 1) * 16; }
+constexpr int fast_smem(int rows) { return kEmitWarps * kEmitCols * (rows + 3) * 16; }
 
 template <int ROWS, bool MULTI>
 __global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTAS : 5) emit_fast_kernel(const EmitArgs a) {
   constexpr int kFastRows = ROWS;                       // 16 or 32
   constexpr int kFastGroups = kFastRows / 8;            // row groups of 8 rows (a lane owns 4 neighbouring pixels of a row)
   constexpr int kFastParts = kBandRows / kFastRows;     // tiles per band and column block
-  constexpr int kFastPitch = kFastRows + 1;             // records per column run in shared memory (+1: bank spread)
+  // Run buffer of column c: kFastPitch 16-byte slots starting at slot c * kFastPitch + 2 * (c >> 3).  A quarter warp (the
+  // unit of a 128-bit shared store) holds 2 rows x the 4 column quads c4 = 0, 4, 8, 12; with a pitch = 3 (mod 8) and the
+  // extra 2 slots for the upper 8 columns their 8 records fall into 8 different 16-byte bank groups when the ranks of
+  // neighbouring rows differ by one (the common case); a plain pitch of rows + 1 left every such store 2-way conflicted.
+  constexpr int kFastPitch = kFastRows + 3;             // 19 (16-row tiles) / 35 (32-row tiles): both = 3 (mod 8)
   extern __shared__ __align__(16) uint8_t emit_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kEmitWarps + warp;
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTA
   uint32_t cb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) cb[k] = __shfl_sync(0xffffffffu, my_bits, c4 + k);
-  const uint32_t rec_base = rec_warp + (uint32_t)(c4 * kFastPitch) * 16u;
+  const uint32_t rec_base = rec_warp + (uint32_t)(c4 * kFastPitch + 2 * (c4 >> 3)) * 16u;
 
   uint2 h2[kFastGroups], v2[kFastGroups];
   uint32_t w0[kFastGroups], w1[kFastGroups], w2[kFastGroups];
@@ -902,7 +906,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTA
       const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, c)
                                      : __shfl_sync(0xffffffffu, my_base, c);
       if (l16 < cnt) {
-        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + l16) * 16u);
+        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + 2 * (c >> 3) + l16) * 16u);
         if (MULTI) {
           out[base + l16] = rec;
           for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + l16] = rec;
@@ -918,7 +922,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTA
       const long long base = a.off32 ? (long long)__shfl_sync(0xffffffffu, (unsigned int)my_base, c)
                                      : __shfl_sync(0xffffffffu, my_base, c);
       if (lane < cnt) {
-        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + lane) * 16u);
+        const uint4 rec = lds_u4(rec_warp + (uint32_t)(c * kFastPitch + 2 * (c >> 3) + lane) * 16u);
         if (MULTI) {
           out[base + lane] = rec;
           for (int k = 0; k < a.n_extra; ++k) reinterpret_cast<uint4*>(a.out_extra[k])[base + lane] = rec;
