@@ -320,9 +320,11 @@ int sl_exchange_create(SlExchange** out, int rank, int world, void* const* ctrl_
   if (max_scans < 1 || max_width < 1 || !ctrl_ptrs) { set_error("bad argument"); return kErrBadArg; }
   for (int r = 0; r < world; ++r)
     if (!ctrl_ptrs[r]) { set_error("control block of rank %d is null", r); return kErrBadArg; }
+  int device = 0;
+  SL_CUDA(cudaGetDevice(&device));
   SlExchange* x = new (std::nothrow) SlExchange();
   if (!x) { set_error("out of host memory"); return kErrAlloc; }
-  SL_CUDA(cudaGetDevice(&x->device));
+  x->device = device;
   x->layout = exchange_layout(world, max_scans, max_width);
   memset(&x->args, 0, sizeof(x->args));
   for (int r = 0; r < world; ++r) x->args.ctrl[r] = static_cast<uint8_t*>(ctrl_ptrs[r]);

@@ -129,21 +129,19 @@ def as_u8_stack(images, device=None) -> torch.Tensor:
     return u.to(dev).contiguous()       # blocking: the pinned staging buffer is reused by the next call
 
 
-_PINNED_STAGE = {}
+_PINNED_STAGE = __import__("threading").local()
 
 
 def _pinned_u8(shape) -> torch.Tensor:
-    """Pinned uint8 staging buffer of the drop-in wrappers (one per thread, grown on demand: pinning 95 MB costs
+    """Pinned uint8 staging buffer of the drop-in wrappers (one per host thread, grown on demand: pinning 95 MB costs
     tens of milliseconds, a capture loop narrows a stack of the same size every scan)."""
-    import threading
     n = 1
     for d in shape:
         n *= int(d)
-    key = threading.get_ident()
-    buf = _PINNED_STAGE.get(key)
+    buf = getattr(_PINNED_STAGE, "buf", None)
     if buf is None or buf.numel() < n:
         buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
-        _PINNED_STAGE[key] = buf
+        _PINNED_STAGE.buf = buf
     return buf[:n].view(*shape)
 
 

@@ -353,7 +353,15 @@ class CloudExchange:
             raise RuntimeError(f"cloud exchange: a wait for a peer rank timed out (stage {err.value})")
         return int(base.value), int(total.value)
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def close(self):
+        """Collective: every rank calls it (nobody unmaps while a peer may still write)."""
         from ._lib import lib
         L = lib()
         if getattr(self, "_x", None):
