@@ -33,6 +33,22 @@ def _worker(rank, world, port, q):
     ok = torch.equal(cloud_all, torch.cat(clouds))
     got = [int(c) for r in cnts for c in r[:-1]]
     ok = ok and got == per_scan
+    # gather to one rank, block sizes known up front (no length exchange), into a caller-supplied pre-sized cloud
+    per_rank = [shard_range(n_scans, r, world)[1] - shard_range(n_scans, r, world)[0] for r in range(world)]
+    out = torch.full((sum(per_scan) + 3, 4), -1.0) if rank == 1 else None
+    got_cloud, cnts2 = gather_clouds(mine, counts, dst=1, scans_per_rank=per_rank, out=out)
+    if rank == 1:
+        ok = ok and torch.equal(got_cloud, torch.cat(clouds)) and got_cloud.data_ptr() == out.data_ptr()
+        ok = ok and bool((out[sum(per_scan):] == -1).all())          # nothing written past the gathered records
+    else:
+        ok = ok and got_cloud is None
+    ok = ok and [int(c) for r in cnts2 for c in r[:-1]] == per_scan and [int(r[-1]) for r in cnts2] == [sum(per_scan[a:b]) for a, b in (shard_range(n_scans, r, world) for r in range(world))]
+    # a rank with nothing to contribute
+    empty = torch.zeros((0, 4)) if rank == 0 else mine
+    ecounts = torch.tensor([0, 0], dtype=torch.int64) if rank == 0 else counts
+    g3, _ = gather_clouds(empty, ecounts)
+    want3 = torch.cat(clouds[shard_range(n_scans, 1, world)[0]:])
+    ok = ok and torch.equal(g3, want3)
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
