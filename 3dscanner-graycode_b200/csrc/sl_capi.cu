@@ -235,6 +235,24 @@ int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H,
   return launch_compact_offsets(h_idx, v_idx, B, H, W, workspace, (long long*)counts, (cudaStream_t)stream);
 }
 
+int sl_compact_offsets_boxed(const int16_t* h_idx, const int16_t* v_idx, const SlCalib* calib, int precision,
+                             const float* cam_rays, const float* proj_rays, double threshold, int B, int H, int W,
+                             void* workspace, int64_t* counts, void* stream) {
+  if (!h_idx || !v_idx || !calib || !workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1) { set_error("bad shape"); return kErrBadArg; }
+  if ((cam_rays == nullptr) != (proj_rays == nullptr)) { set_error("cam_rays and proj_rays go together"); return kErrBadArg; }
+  if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
+  if (!(threshold == threshold)) { set_error("threshold is NaN"); return kErrBadArg; }
+  if ((uintptr_t)h_idx % 2 || (uintptr_t)v_idx % 2 || (uintptr_t)workspace % 256 || (uintptr_t)counts % 8 ||
+      (uintptr_t)cam_rays % 8 || (uintptr_t)proj_rays % 8) {
+    set_error("h_idx / v_idx must be 2-byte aligned, workspace 256-byte, counts and the lens tables 8-byte"); return kErrBadArg;
+  }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_compact_offsets_boxed(h_idx, v_idx, *calib, precision, cam_rays, proj_rays, threshold, B, H, W, workspace,
+                                      (long long*)counts, (cudaStream_t)stream);
+}
+
 int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream) {
   if (!workspace || !counts) { set_error("null buffer"); return kErrBadArg; }
   if (B < 1 || H < 1 || W < 1) { set_error("B, H, W must be positive"); return kErrBadArg; }

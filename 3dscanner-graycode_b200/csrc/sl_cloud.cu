@@ -1031,6 +1031,58 @@ __global__ void __launch_bounds__(256) filter_emit_kernel(const void* __restrict
   }
 }
 
+// ------------------------------------------------------------------ box filter as a predicate of the compaction
+// Triangulate.filter_3d_pts (triangulate.py:99-122: keep |x|, |y|, |z| < threshold) folded into the validity bitmap: bit i
+// = pixel i decoded (triangulate.py:56) AND the point the emission will produce for it lies inside the box.  The point
+// is computed by the very device functions the emit kernels use (same inputs, same roundings), so offsets + emission
+// on this bitmap give exactly sl_filter_cloud_box(emission of everything) -- without the unfiltered cloud ever existing.
+template <int MODE>
+__global__ void __launch_bounds__(256) box_bitmap_kernel(const int16_t* __restrict__ h, const int16_t* __restrict__ v,
+                                                          int H, int W, long long words_per_scan, int B,
+                                                          const float2* __restrict__ cam_rays,
+                                                          const float2* __restrict__ proj_rays, const CalibDev cal,
+                                                          double thr, uint32_t* __restrict__ bitmap,
+                                                          unsigned long long* __restrict__ flags, int n_flags) {
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_flags; i += blockDim.x) flags[i] = 0;
+  const long long npix = (long long)H * W;
+  const long long padded = (npix + 31) & ~31LL;
+  const long long total = padded * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / padded, px = i - b * padded;
+    bool ok = false;
+    if (px < npix) {
+      const int hq = h[b * npix + px], vq = v[b * npix + px];
+      if (hq != -1 && vq != -1) {
+        const int y = (int)(px / W), x = (int)(px - (long long)y * W);
+        const int hc = min(cal.proj_w - 1, (int)(uint16_t)hq), vc = min(cal.proj_h - 1, (int)(uint16_t)vq);   // triangulate.py:60-61
+        float X, Y, Z;
+        if (MODE == kModeTableBT32) {
+          const float2 c = __ldg(cam_rays + (size_t)(cal.row0 + y) * W + x);
+          const float2 e = __ldg(proj_rays + (size_t)vc * cal.proj_w + hc);
+          rays_to_point_fp32_bt(c.x, c.y, e.x, e.y, cal.Tf[0], cal.Tf[1], cal.Tf[2], cal.t_len2f, X, Y, Z);
+        } else if (MODE == kModeTable64) {
+          const float2 c = __ldg(cam_rays + (size_t)(cal.row0 + y) * W + x);
+          const float2 p = __ldg(proj_rays + (size_t)vc * cal.proj_w + hc);
+          double dx, dy, dz;
+          rays_to_point_fp64(c.x, c.y, p.x, p.y, cal, dx, dy, dz);
+          X = (float)dx; Y = (float)dy; Z = (float)dz;
+        } else if (MODE == kModeCloud32) {
+          triangulate_fp32((float)x, (float)(cal.row0 + y), (float)hc, (float)vc, cal, X, Y, Z);
+        } else {
+          double dx, dy, dz;
+          triangulate_fp64((float)x, (float)(cal.row0 + y), (float)hc, (float)vc, cal, dx, dy, dz);
+          X = (float)dx; Y = (float)dy; Z = (float)dz;
+        }
+        ok = inside_box((double)X, (double)Y, (double)Z, thr);       // on the f32 record, like sl_filter_cloud_box
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) bitmap[b * words_per_scan + (px >> 5)] = m;
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 // Tuning knob (SL_STAGE2_PRIORITY): launch the stage-2 kernels with the highest stream priority, so that the short
 // offsets / emit kernels of one scan are placed ahead of the pending decode CTAs of the other streams.
@@ -1083,6 +1135,29 @@ int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int
   const long long padded = ((npix + 31) & ~31LL) * B;
   bitmap_from_idx_kernel<<<grid_for(padded, 256, 148 * 16), 256, 0, st>>>(h, v, npix, c.bitmap_words, B, c.bitmap, c.flags, c.n_flags);
   count_launch();
+  return launch_offsets_from_bitmap(B, H, W, ws, counts, st);
+}
+
+int launch_compact_offsets_boxed(const int16_t* h, const int16_t* v, const SlCalib& calib, int precision,
+                                 const float* cam_rays, const float* proj_rays, double threshold, int B, int H, int W,
+                                 void* ws, long long* counts, cudaStream_t st) {
+  const CloudWorkspace c = carve_workspace(ws, B, H, W);
+  const CalibDev cal = make_calib(calib);
+  const long long npix = (long long)H * W;
+  const long long padded = ((npix + 31) & ~31LL) * B;
+  const int g = grid_for(padded, 256, 148 * 16);
+  const float2* cr = (const float2*)cam_rays;
+  const float2* pr = (const float2*)proj_rays;
+  if (cam_rays && precision == SL_PREC_FP32)
+    box_bitmap_kernel<kModeTableBT32><<<g, 256, 0, st>>>(h, v, H, W, c.bitmap_words, B, cr, pr, cal, threshold, c.bitmap, c.flags, c.n_flags);
+  else if (cam_rays)
+    box_bitmap_kernel<kModeTable64><<<g, 256, 0, st>>>(h, v, H, W, c.bitmap_words, B, cr, pr, cal, threshold, c.bitmap, c.flags, c.n_flags);
+  else if (precision == SL_PREC_FP32)
+    box_bitmap_kernel<kModeCloud32><<<g, 256, 0, st>>>(h, v, H, W, c.bitmap_words, B, cr, pr, cal, threshold, c.bitmap, c.flags, c.n_flags);
+  else
+    box_bitmap_kernel<kModeCloud64><<<g, 256, 0, st>>>(h, v, H, W, c.bitmap_words, B, cr, pr, cal, threshold, c.bitmap, c.flags, c.n_flags);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
   return launch_offsets_from_bitmap(B, H, W, ws, counts, st);
 }
 

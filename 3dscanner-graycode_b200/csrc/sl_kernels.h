@@ -51,6 +51,9 @@ CloudWorkspace carve_workspace(void* ws, int B, int H, int W);
 int launch_compact_offsets(const int16_t* h, const int16_t* v, int B, int H, int W, void* ws,
                            long long* counts, cudaStream_t st);
 int launch_offsets_from_bitmap(int B, int H, int W, void* ws, long long* counts, cudaStream_t st);
+int launch_compact_offsets_boxed(const int16_t* h, const int16_t* v, const SlCalib& calib, int precision,
+                                 const float* cam_rays, const float* proj_rays, double threshold, int B, int H, int W,
+                                 void* ws, long long* counts, cudaStream_t st);
 uint32_t* workspace_bitmap(void* ws, int B, int H, int W, long long* words_per_scan, unsigned long long** flags,
                            int* n_flags);
 int launch_emit_pairs(const int16_t* h, const int16_t* v, const uint8_t* white, int B, int H, int W,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "sl_cloud_workspace_bytes": (_sz, [_i, _i, _i]),
     "sl_compact_offsets": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sl_compact_offsets_decoded": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "sl_compact_offsets_boxed": (_i, [_vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _d, _i, _i, _i, _vp, _vp, _vp]),
     "sl_workspace_col_totals": (_vp, [_vp, _i, _i, _i]),
     "sl_emit_pairs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sl_lens_tables": (_i, [C.POINTER(SlCalib), _i, _i, _i, _vp, _vp, _vp]),

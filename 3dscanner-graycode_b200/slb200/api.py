@@ -604,7 +604,7 @@ class LensTables:
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
                   precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
                   calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None,
-                  row0: int = 0, bgr: bool = False, sm_reserve: int = 0) -> CloudBuffers:
+                  row0: int = 0, bgr: bool = False, sm_reserve: int = 0, box: Optional[float] = None) -> CloudBuffers:
     """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
     decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
 
@@ -618,6 +618,10 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
 
     ``sm_reserve``: SMs the persistent decode grid leaves to the kernels of other streams (see ``sl_decode_u8``);
     8 on a B200 when independent scans are pipelined over several CUDA streams, else 0.
+
+    ``box``: Triangulate.filter_3d_pts (triangulate.py:99-122; src/4-triangulate.py:71 uses 0.5) folded into the
+    compaction (``sl_compact_offsets_boxed``): only points with |x|, |y|, |z| < box are counted and emitted, identical
+    to ``filter_cloud_box`` of the unfiltered cloud, which is never materialised.
 
     Results are in the returned buffers: ``cloud[:counts[B]]`` (XYZRGB records; ``.xyz`` / ``.rgb``
     views) packed scan after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
@@ -652,10 +656,19 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     cam_t = _ptr(tables.cam) if tables is not None else None
     proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
     with torch.cuda.device(dev):
+        if bgr and box is not None:
+            raise ValueError("box is not offered together with bgr")
         if bgr:
             check(L.sl_decode_bgr_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
                                      _ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(buffers.ws), int(sm_reserve), st))
             check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
+            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
+                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
+        elif box is not None:
+            check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(buffers.h_idx), _ptr(buffers.v_idx),
+                                 None, None, None, int(sm_reserve), st))
+            check(L.sl_compact_offsets_boxed(_ptr(buffers.h_idx), _ptr(buffers.v_idx), C.byref(s), _PREC[precision], cam_t,
+                                             proj_t, float(box), b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
             check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
                                   _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
         else:

@@ -149,6 +149,16 @@ size_t sl_cloud_workspace_bytes(int B, int H, int W);
 int sl_compact_offsets(const int16_t* h_idx, const int16_t* v_idx, int B, int H, int W,
                        void* workspace, int64_t* counts, void* stream);
 
+/* The same offsets with Triangulate.filter_3d_pts (triangulate.py:99-122, as src/4-triangulate.py:71 applies it with
+ * threshold 0.5) folded in as one more predicate: a pixel counts only if it decoded (triangulate.py:56) AND the point the
+ * emission will produce for it has |x|, |y|, |z| < threshold (strict, compared as doubles on the float record, exactly
+ * like sl_filter_cloud_box).  sl_emit_cloud / sl_emit_pairs on this workspace then emit the filtered cloud directly, in
+ * the reference's order; the unfiltered cloud never exists.  calib / precision / cam_rays / proj_rays as in sl_emit_cloud
+ * (the emission must be called with the same ones: the predicate is evaluated on the very point it will write). */
+int sl_compact_offsets_boxed(const int16_t* h_idx, const int16_t* v_idx, const SlCalib* calib, int precision,
+                             const float* cam_rays, const float* proj_rays, double threshold, int B, int H, int W,
+                             void* workspace, int64_t* counts, void* stream);
+
 /* Same, for a workspace whose validity bitmap was already written by sl_decode_u8 (same B,H,W). */
 int sl_compact_offsets_decoded(int B, int H, int W, void* workspace, int64_t* counts, void* stream);
 

@@ -224,3 +224,41 @@ def test_offsets_kernel_many_scans_more_ctas_than_fit(T):
         cam, proj, _ = O.cam_proj_pairs(hp[b].astype(np.int64), vp[b].astype(np.int64), (64, 64), None)
         np.testing.assert_array_equal(got[start:start + int(want[b]), :2], cam)
         np.testing.assert_array_equal(got[start:start + int(want[b]), 2:], proj)
+
+
+@pytest.mark.parametrize("precision,use_tables", [("fp32", True), ("fp64", True), ("fp32", False), ("fp64", False)])
+def test_box_filter_as_a_predicate_of_the_compaction(T, precision, use_tables):
+    """filter_3d_pts folded into the compaction == the separate filter on the unfiltered cloud, bit
+    for bit (count, order, records), in every triangulation mode; and == the oracle's filter on its own points
+    away from the box faces."""
+    import slb200
+    calib, frames, white = _scan(T, (320, 200), seed=6)
+    tables = slb200.LensTables(calib, (320, 200), frames.device) if use_tables else None
+    full = slb200.scan_to_cloud(frames, white, calib, precision=precision, tables=tables)
+    n = int(full.counts[1])
+    xyz = full.xyz[:n].cpu().numpy().astype(np.float64)
+    for thr in (0.04, float(np.abs(xyz).max(axis=1).mean()), 10.0):
+        want = slb200.filter_cloud_box(full.cloud[:n], thr)
+        got = slb200.scan_to_cloud(frames, white, calib, precision=precision, tables=tables, box=thr)
+        m = int(got.counts[1])
+        assert m == want.shape[0] == int(got.counts[0])
+        assert T.equal(got.cloud[:m].view(T.int32), want.view(T.int32))
+        assert T.equal(got.h_idx, full.h_idx)                    # the decoded indices are untouched by the filter
+    assert 0 < int(slb200.scan_to_cloud(frames, white, calib, precision=precision, tables=tables,
+                                        box=float(np.abs(xyz).max(axis=1).mean())).counts[1]) < n
+    # a batch, and against the oracle's filter (points farther than 1e-6 from a face cannot flip)
+    fr2 = T.stack([frames, frames]).contiguous(); wh2 = T.stack([white, white]).contiguous()
+    thr = float(np.median(np.abs(xyz).max(axis=1)))
+    got2 = slb200.scan_to_cloud(fr2, wh2, calib, precision=precision, tables=tables, box=thr)
+    c = got2.counts.cpu().numpy()
+    assert c[0] == c[1] and c[2] == 2 * c[0]
+    hp, vp = O.decode_pixels(frames.cpu().numpy().astype(np.float64))
+    cam, proj, col = O.cam_proj_pairs(hp, vp, calib.proj_size, white.cpu().numpy())
+    pts = O.triangulate(cam, proj, calib.cam_mtx, calib.cam_dist, calib.proj_mtx, calib.proj_dist, calib.proj_R, calib.proj_T)
+    kept = np.all(np.abs(pts) < thr, axis=0)                     # the oracle's filter_3d_pts mask on its own points
+    safe = np.abs(np.abs(pts) - thr).min(axis=0) > 2e-4 * np.abs(pts).max()   # farther from a face than the fp32 tolerance
+    mine_kept = np.all(np.abs(xyz) < thr, axis=1)                # the records the GPU kept (== want above, bit for bit)
+    assert int(mine_kept.sum()) == int(c[0]) and safe.sum() > 0.9 * n
+    assert np.array_equal(mine_kept[safe], kept[safe])
+    pts_f, _ = O.filter_3d_pts(pts[:, safe], col[safe], thr)
+    assert pts_f.shape[1] == int(mine_kept[safe].sum())
