@@ -14,10 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libslb200.so")
-SOURCES = ["sl_decode.cu", "sl_cloud.cu", "sl_frames.cu", "sl_outlier.cu", "sl_peer.cu", "sl_capi.cu"]
+SOURCES = ["sl_decode.cu", "sl_cloud.cu", "sl_frames.cu", "sl_outlier.cu", "sl_peer.cu", "sl_host.cu", "sl_capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xptxas=-v", "-shared", "-Xcompiler", "-fPIC",
+    "-Xptxas=-v", "-shared", "-Xcompiler", "-fPIC,-pthread",
 ]
 
 

@@ -135,7 +135,7 @@ def codes_to_pixels(h_codes, v_codes):
     h = torch.as_tensor(np.ascontiguousarray(np.asarray(h_codes, dtype=np.int8))).to(dev)
     v = torch.as_tensor(np.ascontiguousarray(np.asarray(v_codes, dtype=np.int8))).to(dev)
     h_idx, v_idx = slb200.codes_to_pixels(h, v)
-    return h_idx.cpu().numpy().astype(np.int64), v_idx.cpu().numpy().astype(np.int64)
+    return slb200.api.idx_to_host_int64(h_idx), slb200.api.idx_to_host_int64(v_idx)
 
 
 def decode_pixels(images, runs=None, eps=1):
@@ -150,4 +150,4 @@ def decode_pixels(images, runs=None, eps=1):
         codes = [slb200.decode_codes(_stack(r), eps=float(eps))[:2] for r in runs]
         h_idx, v_idx = slb200.codes_to_pixels(torch.stack([c[0] for c in codes]).contiguous(),
                                               torch.stack([c[1] for c in codes]).contiguous())
-    return h_idx.cpu().numpy().astype(np.int64), v_idx.cpu().numpy().astype(np.int64)
+    return slb200.api.idx_to_host_int64(h_idx), slb200.api.idx_to_host_int64(v_idx)

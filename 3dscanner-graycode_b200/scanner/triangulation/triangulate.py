@@ -128,10 +128,9 @@ class Triangulate(object):
             check(lib().sl_emit_cloud(_ptr(bufs.h_idx), _ptr(bufs.v_idx), _ptr(white), C.byref(s), _PREC[precision],
                                       None, None, 1, self.cam_h, self.cam_w, _ptr(bufs.ws), _ptr(bufs.cloud), _stream()))
         n = int(bufs.counts[1].item())
-        # widen on the device.  Colours: an IEEE fp64 division by a TENSOR 255 (torch turns a division by a Python
-        # scalar into a multiplication by its reciprocal, which is not the reference's uint8 / 255, triangulate.py:69)
-        pts = bufs.xyz[:n].to(torch.float64).t().contiguous().cpu().numpy()
-        colors = torch.div(bufs.rgb[:n].to(torch.float64), torch.full((1, 1), 255.0, dtype=torch.float64, device=dev)).cpu().numpy()
+        # 16 bytes per point cross PCIe; the float64 (3,N) / (N,3) arrays of the reference are produced on the host
+        # (sl_host_unpack_cloud: exact widening, colours = uint8 / 255 as an IEEE division, triangulate.py:69)
+        pts, colors = slb200.api.cloud_to_host_f64(bufs.cloud[:n])
         return pts, colors
 
 

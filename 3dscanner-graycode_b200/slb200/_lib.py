@@ -84,6 +84,10 @@ SIGNATURES = {
                                 _vp]),
     "sl_exchange_arrive": (_i, [_vp, C.c_uint32, _i, _vp]),
     "sl_exchange_status": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64)]),
+    "sl_host_narrow_u8": (_i, [_vp, _i, _sz, _vp, _i]),
+    "sl_host_widen_idx": (_i, [_vp, _sz, _vp, _i]),
+    "sl_host_narrow_idx": (_i, [_vp, _sz, _vp, _i]),
+    "sl_host_unpack_cloud": (_i, [_vp, _i64, _vp, _vp, _i]),
     "sl_launch_count": (_i64, []),
 }
 

@@ -116,6 +116,14 @@ def as_u8_stack(images, device=None) -> torch.Tensor:
     # Narrow where the data is: a float64 stack is 8x the bytes of the uint8 samples it holds (763 MB for one 1080p
     # scan), so a host stack is validated and narrowed frame by frame on the host (torch CPU ops, multi-threaded)
     # into one pinned uint8 buffer and only that crosses PCIe.
+    if not t.is_cuda and t.dtype in (torch.float64, torch.float32) and t.is_contiguous():
+        # the reference's own stack dtype: one multi-threaded host pass (convert + validate) into pinned staging
+        u = _pinned_u8(t.shape)
+        rc = lib().sl_host_narrow_u8(t.data_ptr(), 0 if t.dtype == torch.float64 else 1, t.numel(), u.data_ptr(), 0)
+        if rc:
+            raise ValueError("frame stack must hold integer grey levels in 0..255 "
+                             "(the B200 path computes on uint8 samples)")
+        return u.to(dev).contiguous()   # blocking: the pinned staging buffer is reused by the next call
     u = torch.empty(t.shape, dtype=torch.uint8, device=t.device) if t.is_cuda else _pinned_u8(t.shape)
     planes = t.reshape(-1, *t.shape[-2:]) if t.dim() >= 3 else t.reshape(1, -1)
     u_planes = u.reshape(planes.shape)
@@ -143,6 +151,39 @@ def _pinned_u8(shape) -> torch.Tensor:
         buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
         _PINNED_STAGE.buf = buf
     return buf[:n].view(*shape)
+
+
+def _pinned_stage(name: str, nbytes: int) -> torch.Tensor:
+    """Named pinned byte buffer of the calling host thread (grown on demand) for device -> host results."""
+    buf = getattr(_PINNED_STAGE, name, None)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        setattr(_PINNED_STAGE, name, buf)
+    return buf[:nbytes]
+
+
+def idx_to_host_int64(idx: torch.Tensor) -> np.ndarray:
+    """Device int16 index image(s) -> the reference's int64 NumPy array (decode_codes.py:189-229 returns Python ints
+    that the script stores in int64 arrays): int16 over PCIe into pinned staging, widened by sl_host_widen_idx."""
+    idx = idx.contiguous()
+    stage = _pinned_stage("idx", idx.numel() * 2).view(torch.int16)
+    stage.copy_(idx.reshape(-1))                    # blocking (pinned destination, synchronises the stream)
+    out = np.empty(tuple(idx.shape), dtype=np.int64)
+    check(lib().sl_host_widen_idx(stage.data_ptr(), idx.numel(), out.ctypes.data, 0))
+    return out
+
+
+def cloud_to_host_f64(cloud: torch.Tensor, colors: bool = True):
+    """Device ``(n,4)`` packed records -> ``pts (3,n) float64[, colors (n,3) float64]`` NumPy arrays, the return types
+    of Triangulate.triangulate / get_cam_proj_pts (triangulate.py:64-69,95): 16 bytes per point over PCIe into pinned
+    staging, unpacked by sl_host_unpack_cloud (exact widening; colours = channel / 255 as an IEEE division)."""
+    n = int(cloud.shape[0])
+    stage = _pinned_stage("cloud", n * 16).view(torch.float32).view(n, 4)
+    stage.copy_(cloud)
+    pts = np.empty((3, n), dtype=np.float64)
+    col = np.empty((n, 3), dtype=np.float64) if colors else None
+    check(lib().sl_host_unpack_cloud(stage.data_ptr(), n, pts.ctypes.data, col.ctypes.data if colors else None, 0))
+    return (pts, col) if colors else pts
 
 
 def _stack_dims(frames: torch.Tensor):
@@ -365,6 +406,12 @@ def codes_to_pixels(h_codes: torch.Tensor, v_codes: torch.Tensor):
 def _idx16(t, device) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         a = np.asarray(t)
+        if a.dtype == np.int64 and a.flags.c_contiguous and a.size:
+            # the reference's h_pixels / v_pixels dtype: range check + narrowing in one multi-threaded host pass
+            out = np.empty(a.shape, dtype=np.int16)
+            if lib().sl_host_narrow_idx(a.ctypes.data, a.size, out.ctypes.data, 0):
+                raise ValueError("decoded indices must lie in -1..32767")
+            return torch.from_numpy(out).to(device).contiguous()
         if a.size and (a.min() < -1 or a.max() > 32767):
             raise ValueError("decoded indices must lie in -1..32767")
         t = torch.from_numpy(np.ascontiguousarray(a.astype(np.int16)))

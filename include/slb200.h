@@ -363,6 +363,22 @@ int sl_exchange_arrive(SlExchange* x, uint32_t dst_mask, int wait, void* stream)
  * step are then invalid); rank_base / grand_total (nullable) = this rank's first record and the total of the last step. */
 int sl_exchange_status(SlExchange* x, int* error, int64_t* rank_base, int64_t* grand_total);
 
+/* ---- Host-side conversions at the NumPy boundary of the reference API (no device work) ----------------------------------
+ * The reference's scripts hand over a float64 frame stack (src/3-capture_decode.py:66-70) and expect int64 index images
+ * (decode_codes.py:189-229), a (3,N) float64 point array (triangulate.py:95) and (N,3) float64 colours (:64-69).  These
+ * do the dtype changes in one multi-threaded host pass each (threads <= 0: one per hardware thread, at most 32), from /
+ * into pinned staging, so that only uint8 samples, int16 indices and 16-byte records cross PCIe.  Exact or an error. */
+
+/* src (src_type 0 = float64, 1 = float32; n values) -> uint8.  SL_ERR_BAD_ARG if any value is not an integer in 0..255. */
+int sl_host_narrow_u8(const void* src, int src_type, size_t n, uint8_t* dst, int threads);
+/* int16 indices -> the reference's int64 h_pixels / v_pixels. */
+int sl_host_widen_idx(const int16_t* src, size_t n, int64_t* dst, int threads);
+/* int64 h_pixels / v_pixels -> int16.  SL_ERR_BAD_ARG if any value lies outside -1..32767. */
+int sl_host_narrow_idx(const int64_t* src, size_t n, int16_t* dst, int threads);
+/* n packed records (host) -> xyz_3xn: (3,n) float64 row-major (= Triangulate.triangulate's return) and, if non-null,
+ * colors_nx3: (n,3) float64 = channel / 255 as an IEEE double division (triangulate.py:69). */
+int sl_host_unpack_cloud(const float* cloud, int64_t n, double* xyz_3xn, double* colors_nx3, int threads);
+
 /* Number of kernels this library has launched in the calling process (all streams). */
 int64_t sl_launch_count(void);
 

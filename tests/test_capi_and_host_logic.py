@@ -226,3 +226,55 @@ def test_exchange_geometry_and_peer_symbols():
     assert L.sl_exchange_ctrl_bytes(0, 8, 3840) == 0
     assert L.sl_exchange_ctrl_bytes(8, 0, 3840) == 0
     assert not hasattr(slb200, "set_decode_sm_reserve")        # options are launch arguments now, no process-wide setter
+
+
+def test_host_conversions_at_the_numpy_boundary():
+    """sl_host_*: the dtype changes between the reference's NumPy types (float64 stack, int64 indices, (3,N) / (N,3)
+    float64 outputs) and what crosses PCIe; host-only code, so it runs here.  Exact or an error."""
+    from slb200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(5)
+    for dt, code in ((np.float64, 0), (np.float32, 1)):
+        u = rng.integers(0, 256, (6, 37, 53), dtype=np.uint8)
+        u.reshape(-1)[:256] = np.arange(256)
+        src = u.astype(dt)
+        for threads in (0, 1, 3):
+            out = np.full(u.shape, 77, np.uint8)
+            assert L.sl_host_narrow_u8(src.ctypes.data, code, src.size, out.ctypes.data, threads) == 0
+            assert np.array_equal(out, u)
+        for bad in (0.5, -1.0, 256.0, 300.0, np.nan, np.inf, -np.inf, 1e300 if dt is np.float64 else 1e30, -0.25, 254.999):
+            s2 = src.copy()
+            s2.reshape(-1)[rng.integers(0, s2.size)] = bad
+            assert L.sl_host_narrow_u8(s2.ctypes.data, code, s2.size, out.ctypes.data, 0) == -1, bad
+            assert b"0..255" in L.sl_last_error()
+        s2 = src.copy(); s2.reshape(-1)[5] = -0.0          # -0.0 == 0: a valid grey level
+        assert L.sl_host_narrow_u8(s2.ctypes.data, code, s2.size, out.ctypes.data, 0) == 0 and out.reshape(-1)[5] == 0
+    assert L.sl_host_narrow_u8(None, 0, 0, None, 0) == 0      # empty
+    assert L.sl_host_narrow_u8(src.ctypes.data, 7, 4, out.ctypes.data, 0) == -1
+
+    idx = rng.integers(-1, 32768, (211, 97)).astype(np.int16)
+    wide = np.empty(idx.shape, np.int64)
+    assert L.sl_host_widen_idx(idx.ctypes.data, idx.size, wide.ctypes.data, 0) == 0
+    assert np.array_equal(wide, idx.astype(np.int64))
+    back = np.empty(idx.shape, np.int16)
+    assert L.sl_host_narrow_idx(wide.ctypes.data, wide.size, back.ctypes.data, 2) == 0 and np.array_equal(back, idx)
+    for bad in (-2, 32768, 1 << 40, -(1 << 40)):
+        w2 = wide.copy(); w2[3, 4] = bad
+        assert L.sl_host_narrow_idx(w2.ctypes.data, w2.size, back.ctypes.data, 0) == -1
+
+    n = 70001
+    cloud = rng.standard_normal((n, 4)).astype(np.float32)
+    cloud[:, :3] *= np.float32(1e3)
+    cloud[7, 0] = np.float32(np.nan); cloud[8, 1] = np.float32(np.inf)      # nan / inf points (parallel rays) pass through
+    rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    rgb[:256, 0] = np.arange(256)
+    cloud[:, 3] = (rgb[:, 0].astype(np.uint32) | (rgb[:, 1].astype(np.uint32) << 8) | (rgb[:, 2].astype(np.uint32) << 16)).view(np.float32)
+    for threads in (0, 1):
+        pts = np.empty((3, n)); col = np.empty((n, 3))
+        assert L.sl_host_unpack_cloud(cloud.ctypes.data, n, pts.ctypes.data, col.ctypes.data, threads) == 0
+        assert np.array_equal(pts, cloud[:, :3].astype(np.float64).T, equal_nan=True)
+        assert np.array_equal(col, rgb / 255)                  # the reference's img_white[j, i, :] / 255 (triangulate.py:69)
+    pts2 = np.empty((3, n))
+    assert L.sl_host_unpack_cloud(cloud.ctypes.data, n, pts2.ctypes.data, None, 0) == 0
+    assert np.array_equal(pts2, pts, equal_nan=True)
+    assert L.sl_host_unpack_cloud(None, 0, None, None, 0) == 0
