@@ -405,6 +405,7 @@ struct SlPipeline {
     cudaStream_t stream = nullptr;
     cudaEvent_t counted = nullptr;
     uint8_t* frames = nullptr;   // [F][H][W]
+    uint8_t* frames_bgr = nullptr;   // [F][H][W][3], allocated by the first sl_pipeline_submit_bgr on the slot
     uint8_t* white = nullptr;    // [H][W][3]
     int16_t* h = nullptr;
     int16_t* v = nullptr;
@@ -437,7 +438,7 @@ static void pipeline_free(SlPipeline* p) {
   cudaSetDevice(p->device);
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    cudaFree(s.frames); cudaFree(s.white); cudaFree(s.h); cudaFree(s.v); cudaFree(s.ws);
+    cudaFree(s.frames); cudaFree(s.frames_bgr); cudaFree(s.white); cudaFree(s.h); cudaFree(s.v); cudaFree(s.ws);
     cudaFree(s.counts); cudaFreeHost(s.counts_pinned); cudaFree(s.cloud);
     if (s.counted) cudaEventDestroy(s.counted);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -609,8 +610,9 @@ static int pipeline_retire(SlPipeline* p, SlPipeline::Slot& s) {
   return kOk;
 }
 
-int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host, const SlCalib* calib,
-                       int precision, double eps, float* cloud_host, int64_t cap_points, int64_t* count_host) {
+static int pipeline_submit(SlPipeline* p, const uint8_t* frames_host, bool bgr, const uint8_t* white_rgb_host,
+                           const SlCalib* calib, int precision, double eps, float* cloud_host, int64_t cap_points,
+                           int64_t* count_host) {
   if (!p || !frames_host || !calib || !cloud_host || !count_host) { set_error("null argument"); return kErrBadArg; }
   if (precision != SL_PREC_FP32 && precision != SL_PREC_FP64) { set_error("bad precision %d", precision); return kErrBadArg; }
   DeviceGuard guard;
@@ -618,17 +620,20 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
   int rc = pipeline_tables(p, calib, precision);
   if (rc) return rc;
   const size_t npix = (size_t)p->H * p->W;
-  const size_t stack = (size_t)p->F * npix;
+  const size_t frame = bgr ? npix * 3 : npix;
+  const size_t stack = (size_t)p->F * frame;
   auto& s = p->slot[p->submitted % SlPipeline::kSlots];
   if ((rc = pipeline_retire(p, s))) return rc;        // the scan submitted kSlots calls ago leaves the slot first
-  SL_CUDA(cudaMemcpyAsync(s.frames, frames_host, stack, cudaMemcpyHostToDevice, s.stream));
+  if (bgr && !s.frames_bgr) SL_CUDA(cudaMalloc(&s.frames_bgr, stack));     // first colour scan on this slot
+  uint8_t* dev_frames = bgr ? s.frames_bgr : s.frames;
+  SL_CUDA(cudaMemcpyAsync(dev_frames, frames_host, stack, cudaMemcpyHostToDevice, s.stream));
   if (white_rgb_host) SL_CUDA(cudaMemcpyAsync(s.white, white_rgb_host, npix * 3, cudaMemcpyHostToDevice, s.stream));
   long long bm_words = 0;
   unsigned long long* flags = nullptr;
   int n_flags = 0;
   uint32_t* bm = workspace_bitmap(s.ws, 1, p->H, p->W, &bm_words, &flags, &n_flags);
-  if ((rc = launch_decode(s.frames, 1, p->F, (long long)npix, npix, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
-                          flags, n_flags, p->sms, s.stream, false, p->sm_reserve))) return rc;
+  if ((rc = launch_decode(dev_frames, 1, p->F, (long long)npix, frame, stack, eps, s.h, s.v, nullptr, nullptr, bm, bm_words,
+                          flags, n_flags, p->sms, s.stream, bgr, p->sm_reserve))) return rc;
   if ((rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream))) return rc;
   SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
   if ((rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
@@ -638,6 +643,17 @@ int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t*
   s.user_cloud = cloud_host; s.user_cap = cap_points; s.user_count = count_host;
   ++p->submitted;
   return kOk;
+}
+
+int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host, const SlCalib* calib,
+                       int precision, double eps, float* cloud_host, int64_t cap_points, int64_t* count_host) {
+  return pipeline_submit(p, frames_host, false, white_rgb_host, calib, precision, eps, cloud_host, cap_points, count_host);
+}
+
+int sl_pipeline_submit_bgr(SlPipeline* p, const uint8_t* frames_bgr_host, const uint8_t* white_rgb_host,
+                           const SlCalib* calib, int precision, double eps, float* cloud_host, int64_t cap_points,
+                           int64_t* count_host) {
+  return pipeline_submit(p, frames_bgr_host, true, white_rgb_host, calib, precision, eps, cloud_host, cap_points, count_host);
 }
 
 int sl_pipeline_flush(SlPipeline* p) {

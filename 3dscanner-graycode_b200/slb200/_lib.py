@@ -68,6 +68,7 @@ SIGNATURES = {
     "sl_pipeline_set_sm_reserve": (_i, [_vp, _i]),
     "sl_scan_to_cloud_host": (_i, [_vp, _vp, _vp, _i, C.POINTER(SlCalib), _i, _d, _vp, _vp, _vp, _i64, _vp]),
     "sl_pipeline_submit": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _d, _vp, _i64, _vp]),
+    "sl_pipeline_submit_bgr": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _d, _vp, _i64, _vp]),
     "sl_pipeline_flush": (_i, [_vp]),
     "sl_decode_host": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp]),
     "sl_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),

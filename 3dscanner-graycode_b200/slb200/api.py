@@ -826,19 +826,22 @@ class Pipeline:
         n = int(counts[b])
         return cloud[:n], counts
 
-    def submit(self, frames, white_rgb, calib: Calibration, cloud, count, precision="fp32", eps: float = 1.0):
+    def submit(self, frames, white_rgb, calib: Calibration, cloud, count, precision="fp32", eps: float = 1.0,
+               bgr: bool = False):
         """Streaming form (``sl_pipeline_submit``): queue ONE scan ``(F,H,W)`` uint8 (host, ideally pinned) and
         return; its records go to the host tensor ``cloud`` ``(cap,4)`` f32 and its point count to ``count``
         (int64 host tensor / array of one element).  Results are valid after :meth:`flush`; the buffers must
-        stay alive until then."""
-        self._host_check(frames, "frames", "uint8", shape=(self.f, self.h, self.w))
+        stay alive until then.  ``bgr=True`` (``sl_pipeline_submit_bgr``): ``frames`` is ``(F,H,W,3)`` 8-bit BGR as
+        the camera delivers it; cv2's BGR2GRAY happens inside the decode load, bit-identical."""
+        fshape = (self.f, self.h, self.w, 3) if bgr else (self.f, self.h, self.w)
+        self._host_check(frames, "frames", "uint8", shape=fshape)
         self._host_check(white_rgb, "white_rgb", "uint8", shape=(self.h, self.w, 3), nullable=True)
         self._host_check(cloud, "cloud", "float32", shape=(None, 4))
         self._host_check(count, "count", "int64", min_elems=1)
         s = calib.struct()
-        check(lib().sl_pipeline_submit(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), C.byref(s),
-                                       _PREC[precision], float(eps), self._host_ptr(cloud), int(cloud.shape[0]),
-                                       self._host_ptr(count)))
+        fn = lib().sl_pipeline_submit_bgr if bgr else lib().sl_pipeline_submit
+        check(fn(self._h, self._host_ptr(frames), self._host_ptr(white_rgb), C.byref(s), _PREC[precision], float(eps),
+                 self._host_ptr(cloud), int(cloud.shape[0]), self._host_ptr(count)))
 
     def flush(self):
         """Wait until every submitted scan's cloud and count are in host memory (``sl_pipeline_flush``)."""

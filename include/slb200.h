@@ -289,6 +289,12 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
 int sl_pipeline_submit(SlPipeline* p, const uint8_t* frames_host, const uint8_t* white_rgb_host,
                        const SlCalib* calib, int precision, double eps, float* cloud_host, int64_t cap_points,
                        int64_t* count_host);
+/* sl_pipeline_submit for a capture loop's own frames: frames_bgr_host u8 [F][H][W][3], 8-bit BGR as cv2.VideoCapture
+ * delivers them.  cv2.cvtColor(frame, COLOR_BGR2GRAY) (src/3-capture_decode.py:66, decode_codes.py:86) happens inside
+ * the decode load (as in sl_decode_bgr_u8), bit-identical; 3x the PCIe bytes, no host pass over the frames. */
+int sl_pipeline_submit_bgr(SlPipeline* p, const uint8_t* frames_bgr_host, const uint8_t* white_rgb_host,
+                           const SlCalib* calib, int precision, double eps, float* cloud_host, int64_t cap_points,
+                           int64_t* count_host);
 int sl_pipeline_flush(SlPipeline* p);
 
 /* Decode only, HOST buffers (get_codes + gray_to_decimal loops for one or more scans). */

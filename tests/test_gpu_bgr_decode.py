@@ -138,3 +138,39 @@ def test_bgr_identity_full_size_4k():
     xs = torch.arange(3840, device="cuda", dtype=torch.int16)[None, :].expand(2160, 3840)
     ys = torch.arange(2160, device="cuda", dtype=torch.int16)[:, None].expand(2160, 3840)
     assert torch.equal(h, xs) and torch.equal(v, ys)
+
+
+def test_pipeline_submit_bgr_matches_gray_submit():
+    """sl_pipeline_submit_bgr (the camera's BGR frames in host memory, more scans than the pipeline has slots, mixed with
+    gray submits on the same pipeline) == cv2-formula gray on the host + sl_pipeline_submit, bit for bit."""
+    import torch
+    import slb200
+    from slb200 import synth
+    cam_size, proj_size = (320, 200), (1024, 768)
+    calib = synth.synthetic_calibration(cam_size, proj_size)
+    rng = np.random.default_rng(11)
+    scans = [synth.render_scan(cam_size, proj_size, seed=s, device="cpu") for s in range(5)]
+    bgrs = [torch.from_numpy(colourise(rng, s[0].numpy())).pin_memory() for s in scans]
+    grays = [torch.from_numpy(gray_of(b.numpy())).pin_memory() for b in bgrs]
+    whites = [s[1].contiguous().pin_memory() for s in scans]
+    f = bgrs[0].shape[0]
+    pipe = slb200.Pipeline(f, 200, 320, max_batch=1)
+    cl_b = [torch.zeros((200 * 320, 4), dtype=torch.float32).pin_memory() for _ in scans]
+    cl_g = [torch.zeros((200 * 320, 4), dtype=torch.float32).pin_memory() for _ in scans]
+    n_b = [torch.zeros(1, dtype=torch.int64) for _ in scans]
+    n_g = [torch.zeros(1, dtype=torch.int64) for _ in scans]
+    for i in range(5):
+        pipe.submit(bgrs[i], whites[i], calib, cl_b[i], n_b[i], bgr=True)
+        pipe.submit(grays[i], whites[i], calib, cl_g[i], n_g[i])
+    pipe.flush()
+    for i in range(5):
+        n = int(n_g[i])
+        assert int(n_b[i]) == n and n > 0
+        assert torch.equal(cl_b[i][:n].view(torch.int32), cl_g[i][:n].view(torch.int32))
+    hp, vp = oracle_pixels(grays[0].numpy())
+    assert int(n_g[0]) == int(((hp != -1) & (vp != -1)).sum())
+    with pytest.raises(ValueError):
+        pipe.submit(grays[0], whites[0], calib, cl_b[0], n_b[0], bgr=True)        # a gray stack handed in as BGR
+    with pytest.raises(ValueError):
+        pipe.submit(bgrs[0], whites[0], calib, cl_b[0], n_b[0])
+    pipe.close()
