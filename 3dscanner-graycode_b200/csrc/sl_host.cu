@@ -10,6 +10,9 @@
 #include <cstdint>
 #include <cstring>
 #include <thread>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 #include <vector>
 #include "sl_common.cuh"
 
@@ -55,11 +58,54 @@ size_t narrow_u8_range(const T* src, uint8_t* dst, size_t b, size_t e) {
   return bad;
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#define SL_HOST_AVX2 1
+// 8 doubles per step: truncate to int32 (out-of-range and NaN give INT_MIN), require the round trip to be exact and the
+// integer to be in 0..255, pack to bytes.  The plain loop above costs ~2.5 ns per sample and thread; this one is
+// bound by reading the stack.
+__attribute__((target("avx2"))) size_t narrow_f64_avx2(const double* src, uint8_t* dst, size_t b, size_t e) {
+  size_t i = b;
+  __m256i bad = _mm256_setzero_si256();
+  const __m128i hi = _mm_set1_epi32(~255);
+  for (; i + 8 <= e; i += 8) {
+    const __m256d a = _mm256_loadu_pd(src + i), c = _mm256_loadu_pd(src + i + 4);
+    const __m128i ia = _mm256_cvttpd_epi32(a), ic = _mm256_cvttpd_epi32(c);
+    const __m256d ne_a = _mm256_cmp_pd(_mm256_cvtepi32_pd(ia), a, _CMP_NEQ_UQ);     // unordered (NaN) counts as different
+    const __m256d ne_c = _mm256_cmp_pd(_mm256_cvtepi32_pd(ic), c, _CMP_NEQ_UQ);
+    bad = _mm256_or_si256(bad, _mm256_castpd_si256(_mm256_or_pd(ne_a, ne_c)));
+    const __m128i out_of_range = _mm_and_si128(_mm_or_si128(ia, ic), hi);           // any bit above 255, or negative
+    bad = _mm256_or_si256(bad, _mm256_castsi128_si256(out_of_range));
+    const __m128i w = _mm_packs_epi32(ia, ic);                                      // 8 x int16
+    _mm_storel_epi64(reinterpret_cast<__m128i*>(dst + i), _mm_packus_epi16(w, w));  // 8 x uint8
+  }
+  size_t nbad = _mm256_testz_si256(bad, bad) ? 0 : 1;
+  if (nbad) {                        // recount exactly (the error message reports how many)
+    nbad = 0;
+    for (size_t k = b; k < i; ++k) {
+      const double v = src[k];
+      const bool in = (v >= 0.0) && (v <= 255.0);
+      nbad += (size_t)!(in && (double)(uint8_t)(int)(in ? v : 0.0) == v);
+    }
+  }
+  return nbad + narrow_u8_range(src, dst, i, e);
+}
+#endif
+
+template <class T>
+size_t narrow_u8_dispatch(const T* src, uint8_t* dst, size_t b, size_t e) { return narrow_u8_range(src, dst, b, e); }
+#if defined(SL_HOST_AVX2)
+template <>
+size_t narrow_u8_dispatch<double>(const double* src, uint8_t* dst, size_t b, size_t e) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  return avx2 ? narrow_f64_avx2(src, dst, b, e) : narrow_u8_range(src, dst, b, e);
+}
+#endif
+
 template <class T>
 int narrow_u8(const T* src, uint8_t* dst, size_t n, int threads) {
   std::atomic<size_t> bad{0};
   parallel_chunks(n, pick_threads(threads, n, 1u << 16), 64, [&](size_t b, size_t e) {
-    const size_t k = narrow_u8_range(src, dst, b, e);
+    const size_t k = narrow_u8_dispatch(src, dst, b, e);
     if (k) bad.fetch_add(k, std::memory_order_relaxed);
   });
   if (bad.load()) {

@@ -249,6 +249,17 @@ def test_host_conversions_at_the_numpy_boundary():
             assert b"0..255" in L.sl_last_error()
         s2 = src.copy(); s2.reshape(-1)[5] = -0.0          # -0.0 == 0: a valid grey level
         assert L.sl_host_narrow_u8(s2.ctypes.data, code, s2.size, out.ctypes.data, 0) == 0 and out.reshape(-1)[5] == 0
+    # several threads, a length that is no multiple of the vector width or the chunk grain, bad samples at the ends
+    big = rng.integers(0, 256, 1_000_003, dtype=np.uint8)
+    src = big.astype(np.float64)
+    out = np.zeros_like(big)
+    for threads in (0, 2, 7):
+        assert L.sl_host_narrow_u8(src.ctypes.data, 0, src.size, out.ctypes.data, threads) == 0
+        assert np.array_equal(out, big)
+    for pos in (0, 7, 8, src.size // 2, src.size - 9, src.size - 1):
+        s2 = src.copy(); s2[pos] = 255.5
+        assert L.sl_host_narrow_u8(s2.ctypes.data, 0, s2.size, out.ctypes.data, 7) == -1, pos
+        assert b"(1 samples" in L.sl_last_error()
     assert L.sl_host_narrow_u8(None, 0, 0, None, 0) == 0      # empty
     assert L.sl_host_narrow_u8(src.ctypes.data, 7, 4, out.ctypes.data, 0) == -1
 
