@@ -330,6 +330,15 @@ int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_
                             clouds, n_clouds, 1, max_points, stream);
 }
 
+int sl_emit_cloud_at(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                     const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                     int B, int H, int W, const void* workspace, float* cloud, int64_t max_points, void* stream) {
+  if (max_points < 1) { set_error("max_points must be positive"); return kErrBadArg; }
+  float* one[1] = {cloud};
+  return emit_cloud_checked(h_idx, v_idx, white_rgb, calib, precision, cam_rays, proj_rays, B, H, W, workspace,
+                            one, 1, 0, max_points, stream);
+}
+
 int sl_decode_triangulate_fused(const uint8_t* frames, int B, int F, int H, int W, size_t frame_pitch,
                                 size_t scan_pitch, double eps, const uint8_t* white_rgb, const SlCalib* calib,
                                 int precision, const float* cam_rays, const float* proj_rays, int16_t* h_idx,

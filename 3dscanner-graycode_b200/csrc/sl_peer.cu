@@ -13,6 +13,10 @@
 //                             wait for everybody's, rebase col_base of the local workspace
 //   (emit_kernel, sl_cloud.cu, writes to the peer-mapped cloud(s))
 //   exchange_arrive_kernel    tell the gathering rank(s) that my records have landed / wait for all ranks
+//   exchange_push_kernel      the other transport for scan-sharded batches: a rank's records of one step are one
+//                             contiguous block of the gathered cloud, so they can also be emitted locally (at the
+//                             local emission's speed) and pushed as one stream of full 128-byte lines by a few CTAs
+//                             while the SMs go on with the next batch
 //
 // Control blocks live in cudaMalloc memory exported with CUDA IPC (sl_peer_*); flags are 64-bit step numbers
 // written with st.release.sys and polled with ld.acquire.sys.  Every wait has a time-out (a dead peer must not
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kExchangeThreads) exchange_offsets_kernel(cons
     }
     const long long base = base_s;
     const long long m = (long long)B * W;
-    if (base != 0)
+    if (base != 0 && col_base)           // col_base == nullptr: counts only (the records are pushed as a block)
       for (long long i = tid; i < m; i += kExchangeThreads) col_base[i] += base;
     return;
   }
@@ -249,6 +253,50 @@ __global__ void __launch_bounds__(32) exchange_arrive_kernel(const ExchangeArgs 
   if (wait && lane < x.world) {
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(x.ctrl[x.rank] + x.done_off) + lane;
     if (!wait_flag(flag, seq, x.timeout_ns)) local->error = 2;
+  }
+}
+
+struct PushDsts {
+  uint4* cloud[kMaxWorld];
+  int n;
+};
+
+// Copy this rank's records of the step, src[0 .. n) (src_rebased: src is laid out like the gathered cloud and the
+// records start at src + rank_base), to [rank_base, rank_base + n) of every destination cloud (peer-mapped or local).
+// n = *total_ptr and rank_base come from device memory: no host synchronisation.  The first few records are copied
+// apart so that the warps of the main loop write whole, aligned 128-byte lines of the destination.
+constexpr int kPushThreads = 512;
+__global__ void __launch_bounds__(kPushThreads) exchange_push_kernel(const ExchangeArgs x, const uint4* __restrict__ src,
+                                                                      int src_rebased, const long long* __restrict__ total_ptr,
+                                                                      const PushDsts d, long long max_points) {
+  ExchangeLocal* local = reinterpret_cast<ExchangeLocal*>(x.ctrl[x.rank]);
+  if (local->error == 1) return;                          // the count exchange timed out: rank_base is not valid
+  const long long base = local->rank_base;
+  const long long n = *total_ptr;
+  if (n <= 0) return;
+  if (base < 0 || base + n > max_points) {                // the gathered cloud is too small: nothing is written
+    if (blockIdx.x == 0 && threadIdx.x == 0) local->error = 3;
+    return;
+  }
+  const uint4* s = src + (src_rebased ? base : 0);
+  const long long head = min(n, (long long)((8 - (base & 7)) & 7));
+  const long long tid = (long long)blockIdx.x * kPushThreads + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * kPushThreads;
+  if (tid < head) {
+    const uint4 v = s[tid];
+    for (int k = 0; k < d.n; ++k) d.cloud[k][base + tid] = v;
+  }
+  for (long long i = head + tid; i < n; i += 4 * nthr) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i + j * nthr < n) v[j] = __ldcs(s + i + j * nthr);
+    for (int k = 0; k < d.n; ++k) {
+      uint4* o = d.cloud[k] + base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i + j * nthr < n) o[i + j * nthr] = v[j];
+    }
   }
 }
 
@@ -341,11 +389,11 @@ void sl_exchange_destroy(SlExchange* x) { delete x; }
 
 int sl_exchange_offsets_by_scan(SlExchange* x, int B, int H, int W, void* workspace, const int64_t* counts,
                                 int64_t* counts_all, void* stream) {
-  if (!x || !workspace || !counts) { set_error("null argument"); return kErrBadArg; }
+  if (!x || !counts) { set_error("null argument"); return kErrBadArg; }
   if (B < 1 || B > x->layout.max_scans || H < 1 || W < 1) { set_error("B=%d outside 1..max_scans=%d", B, x->layout.max_scans); return kErrBadArg; }
-  const CloudWorkspace c = carve_workspace(workspace, B, H, W);
+  long long* col_base = workspace ? carve_workspace(workspace, B, H, W).col_base : nullptr;
   exchange_offsets_kernel<false><<<1, kExchangeThreads, 0, (cudaStream_t)stream>>>(
-      x->args, B, W, (const long long*)counts, nullptr, c.col_base, (long long*)counts_all);
+      x->args, B, W, (const long long*)counts, nullptr, col_base, (long long*)counts_all);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;
@@ -358,6 +406,29 @@ int sl_exchange_offsets_row_band(SlExchange* x, int H, int W, void* workspace, c
   const CloudWorkspace c = carve_workspace(workspace, 1, H, W);
   exchange_offsets_kernel<true><<<1, kExchangeThreads, 0, (cudaStream_t)stream>>>(
       x->args, 1, W, (const long long*)counts, c.col_tot, c.col_base, (long long*)counts_all);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int sl_exchange_push(SlExchange* x, const float* src, int src_rebased, const int64_t* total, float* const* clouds,
+                     int n_clouds, int64_t max_points, int n_ctas, void* stream) {
+  if (!x || !src || !total || !clouds) { set_error("null argument"); return kErrBadArg; }
+  if (n_clouds < 1 || n_clouds > kMaxWorld) { set_error("n_clouds must be 1..%d", kMaxWorld); return kErrBadArg; }
+  if (max_points < 1) { set_error("max_points must be positive"); return kErrBadArg; }
+  if ((uintptr_t)src % 16 || (uintptr_t)total % 8) { set_error("src must be 16-byte aligned, total 8-byte"); return kErrBadArg; }
+  PushDsts d;
+  memset(&d, 0, sizeof(d));
+  for (int k = 0; k < n_clouds; ++k) {
+    if (!clouds[k] || (uintptr_t)clouds[k] % 16) { set_error("cloud buffers must be non-null and 16-byte aligned"); return kErrBadArg; }
+    d.cloud[k] = reinterpret_cast<uint4*>(clouds[k]);
+  }
+  d.n = n_clouds;
+  if (n_ctas <= 0) n_ctas = 32;
+  if (n_ctas > 1024) n_ctas = 1024;
+  exchange_push_kernel<<<n_ctas, kPushThreads, 0, (cudaStream_t)stream>>>(x->args, reinterpret_cast<const uint4*>(src),
+                                                                          src_rebased ? 1 : 0, (const long long*)total, d,
+                                                                          (long long)max_points);
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;

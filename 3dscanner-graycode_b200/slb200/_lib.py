@@ -83,6 +83,8 @@ SIGNATURES = {
     "sl_exchange_offsets_row_band": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "sl_emit_cloud_multi": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, C.POINTER(_vp), _i, _i64,
                                 _vp]),
+    "sl_emit_cloud_at": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "sl_exchange_push": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _i, _vp]),
     "sl_exchange_arrive": (_i, [_vp, C.c_uint32, _i, _vp]),
     "sl_exchange_status": (_i, [_vp, C.POINTER(_i), C.POINTER(_i64), C.POINTER(_i64)]),
     "sl_host_narrow_u8": (_i, [_vp, _i, _sz, _vp, _i]),

@@ -205,13 +205,20 @@ class CloudExchange:
     """
 
     def __init__(self, max_scans: int, max_width: int, max_points: int, group=None, gather_to=0,
-                 timeout_s: float = 20.0):
+                 timeout_s: float = 20.0, transport: str = "emit", push_ctas: int = 0):
         from ._lib import check, lib
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         if self.world > 16:
             raise ValueError("CloudExchange supports up to 16 ranks")
+        if transport not in ("emit", "push"):
+            raise ValueError("transport must be 'emit' or 'push'")
+        # "emit": the emission writes through the peer mapping (both sharding modes).  "push" (scan-sharded steps
+        # only; row bands interleave per column and always use "emit"): emit locally, then sl_exchange_push copies
+        # the rank's block with push_ctas CTAs -- the better choice when the next batch's compute can overlap it.
+        self.transport, self.push_ctas = transport, int(push_ctas)
+        self._stage = None
         self.max_points = int(max_points)
         self.max_scans, self.max_width = int(max_scans), int(max_width)
         self.dsts = list(range(self.world)) if gather_to == "all" else [int(gather_to)]
@@ -247,6 +254,9 @@ class CloudExchange:
         order = ([self.rank] if self.is_dst else []) + [d for d in self.dsts if d != self.rank]
         self._cloud_ptr_list = [cloud_ptrs[d] for d in order]
         self._clouds_c = (C.c_void_p * len(order))(*self._cloud_ptr_list)
+        others = [cloud_ptrs[d] for d in self.dsts if d != self.rank]
+        self._other_ptr_list = others
+        self._others_c = (C.c_void_p * max(1, len(others)))(*others)
         arr = (C.c_void_p * self.world)(*ctrl_ptrs)
         self._x = C.c_void_p()
         check(L.sl_exchange_create(C.byref(self._x), self.rank, self.world, arr, self.max_scans, self.max_width,
@@ -280,6 +290,40 @@ class CloudExchange:
                                         _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), self._clouds_c,
                                         len(self._cloud_ptr_list), self.max_points, _stream()))
 
+    def counts_by_scan(self, buffers, b: int, h: int, w: int):
+        """Count exchange without rebasing the local offsets (``sl_exchange_offsets_by_scan`` with a null workspace)."""
+        from ._lib import check, lib
+        from .api import _ptr, _stream
+        check(lib().sl_exchange_offsets_by_scan(self._x, b, h, w, None, _ptr(buffers.counts), _ptr(self.counts_all),
+                                                _stream()))
+
+    def _emit_and_push(self, buffers, white_rgb, calib_struct, precision, tables, b: int, h: int, w: int):
+        """transport="push": local emission, then the rank's block goes to the gathering rank(s) as one stream."""
+        from ._lib import check, lib
+        from .api import _PREC, _ptr, _stream
+        L, st = lib(), _stream()
+        cam_t = _ptr(tables.cam) if tables is not None else None
+        proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
+        total = C.c_void_p(buffers.counts.data_ptr() + 8 * b)
+        if self.is_dst:
+            # my own records go straight to their place in my gathered cloud; the other receivers get a copy of it
+            self.offsets_by_scan(buffers, b, h, w)
+            check(L.sl_emit_cloud_at(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
+                                     _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws),
+                                     C.c_void_p(self._cloud.ptr), self.max_points, st))
+            if self._other_ptr_list:
+                check(L.sl_exchange_push(self._x, C.c_void_p(self._cloud.ptr), 1, total, self._others_c,
+                                         len(self._other_ptr_list), self.max_points, self.push_ctas, st))
+        else:
+            self.counts_by_scan(buffers, b, h, w)
+            need = b * h * w
+            if self._stage is None or self._stage.shape[0] < need:
+                self._stage = torch.empty((need, 4), dtype=torch.float32, device=self.device)
+            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
+                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(self._stage), st))
+            check(L.sl_exchange_push(self._x, _ptr(self._stage), 0, total, self._others_c, len(self._other_ptr_list),
+                                     self.max_points, self.push_ctas, st))
+
     def arrive(self):
         from ._lib import check, lib
         from .api import _stream
@@ -304,8 +348,11 @@ class CloudExchange:
         check(L.sl_decode_u8(api._ptr(frames), b, f, h, w, fp, sp, float(eps), api._ptr(buffers.h_idx),
                              api._ptr(buffers.v_idx), None, None, api._ptr(buffers.ws), int(sm_reserve), st))
         check(L.sl_compact_offsets_decoded(b, h, w, api._ptr(buffers.ws), api._ptr(buffers.counts), st))
-        self.offsets_by_scan(buffers, b, h, w)
-        self.emit(buffers, white_rgb, s, precision, tables, b, h, w)
+        if self.transport == "push":
+            self._emit_and_push(buffers, white_rgb, s, precision, tables, b, h, w)
+        else:
+            self.offsets_by_scan(buffers, b, h, w)
+            self.emit(buffers, white_rgb, s, precision, tables, b, h, w)
         self.arrive()
         return buffers
 
@@ -350,6 +397,8 @@ class CloudExchange:
         err, base, total = C.c_int(), C.c_int64(), C.c_int64()
         check(lib().sl_exchange_status(self._x, C.byref(err), C.byref(base), C.byref(total)))
         if err.value:
+            if err.value == 3:
+                raise RuntimeError("cloud exchange: the gathered cloud (max_points) is too small for this step")
             raise RuntimeError(f"cloud exchange: a wait for a peer rank timed out (stage {err.value})")
         return int(base.value), int(total.value)
 
@@ -373,6 +422,7 @@ class CloudExchange:
             L.sl_exchange_destroy(self._x)
             self._x = None
             self.cloud = None
+            self._stage = None
             for p in self._opened:
                 L.sl_peer_close(C.c_void_p(p))
             self._opened = []

@@ -342,7 +342,9 @@ void sl_exchange_destroy(SlExchange* x);
  * output, still on the device): every offset in `workspace` is advanced by the number of points of all lower ranks,
  * so that the emission writes at the packed position of the whole batch.  counts_all (nullable, device int64
  * [total scans + 1]): every scan's point count in rank order, then the grand total.  Asynchronous on `stream`;
- * every rank must make the same sequence of sl_exchange_* calls. */
+ * every rank must make the same sequence of sl_exchange_* calls.  workspace may be null: then only the counts are
+ * exchanged (this rank's first record and the total stay in the exchange for sl_exchange_push) and the offsets keep
+ * their local values. */
 int sl_exchange_offsets_by_scan(SlExchange* x, int B, int H, int W, void* workspace, const int64_t* counts,
                                 int64_t* counts_all, void* stream);
 /* One capture cut into row bands, rank r holding the r-th band (H rows here, boundaries multiples of 32 rows, calib
@@ -360,13 +362,30 @@ int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_
                         int B, int H, int W, const void* workspace, float* const* clouds, int n_clouds,
                         int64_t max_points, void* stream);
 
+/* sl_emit_cloud into LOCAL memory for a workspace whose offsets sl_exchange_offsets_* has rebased: cloud is laid out
+ * like the gathered cloud (capacity max_points records). */
+int sl_emit_cloud_at(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
+                     const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
+                     int B, int H, int W, const void* workspace, float* cloud, int64_t max_points, void* stream);
+
+/* The other transport for scan-sharded batches.  A rank's records of one step are ONE contiguous block of the gathered
+ * cloud, so instead of emitting through the peer mapping (NVLink store requests of 256-512 bytes at the pace of the
+ * emission) the rank emits locally at full speed and n_ctas CTAs (<= 0: 32) then copy the block as whole 128-byte lines
+ * while the other SMs go on with the next batch.  src = the local records: packed from src[0] (src_rebased = 0, after
+ * sl_exchange_offsets_by_scan with a null workspace + sl_emit_cloud) or laid out like the gathered cloud
+ * (src_rebased = 1, after the rebasing exchange + sl_emit_cloud_at); total = device pointer to this rank's point count
+ * (counts + B); clouds = the n_clouds destinations (peer-mapped or local, 16-byte aligned), each of capacity max_points.
+ * No host synchronisation.  If the block does not fit, nothing is written and sl_exchange_status reports error 3. */
+int sl_exchange_push(SlExchange* x, const float* src, int src_rebased, const int64_t* total, float* const* clouds,
+                     int n_clouds, int64_t max_points, int n_ctas, void* stream);
+
 /* After the emission: tell the ranks in dst_mask (bit r = rank r) that this rank's records of the current step have
  * landed; with wait != 0 also wait (on the stream, not the host) until every rank has told this one the same --
  * the gathered cloud is then complete for whatever is queued next on `stream`. */
 int sl_exchange_arrive(SlExchange* x, uint32_t dst_mask, int wait, void* stream);
 
-/* Synchronous: error = 0, or 1 / 2 if a wait in sl_exchange_offsets_* / sl_exchange_arrive timed out (results of that
- * step are then invalid); rank_base / grand_total (nullable) = this rank's first record and the total of the last step. */
+/* Synchronous: error = 0, 1 / 2 if a wait in sl_exchange_offsets_* / sl_exchange_arrive timed out, 3 if sl_exchange_push
+ * found the gathered cloud too small (results of that step are then invalid); rank_base / grand_total (nullable) = this rank's first record and the total of the last step. */
 int sl_exchange_status(SlExchange* x, int* error, int64_t* rank_base, int64_t* grand_total);
 
 /* ---- Host-side conversions at the NumPy boundary of the reference API (no device work) ----------------------------------

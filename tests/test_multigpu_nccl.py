@@ -1,8 +1,9 @@
 """Multi-rank runs on real GPUs (2, 4 and 8 ranks where the box has them; skipped below 2 GPUs) of both sharding
 modes, through both gathers:
   * by scan: each rank processes its block of scans; the gathered cloud == the single-GPU batch, bit for bit
-      - CloudExchange (records emitted straight into the gathering rank's cloud over NVLink peer memory), gather to
-        rank 0 and all-gather, several steps in a row (the control blocks are double-buffered by step parity)
+      - CloudExchange, both transports ("emit": records emitted straight into the gathering rank's cloud over NVLink
+        peer memory; "push": local emission, then sl_exchange_push copies the rank's block), gather to rank 0 / to the
+        last rank and all-gather, several steps in a row (the control blocks are double-buffered by step parity)
       - gather_clouds over NCCL (all-gather and gather to rank 0)
   * by row band: each rank decodes + triangulates one band of the same capture
       - CloudExchange.band_to_cloud: per-column counts exchanged on the device, records land at their x-major
@@ -58,8 +59,11 @@ def _worker(rank, world, port, q):
         return fr, wh
 
     # ---- by scan, peer-memory exchange: gather to rank 0, then all-gather; 3 steps each
-    for mode in (0, "all"):
-        ex = CloudExchange(max_scans=max(per_rank), max_width=W, max_points=n_scans * H * W, gather_to=mode)
+    last = world - 1
+    for mode, transport in ((0, "emit"), ("all", "emit"), (0, "push"), ("all", "push"), (last, "push")):
+        ex = CloudExchange(max_scans=max(per_rank), max_width=W, max_points=n_scans * H * W, gather_to=mode,
+                           transport=transport, push_ctas=(3 if mode == last else 0))
+        mode = f"{mode}/{transport}"
         for step in range(3):
             fr, wh = batch(step)
             ex.scan_to_cloud(fr[lo:hi].contiguous(), wh[lo:hi].contiguous(), calib, tables=tables)
@@ -77,7 +81,8 @@ def _worker(rank, world, port, q):
 
     # ---- two exchanges on two streams, batches alternating between them (the gather of one batch beside the compute of
     # the next): both gathered clouds are complete and exact
-    exs = [CloudExchange(max_scans=max(per_rank), max_width=W, max_points=n_scans * H * W, gather_to=0) for _ in range(2)]
+    exs = [CloudExchange(max_scans=max(per_rank), max_width=W, max_points=n_scans * H * W, gather_to=0,
+                         transport=("emit", "push")[k]) for k in range(2)]
     sts = [torch.cuda.Stream(dev) for _ in range(2)]
     refs = []
     for step in range(4):
