@@ -330,6 +330,21 @@ int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_
                             clouds, n_clouds, 1, max_points, stream);
 }
 
+int sl_emit_cloud_rows(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, const SlCalib* calib,
+                       const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
+                       const void* workspace, float* cloud, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !cloud || !calib || !cam_rays_t || !proj_bt_t) { set_error("null buffer"); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1 || cam_rows < 1) { set_error("bad shape"); return kErrBadArg; }
+  if ((uintptr_t)h_idx % 16 || (uintptr_t)v_idx % 16 || (uintptr_t)white_rgb % 16 || (uintptr_t)cloud % 16 ||
+      (uintptr_t)cam_rays_t % 8 || (uintptr_t)proj_bt_t % 8) {
+    set_error("h_idx, v_idx, white_rgb and cloud must be 16-byte aligned, the tables 8-byte"); return kErrBadArg;
+  }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_emit_rows(h_idx, v_idx, white_rgb, *calib, cam_rays_t, cam_rows, proj_bt_t, B, H, W, workspace, cloud,
+                          (cudaStream_t)stream);
+}
+
 int sl_emit_cloud_at(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
                      const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
                      int B, int H, int W, const void* workspace, float* cloud, int64_t max_points, void* stream) {

@@ -934,6 +934,177 @@ __global__ void __launch_bounds__(kEmitWarps * 32, ROWS == 16 ? SL_EMITF_MIN_CTA
   }
 }
 
+// ------------------------------------------------------------------ K2r emit, lane = row
+// emit_fast_kernel above is bound by the LSU: a lane owns 4 neighbouring pixels of a row, so every load instruction of the
+// warp spans 8 image rows = 8 cache lines, whatever its width (ncu on a 16-scan batch: 36 L1 wavefronts per 32 pixels, the
+// l1tex data pipe at 75 %), and the x-major order is restored by staging the 16-byte records in shared memory.
+// This kernel transposes on the INPUT side instead, where a pixel is 7 bytes and not 16:
+//   * a warp takes a tile of 32 rows x 32 columns; the row-major inputs (indices, colours) are fetched with full-width
+//     16-byte loads (4 / 6 lanes per row) and parked in shared memory (indices: 16-byte chunks XOR-swizzled so that both the
+//     row-wise stores and the per-lane 16-byte reads are conflict-free; colours: 104-byte row pitch);
+//   * then lane = row.  For a column c the 32 lanes hold the 32 rows of that column, i.e. the column's run in order:
+//     rank = popc(ballot(valid) below the lane), and the valid lanes write their records straight from registers to
+//     consecutive slots -- one coalesced store of up to 512 bytes per column, no record ever touches shared memory;
+//   * the lens tables are read along a column, so they are stored TRANSPOSED (cam_t [W][rows], proj_t [proj_w][proj_h],
+//     built once per calibration): the camera rays of a column are contiguous (2 lines per load), and the projector
+//     entries of a column are too, because along a camera column the decoded projector row advances with the camera row
+//     while the projector column stays put.
+// Per 32 pixels that is ~17 L1 wavefronts: staging 3 + 1.5, shared reads 1.75, bases 1, camera rays 2, gather ~3, store
+// ~4.5.  The records are bit-identical to emit_fast_kernel's (same table values, same formula).
+struct EmitRowsArgs {
+  const int16_t* h;
+  const int16_t* v;
+  const uint8_t* white;     // nullable
+  const uint32_t* band_pre;
+  const uint32_t* col_bits;
+  const long long* col_base;
+  uint4* out;
+  const float2* cam_t;      // [W][cam_rows]
+  const float2* proj_t;     // [proj_w][proj_h]: (|T x p|, T.p)
+  int H, W, bands, tiles_x, cam_rows, row0;
+  uint32_t pw1, ph1, ph;
+  float t0, t1, t2, tl2;
+  long long total_tiles;
+};
+constexpr int kRowsWarps = 4;
+constexpr int kRowsWhitePitch = 104;                     // bytes; 26 words: 16 consecutive rows start in 16 different even banks
+constexpr int kRowsIdxBytes = 32 * 64;                   // one index tile: 32 rows x 32 int16
+constexpr int kRowsSmemWarp = 2 * kRowsIdxBytes + 32 * kRowsWhitePitch + 32 * 8;     // h, v, colours, column bases
+constexpr int kRowsSmem = kRowsWarps * kRowsSmemWarp;
+
+__device__ __forceinline__ uint4 ldg_u4_hint(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(kRowsWarps * 32, 4) emit_rows_kernel(const EmitRowsArgs a) {
+  extern __shared__ __align__(16) uint8_t rows_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kRowsWarps + warp;
+  if (t >= a.total_tiles) return;
+  const uint32_t ti = (uint32_t)t;
+  const uint32_t per_scan = (uint32_t)a.tiles_x * (uint32_t)a.bands;
+  const int b = (int)(ti / per_scan);
+  const uint32_t in_scan = ti - (uint32_t)b * per_scan;
+  const int band = (int)(in_scan / (uint32_t)a.tiles_x);
+  const int tx = (int)(in_scan - (uint32_t)band * (uint32_t)a.tiles_x);
+  const int x0 = tx * 32, y0 = band * kBandRows;
+  const int rows = min(kBandRows, a.H - y0);
+  const size_t img = (size_t)b * a.H * a.W;
+  const size_t cell = ((size_t)b * a.bands + band) * a.W + x0;
+  const uint32_t h_s = smem_u32(rows_smem) + (uint32_t)warp * kRowsSmemWarp;
+  const uint32_t v_s = h_s + kRowsIdxBytes, w_s = v_s + kRowsIdxBytes, b_s = w_s + 32 * kRowsWhitePitch;
+  const bool has_rgb = a.white != nullptr;
+  const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
+
+  // ---- the row-major inputs of the tile, full-width loads (chunk q of 16 bytes: row q / 4, columns 8 (q % 4) ..)
+  uint4 hq[4], vq[4], wq[6];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int q = j * 32 + lane;
+    const int r = min(q >> 2, rows - 1);                    // rows past the image repeat the last one (never valid)
+    const size_t g = img + (size_t)(y0 + r) * a.W + x0 + (q & 3) * 8;
+    hq[j] = ldg_u4_hint(a.h + g, stream);
+    vq[j] = ldg_u4_hint(a.v + g, stream);
+  }
+  if (has_rgb) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int q = j * 32 + lane;
+      const int r6 = q / 6, k = q - 6 * r6;
+      const int r = min(r6, rows - 1);
+      wq[j] = ldg_u4_hint(a.white + (img + (size_t)(y0 + r) * a.W + x0) * 3 + k * 16, stream);
+    }
+  }
+  // column metadata, lane <-> column x0 + lane
+  const uint32_t my_bits = a.col_bits[cell + lane];
+  const long long my_base = a.col_base[(size_t)b * a.W + x0 + lane] + (long long)a.band_pre[cell + lane];
+  sts_u2(b_s + (uint32_t)lane * 8u, (uint32_t)(unsigned long long)my_base, (uint32_t)((unsigned long long)my_base >> 32));
+  // validity of MY ROW's 32 columns: the transpose of the column words, one vote per row
+  uint32_t rowbits = 0;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const uint32_t m = __ballot_sync(0xffffffffu, (my_bits >> r) & 1u);
+    if (lane == r) rowbits = m;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int q = j * 32 + lane;
+    const int r = q >> 2, k = q & 3;
+    const uint32_t off = (uint32_t)(r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
+    sts_u4(h_s + off, hq[j].x, hq[j].y, hq[j].z, hq[j].w);
+    sts_u4(v_s + off, vq[j].x, vq[j].y, vq[j].z, vq[j].w);
+  }
+  if (has_rgb) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int q = j * 32 + lane;
+      const int r6 = q / 6, k = q - 6 * r6;
+      const uint32_t off = w_s + (uint32_t)(r6 * kRowsWhitePitch + k * 16);
+      sts_u2(off, wq[j].x, wq[j].y);
+      sts_u2(off + 8, wq[j].z, wq[j].w);
+    }
+  }
+  __syncwarp();
+
+  // ---- lane = row
+  const size_t cam_row = (size_t)(a.row0 + y0 + min(lane, rows - 1));
+  const uint32_t below = (1u << lane) - 1u;
+  const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t ioff = (uint32_t)(lane * 64) + ((((uint32_t)g) ^ swz) << 4);
+    const uint4 h8 = lds_u4(h_s + ioff), v8 = lds_u4(v_s + ioff);
+    uint32_t cw[7];                                        // 24 colour bytes of columns 8g .. 8g+7 (+ a zero word)
+    if (has_rgb) {
+      const uint32_t woff = w_s + (uint32_t)(lane * kRowsWhitePitch + g * 24);
+      const uint2 c0 = lds_u2(woff), c1 = lds_u2(woff + 8), c2 = lds_u2(woff + 16);
+      cw[0] = c0.x; cw[1] = c0.y; cw[2] = c1.x; cw[3] = c1.y; cw[4] = c2.x; cw[5] = c2.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cw[i] = 0;
+    }
+    cw[6] = 0;
+    const uint32_t hw[4] = {h8.x, h8.y, h8.z, h8.w}, vw[4] = {v8.x, v8.y, v8.z, v8.w};
+    float2 cam[8], pe[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      cam[k] = ldg_f2_hint(a.cam_t + (size_t)(x0 + c) * a.cam_rows + cam_row, keep);
+      // triangulate.py:60-61: min(proj_w - 1, h), min(proj_h - 1, v) (-1 = 0xffff clamps too; such a pixel is not valid)
+      const uint32_t hc = min((hw[k >> 1] >> (16 * (k & 1))) & 0xffffu, a.pw1);
+      const uint32_t vc = min((vw[k >> 1] >> (16 * (k & 1))) & 0xffffu, a.ph1);
+      pe[k] = make_float2(0.f, 0.f);
+      if ((rowbits >> c) & 1u) pe[k] = ldg_f2_hint(a.proj_t + (size_t)hc * a.ph + vc, keep);        // triangulate.py:56
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      const bool valid = (rowbits >> c) & 1u;
+      float X, Y, Z;
+      rays_to_point_fp32_bt(cam[k].x, cam[k].y, pe[k].x, pe[k].y, a.t0, a.t1, a.t2, a.tl2, X, Y, Z);
+      // the colour of column 8g + k: bytes 3k .. 3k+2 of the 24 (triangulate.py:64)
+      const uint32_t colour = __funnelshift_r(cw[(3 * k) >> 2], cw[((3 * k) >> 2) + 1], 8 * ((3 * k) & 3)) & 0xffffffu;
+      const uint32_t colword = __ballot_sync(0xffffffffu, valid);       // = the column's bits: lanes are its rows
+      const uint2 bb = lds_u2(b_s + (uint32_t)c * 8u);
+      const long long base = (long long)(((unsigned long long)bb.y << 32) | bb.x);
+      if (valid)
+        stg_u4_hint(a.out + base + __popc(colword & below),
+                    make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), colour), stream);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ points API
 template <bool FP64>
 __global__ void __launch_bounds__(256) points_kernel(const float2* __restrict__ cam,
@@ -1269,6 +1440,28 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
     else SL_CUDA(launch_stage2(emit_kernel<kModeTableBT32>, g, thr, (size_t)kEmitSmemCloud, st, a));
   } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmemCloud, st>>>(a);
   else emit_kernel<kModeCloud32><<<g, thr, kEmitSmemCloud, st>>>(a);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_emit_rows(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib, const float* cam_t,
+                     int cam_rows, const float* proj_t, int B, int H, int W, const void* ws, float* cloud, cudaStream_t st) {
+  if (W % 32) { set_error("the row-mapped emission needs W to be a multiple of 32 (got %d)", W); return kErrBadArg; }
+  if (calib.cam_row0 < 0 || calib.cam_row0 + H > cam_rows) { set_error("camera table has %d rows, the band needs %d", cam_rows, calib.cam_row0 + H); return kErrBadArg; }
+  const CloudWorkspace c = carve_workspace(const_cast<void*>(ws), B, H, W);
+  const CalibDev cal = make_calib(calib);
+  EmitRowsArgs a;
+  a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_bits = c.col_bits; a.col_base = c.col_base;
+  a.out = reinterpret_cast<uint4*>(cloud);
+  a.cam_t = reinterpret_cast<const float2*>(cam_t); a.proj_t = reinterpret_cast<const float2*>(proj_t);
+  a.H = H; a.W = W; a.bands = c.bands; a.tiles_x = W / 32; a.cam_rows = cam_rows; a.row0 = cal.row0;
+  a.pw1 = (uint32_t)(cal.proj_w - 1); a.ph1 = (uint32_t)(cal.proj_h - 1); a.ph = (uint32_t)cal.proj_h;
+  a.t0 = cal.Tf[0]; a.t1 = cal.Tf[1]; a.t2 = cal.Tf[2]; a.tl2 = cal.t_len2f;
+  a.total_tiles = (long long)B * a.bands * a.tiles_x;
+  if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one emit launch"); return kErrBadArg; }
+  const int grid = (int)((a.total_tiles + kRowsWarps - 1) / kRowsWarps);
+  SL_CUDA(launch_stage2(emit_rows_kernel, grid, kRowsWarps * 32, (size_t)kRowsSmem, st, a));
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;

@@ -618,6 +618,10 @@ class CloudBuffers:
                    torch.empty((cap, 4), dtype=torch.float32, device=device))
 
 
+# default of scan_to_cloud(emit="auto"): the row-mapped emission where it applies (SLB200_EMIT=tiles turns it off)
+_AUTO_EMIT_ROWS = __import__("os").environ.get("SLB200_EMIT", "tiles") == "rows"
+
+
 class LensTables:
     """Undistorted rays of the camera and projector pixel lattices for one calibration
     (``sl_lens_tables``); build once, reuse for every scan.  ``cam``: the camera rays (rotated by R);
@@ -640,6 +644,18 @@ class LensTables:
                     self.proj = t
                 else:
                     self.proj_bt = t
+            self._transposed = None
+            if self.proj_bt is not None and _AUTO_EMIT_ROWS:
+                self.transposed()          # now, not inside somebody's CUDA graph capture
+
+    def transposed(self):
+        """``(cam_t (W,H,2), proj_bt_t (pw,ph,2))``: the fp32 mode's tables stored column-major, what the row-mapped
+        emission (``sl_emit_cloud_rows``) reads; built on first use, once per calibration."""
+        if getattr(self, "_transposed", None) is None:
+            if self.proj_bt is None:
+                raise ValueError("lens tables were built for the other triangulation precision")
+            self._transposed = (self.cam.permute(1, 0, 2).contiguous(), self.proj_bt.permute(1, 0, 2).contiguous())
+        return self._transposed
 
     def projector_table(self, precision) -> torch.Tensor:
         t = self.proj if _PREC[precision] == SL_PREC_FP64 else self.proj_bt
@@ -651,7 +667,8 @@ class LensTables:
 def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib: Calibration,
                   precision="fp32", eps: float = 1.0, buffers: Optional[CloudBuffers] = None,
                   calib_struct: Optional[SlCalib] = None, tables: Optional[LensTables] = None,
-                  row0: int = 0, bgr: bool = False, sm_reserve: int = 0, box: Optional[float] = None) -> CloudBuffers:
+                  row0: int = 0, bgr: bool = False, sm_reserve: int = 0, box: Optional[float] = None,
+                  emit: str = "auto") -> CloudBuffers:
     """Whole device-resident path for ``(F,H,W)`` / ``(B,F,H,W)`` uint8 stacks:
     decode -> ordered compaction -> undistort + triangulate.  No host synchronisation.
 
@@ -669,6 +686,9 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     ``box``: Triangulate.filter_3d_pts (triangulate.py:99-122; src/4-triangulate.py:71 uses 0.5) folded into the
     compaction (``sl_compact_offsets_boxed``): only points with |x|, |y|, |z| < box are counted and emitted, identical
     to ``filter_cloud_box`` of the unfiltered cloud, which is never materialised.
+
+    ``emit``: ``"tiles"`` = ``sl_emit_cloud``; ``"rows"`` = ``sl_emit_cloud_rows`` (fp32, tables, W % 32 == 0; the same
+    records bit for bit from transposed tables, fewer L1 wavefronts per pixel); ``"auto"`` picks.
 
     Results are in the returned buffers: ``cloud[:counts[B]]`` (XYZRGB records; ``.xyz`` / ``.rgb``
     views) packed scan after scan, each scan in the reference's x-major order; ``counts[b]`` points per scan.
@@ -702,6 +722,24 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
     st = _stream()
     cam_t = _ptr(tables.cam) if tables is not None else None
     proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
+    if emit not in ("auto", "tiles", "rows"):
+        raise ValueError("emit must be 'auto', 'tiles' or 'rows'")
+    rows_ok = (tables is not None and _PREC[precision] == SL_PREC_FP32 and w % 32 == 0 and tables.proj_bt is not None
+               and buffers.h_idx.data_ptr() % 16 == 0 and buffers.v_idx.data_ptr() % 16 == 0
+               and (white_rgb is None or white_rgb.data_ptr() % 16 == 0))
+    if emit == "rows" and not rows_ok:
+        raise ValueError("the row-mapped emission needs fp32 lens tables, W % 32 == 0 and 16-byte aligned buffers")
+    use_rows = rows_ok and (emit == "rows" or (emit == "auto" and _AUTO_EMIT_ROWS))
+
+    def emit_cloud():
+        if use_rows:
+            cam_tt, proj_tt = tables.transposed()
+            check(L.sl_emit_cloud_rows(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s), _ptr(cam_tt),
+                                       int(cam_tt.shape[1]), _ptr(proj_tt), b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
+        else:
+            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
+                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
+
     with torch.cuda.device(dev):
         if bgr and box is not None:
             raise ValueError("box is not offered together with bgr")
@@ -709,15 +747,18 @@ def scan_to_cloud(frames: torch.Tensor, white_rgb: Optional[torch.Tensor], calib
             check(L.sl_decode_bgr_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps),
                                      _ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(buffers.ws), int(sm_reserve), st))
             check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
-            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
-                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
+            emit_cloud()
         elif box is not None:
             check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(buffers.h_idx), _ptr(buffers.v_idx),
                                  None, None, None, int(sm_reserve), st))
             check(L.sl_compact_offsets_boxed(_ptr(buffers.h_idx), _ptr(buffers.v_idx), C.byref(s), _PREC[precision], cam_t,
                                              proj_t, float(box), b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
-            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(s),
-                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(buffers.cloud), st))
+            emit_cloud()
+        elif use_rows:
+            check(L.sl_decode_u8(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(buffers.h_idx), _ptr(buffers.v_idx),
+                                 None, None, _ptr(buffers.ws), int(sm_reserve), st))
+            check(L.sl_compact_offsets_decoded(b, h, w, _ptr(buffers.ws), _ptr(buffers.counts), st))
+            emit_cloud()
         else:
             check(L.sl_decode_triangulate_fused(_ptr(frames), b, f, h, w, fp, sp, float(eps), _ptr(white_rgb), C.byref(s),
                                                 _PREC[precision], cam_t, proj_t, _ptr(buffers.h_idx), _ptr(buffers.v_idx),

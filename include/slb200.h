@@ -362,6 +362,14 @@ int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_
                         int B, int H, int W, const void* workspace, float* const* clouds, int n_clouds,
                         int64_t max_points, void* stream);
 
+/* sl_emit_cloud (fp32, lens tables, local cloud) with the lane = row mapping: the same records, bit for bit, from
+ * TRANSPOSED lens tables -- cam_rays_t float2 [W][cam_rows] (cam_rays_t[x * cam_rows + y] = cam_rays[y * W + x]) and
+ * proj_bt_t float2 [proj_w][proj_h] (the SL_PREC_FP32 projector table transposed).  Needs W % 32 == 0 and 16-byte aligned
+ * h_idx / v_idx / white_rgb / cloud (SL_ERR_BAD_ARG otherwise: use sl_emit_cloud).  calib->cam_row0 + H <= cam_rows. */
+int sl_emit_cloud_rows(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, const SlCalib* calib,
+                       const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
+                       const void* workspace, float* cloud, void* stream);
+
 /* sl_emit_cloud into LOCAL memory for a workspace whose offsets sl_exchange_offsets_* has rebased: cloud is laid out
  * like the gathered cloud (capacity max_points records). */
 int sl_emit_cloud_at(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,

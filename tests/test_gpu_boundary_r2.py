@@ -262,3 +262,42 @@ def test_box_filter_as_a_predicate_of_the_compaction(T, precision, use_tables):
     assert np.array_equal(mine_kept[safe], kept[safe])
     pts_f, _ = O.filter_3d_pts(pts[:, safe], col[safe], thr)
     assert pts_f.shape[1] == int(mine_kept[safe].sum())
+
+
+@pytest.mark.parametrize("cam_size", [(160, 96), (320, 200), (1920, 1080), (3840, 77)])
+def test_row_mapped_emission_equals_the_tiled_one(T, cam_size):
+    """sl_emit_cloud_rows (lane = row, transposed lens tables) writes the same records as sl_emit_cloud, bit for bit: whole
+    and ragged bands, a batch, no colour image, a row band of a larger image, the boxed compaction."""
+    import slb200
+    W, H = cam_size
+    calib, frames, white = _scan(T, cam_size, seed=9, proj_size=(1024, 768) if W < 1000 else (1920, 1080))
+    tables = slb200.LensTables(calib, cam_size, frames.device)
+    a = slb200.scan_to_cloud(frames, white, calib, tables=tables, emit="tiles")
+    b = slb200.scan_to_cloud(frames, white, calib, tables=tables, emit="rows")
+    n = int(a.counts[1])
+    assert n == int(b.counts[1]) and n > 0
+    assert T.equal(a.cloud[:n].view(T.int32), b.cloud[:n].view(T.int32))
+    # no colour image
+    a = slb200.scan_to_cloud(frames, None, calib, tables=tables, emit="tiles")
+    b = slb200.scan_to_cloud(frames, None, calib, tables=tables, emit="rows")
+    assert T.equal(a.cloud[:n].view(T.int32), b.cloud[:n].view(T.int32))
+    if W > 2000:
+        return
+    # a batch of 3 (the third scan partly dark) and the boxed compaction
+    f3 = T.stack([frames, frames.flip(2), frames]).contiguous()
+    f3[2, :, H // 2:] = 0
+    w3 = T.stack([white, white.flip(1), white]).contiguous()
+    for box in (None, 0.45):
+        a = slb200.scan_to_cloud(f3, w3, calib, tables=tables, emit="tiles", box=box)
+        b = slb200.scan_to_cloud(f3, w3, calib, tables=tables, emit="rows", box=box)
+        assert T.equal(a.counts, b.counts)
+        m = int(a.counts[3])
+        assert 0 < m and T.equal(a.cloud[:m].view(T.int32), b.cloud[:m].view(T.int32))
+    # a row band of the image (rows 32 .. H): camera rows are absolute
+    if H > 64:
+        a = slb200.scan_to_cloud(frames[:, 32:], white[32:].contiguous(), calib, tables=tables, row0=32, emit="tiles")
+        b = slb200.scan_to_cloud(frames[:, 32:], white[32:].contiguous(), calib, tables=tables, row0=32, emit="rows")
+        m = int(a.counts[1])
+        assert m == int(b.counts[1]) and T.equal(a.cloud[:m].view(T.int32), b.cloud[:m].view(T.int32))
+    with pytest.raises(ValueError):
+        slb200.scan_to_cloud(frames, white, calib, tables=tables, emit="rows", precision="fp64")
