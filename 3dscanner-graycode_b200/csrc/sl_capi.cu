@@ -330,6 +330,14 @@ int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_
                             clouds, n_clouds, 1, max_points, stream);
 }
 
+int sl_transpose_table(const float* src, int rows, int cols, float* dst, void* stream) {
+  if (!src || !dst || rows < 1 || cols < 1) { set_error("bad argument"); return kErrBadArg; }
+  if ((uintptr_t)src % 8 || (uintptr_t)dst % 8) { set_error("tables must be 8-byte aligned"); return kErrBadArg; }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_transpose_f2(src, rows, cols, dst, (cudaStream_t)stream);
+}
+
 int sl_emit_cloud_rows(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, const SlCalib* calib,
                        const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
                        const void* workspace, float* cloud, void* stream) {
@@ -454,7 +462,20 @@ struct SlPipeline {
   float* cam_rays = nullptr;
   float* proj_rays = nullptr;
   size_t proj_rays_elems = 0;
+  // the same tables stored column-major for the row-mapped emission (fp32, W % 32 == 0)
+  float* cam_rays_t = nullptr;
+  float* proj_rays_t = nullptr;
+  size_t proj_rays_t_elems = 0;
+  bool have_transposed = false;
 };
+
+// the emission of one pipeline step: row-mapped where it applies, else the general one
+static int pipeline_emit(SlPipeline* p, const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib,
+                         int precision, int B, const void* ws, float* cloud, cudaStream_t st) {
+  if (p->have_transposed && precision == SL_PREC_FP32)
+    return launch_emit_rows(h, v, white, calib, p->cam_rays_t, p->H, p->proj_rays_t, B, p->H, p->W, ws, cloud, st);
+  return launch_emit_cloud(h, v, white, calib, precision, p->cam_rays, p->proj_rays, B, p->H, p->W, ws, cloud, st);
+}
 
 static void pipeline_free(SlPipeline* p) {
   if (!p) return;
@@ -468,7 +489,7 @@ static void pipeline_free(SlPipeline* p) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   cudaFree(p->h_codes); cudaFree(p->v_codes);
-  cudaFree(p->cam_rays); cudaFree(p->proj_rays);
+  cudaFree(p->cam_rays); cudaFree(p->proj_rays); cudaFree(p->cam_rays_t); cudaFree(p->proj_rays_t);
   delete p;
 }
 
@@ -532,6 +553,19 @@ static int pipeline_tables(SlPipeline* p, const SlCalib* calib, int precision) {
   }
   const int trc = launch_lens_tables(*calib, p->W, p->H, precision, p->cam_rays, p->proj_rays, p->slot[0].stream);
   if (trc) return trc;
+  p->have_transposed = false;
+  if (precision == SL_PREC_FP32 && p->W % 32 == 0) {
+    if (!p->cam_rays_t) SL_CUDA(cudaMalloc(&p->cam_rays_t, npix * 2 * sizeof(float)));
+    if (pe > p->proj_rays_t_elems) {
+      cudaFree(p->proj_rays_t); p->proj_rays_t = nullptr; p->proj_rays_t_elems = 0;
+      SL_CUDA(cudaMalloc(&p->proj_rays_t, pe * sizeof(float)));
+      p->proj_rays_t_elems = pe;
+    }
+    int xrc = launch_transpose_f2(p->cam_rays, p->H, p->W, p->cam_rays_t, p->slot[0].stream);
+    if (!xrc) xrc = launch_transpose_f2(p->proj_rays, calib->proj_h, calib->proj_w, p->proj_rays_t, p->slot[0].stream);
+    if (xrc) return xrc;
+    p->have_transposed = true;
+  }
   SL_CUDA(cudaStreamSynchronize(p->slot[0].stream));
   p->table_calib = *calib;
   p->table_precision = precision;
@@ -601,8 +635,7 @@ int sl_scan_to_cloud_host(SlPipeline* p, const uint8_t* frames_host, const uint8
     rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream);
     if (rc) break;
     SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
-    rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
-                           1, p->H, p->W, s.ws, s.cloud, s.stream);
+    rc = pipeline_emit(p, s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, 1, s.ws, s.cloud, s.stream);
     if (rc) break;
     SL_CUDA(cudaEventRecord(s.counted, s.stream));
   }
@@ -660,8 +693,7 @@ static int pipeline_submit(SlPipeline* p, const uint8_t* frames_host, bool bgr, 
                           flags, n_flags, p->sms, s.stream, bgr, p->sm_reserve))) return rc;
   if ((rc = launch_offsets_from_bitmap(1, p->H, p->W, s.ws, s.counts, s.stream))) return rc;
   SL_CUDA(cudaMemcpyAsync(s.counts_pinned, s.counts, 2 * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
-  if ((rc = launch_emit_cloud(s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, p->cam_rays, p->proj_rays,
-                              1, p->H, p->W, s.ws, s.cloud, s.stream))) return rc;
+  if ((rc = pipeline_emit(p, s.h, s.v, white_rgb_host ? s.white : nullptr, *calib, precision, 1, s.ws, s.cloud, s.stream))) return rc;
   SL_CUDA(cudaEventRecord(s.counted, s.stream));
   s.pending = true;
   s.user_cloud = cloud_host; s.user_cap = cap_points; s.user_count = count_host;

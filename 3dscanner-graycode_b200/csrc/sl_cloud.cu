@@ -987,7 +987,15 @@ __device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-__global__ void __launch_bounds__(kRowsWarps * 32, 4) emit_rows_kernel(const EmitRowsArgs a) {
+#ifndef SL_ROWS_MIN_CTAS
+#define SL_ROWS_MIN_CTAS 4
+#endif
+#ifndef SL_ROWS_UNROLL
+#define SL_ROWS_UNROLL 1
+#endif
+#define SL_PRAGMA_(x) _Pragma(#x)
+#define SL_UNROLL_N(n) SL_PRAGMA_(unroll n)
+__global__ void __launch_bounds__(kRowsWarps * 32, SL_ROWS_MIN_CTAS) emit_rows_kernel(const EmitRowsArgs a) {
   extern __shared__ __align__(16) uint8_t rows_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t = (long long)blockIdx.x * kRowsWarps + warp;
@@ -1061,7 +1069,12 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) emit_rows_kernel(const Emi
   const size_t cam_row = (size_t)(a.row0 + y0 + min(lane, rows - 1));
   const uint32_t below = (1u << lane) - 1u;
   const uint32_t swz = (uint32_t)((lane >> 1) & 3);
-#pragma unroll 1
+#if defined(SL_ROWS_PREFETCH)
+  float2 cam_next[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cam_next[k] = ldg_f2_hint(a.cam_t + (size_t)(x0 + k) * a.cam_rows + cam_row, keep);
+#endif
+  SL_UNROLL_N(SL_ROWS_UNROLL)
   for (int g = 0; g < 4; ++g) {
     const uint32_t ioff = (uint32_t)(lane * 64) + ((((uint32_t)g) ^ swz) << 4);
     const uint4 h8 = lds_u4(h_s + ioff), v8 = lds_u4(v_s + ioff);
@@ -1080,13 +1093,24 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) emit_rows_kernel(const Emi
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = g * 8 + k;
+#if defined(SL_ROWS_PREFETCH)
+      cam[k] = cam_next[k];
+#else
       cam[k] = ldg_f2_hint(a.cam_t + (size_t)(x0 + c) * a.cam_rows + cam_row, keep);
+#endif
       // triangulate.py:60-61: min(proj_w - 1, h), min(proj_h - 1, v) (-1 = 0xffff clamps too; such a pixel is not valid)
       const uint32_t hc = min((hw[k >> 1] >> (16 * (k & 1))) & 0xffffu, a.pw1);
       const uint32_t vc = min((vw[k >> 1] >> (16 * (k & 1))) & 0xffffu, a.ph1);
       pe[k] = make_float2(0.f, 0.f);
       if ((rowbits >> c) & 1u) pe[k] = ldg_f2_hint(a.proj_t + (size_t)hc * a.ph + vc, keep);        // triangulate.py:56
     }
+#if defined(SL_ROWS_PREFETCH)
+    if (g < 3) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        cam_next[k] = ldg_f2_hint(a.cam_t + (size_t)(x0 + g * 8 + 8 + k) * a.cam_rows + cam_row, keep);
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = g * 8 + k;
@@ -1440,6 +1464,28 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
     else SL_CUDA(launch_stage2(emit_kernel<kModeTableBT32>, g, thr, (size_t)kEmitSmemCloud, st, a));
   } else if (precision == SL_PREC_FP64) emit_kernel<kModeCloud64><<<g, thr, kEmitSmemCloud, st>>>(a);
   else emit_kernel<kModeCloud32><<<g, thr, kEmitSmemCloud, st>>>(a);
+  count_launch();
+  SL_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// dst[c][r] = src[r][c] for a table of float2 (32 x 32 tiles through shared memory); once per calibration
+__global__ void __launch_bounds__(256) transpose_f2_kernel(const float2* __restrict__ src, int rows, int cols,
+                                                            float2* __restrict__ dst) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = src[(size_t)(r0 + i) * cols + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) dst[(size_t)(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+
+int launch_transpose_f2(const float* src, int rows, int cols, float* dst, cudaStream_t st) {
+  const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  if (grid.y > 65535u) { set_error("table too tall to transpose"); return kErrBadArg; }
+  transpose_f2_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(src), rows, cols, reinterpret_cast<float2*>(dst));
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;

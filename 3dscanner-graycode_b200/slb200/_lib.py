@@ -83,6 +83,7 @@ SIGNATURES = {
     "sl_exchange_offsets_row_band": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "sl_emit_cloud_multi": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, C.POINTER(_vp), _i, _i64,
                                 _vp]),
+    "sl_transpose_table": (_i, [_vp, _i, _i, _vp, _vp]),
     "sl_emit_cloud_rows": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sl_emit_cloud_at": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sl_exchange_push": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _i, _vp]),

@@ -305,12 +305,26 @@ class CloudExchange:
         cam_t = _ptr(tables.cam) if tables is not None else None
         proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
         total = C.c_void_p(buffers.counts.data_ptr() + 8 * b)
+        rows = (tables is not None and precision == "fp32" and w % 32 == 0 and tables.proj_bt is not None
+                and (white_rgb is None or white_rgb.data_ptr() % 16 == 0))
+
+        def emit_local(cloud_ptr, max_points):
+            # the offsets in the workspace say where (local or rebased positions); both emissions just follow them
+            if rows:
+                cam_tt, proj_tt = tables.transposed()
+                check(L.sl_emit_cloud_rows(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
+                                           _ptr(cam_tt), int(cam_tt.shape[1]), _ptr(proj_tt), b, h, w, _ptr(buffers.ws),
+                                           cloud_ptr, st))
+            elif max_points:
+                check(L.sl_emit_cloud_at(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
+                                         _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), cloud_ptr, max_points, st))
+            else:
+                check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
+                                      _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), cloud_ptr, st))
         if self.is_dst:
             # my own records go straight to their place in my gathered cloud; the other receivers get a copy of it
             self.offsets_by_scan(buffers, b, h, w)
-            check(L.sl_emit_cloud_at(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
-                                     _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws),
-                                     C.c_void_p(self._cloud.ptr), self.max_points, st))
+            emit_local(C.c_void_p(self._cloud.ptr), self.max_points)
             if self._other_ptr_list:
                 check(L.sl_exchange_push(self._x, C.c_void_p(self._cloud.ptr), 1, total, self._others_c,
                                          len(self._other_ptr_list), self.max_points, self.push_ctas, st))
@@ -319,8 +333,7 @@ class CloudExchange:
             need = b * h * w
             if self._stage is None or self._stage.shape[0] < need:
                 self._stage = torch.empty((need, 4), dtype=torch.float32, device=self.device)
-            check(L.sl_emit_cloud(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),
-                                  _PREC[precision], cam_t, proj_t, b, h, w, _ptr(buffers.ws), _ptr(self._stage), st))
+            emit_local(_ptr(self._stage), 0)
             check(L.sl_exchange_push(self._x, _ptr(self._stage), 0, total, self._others_c, len(self._other_ptr_list),
                                      self.max_points, self.push_ctas, st))
 

@@ -366,6 +366,10 @@ int sl_emit_cloud_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_
  * TRANSPOSED lens tables -- cam_rays_t float2 [W][cam_rows] (cam_rays_t[x * cam_rows + y] = cam_rays[y * W + x]) and
  * proj_bt_t float2 [proj_w][proj_h] (the SL_PREC_FP32 projector table transposed).  Needs W % 32 == 0 and 16-byte aligned
  * h_idx / v_idx / white_rgb / cloud (SL_ERR_BAD_ARG otherwise: use sl_emit_cloud).  calib->cam_row0 + H <= cam_rows. */
+/* dst[c * rows + r] = src[r * cols + c] for a table of float2 entries (rows x cols): the transposed lens tables of
+ * sl_emit_cloud_rows from the ones sl_lens_tables builds (camera table: rows = h, cols = w; SL_PREC_FP32 projector table:
+ * rows = proj_h, cols = proj_w).  Once per calibration. */
+int sl_transpose_table(const float* src, int rows, int cols, float* dst, void* stream);
 int sl_emit_cloud_rows(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, const SlCalib* calib,
                        const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
                        const void* workspace, float* cloud, void* stream);
