@@ -966,7 +966,10 @@ struct EmitRowsArgs {
   float t0, t1, t2, tl2;
   long long total_tiles;
 };
-constexpr int kRowsWarps = 4;
+#ifndef SL_ROWS_WARPS
+#define SL_ROWS_WARPS 4
+#endif
+constexpr int kRowsWarps = SL_ROWS_WARPS;
 constexpr int kRowsWhitePitch = 104;                     // bytes; 26 words: 16 consecutive rows start in 16 different even banks
 constexpr int kRowsIdxBytes = 32 * 64;                   // one index tile: 32 rows x 32 int16
 constexpr int kRowsSmemWarp = 2 * kRowsIdxBytes + 32 * kRowsWhitePitch + 32 * 8;     // h, v, colours, column bases
