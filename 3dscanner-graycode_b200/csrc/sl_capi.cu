@@ -353,6 +353,24 @@ int sl_emit_cloud_rows(const int16_t* h_idx, const int16_t* v_idx, const uint8_t
                           (cudaStream_t)stream);
 }
 
+int sl_emit_cloud_rows_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, const SlCalib* calib,
+                             const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
+                             const void* workspace, float* const* clouds, int n_clouds, void* stream) {
+  if (!h_idx || !v_idx || !workspace || !clouds || !calib || !cam_rays_t || !proj_bt_t) { set_error("null buffer"); return kErrBadArg; }
+  if (n_clouds < 1 || n_clouds > kMaxWorld) { set_error("n_clouds must be 1..%d", kMaxWorld); return kErrBadArg; }
+  if (B < 1 || H < 1 || W < 1 || calib->proj_w < 1 || calib->proj_h < 1 || cam_rows < 1) { set_error("bad shape"); return kErrBadArg; }
+  for (int k = 0; k < n_clouds; ++k)
+    if (!clouds[k] || (uintptr_t)clouds[k] % 16) { set_error("cloud buffers must be non-null and 16-byte aligned"); return kErrBadArg; }
+  if ((uintptr_t)h_idx % 16 || (uintptr_t)v_idx % 16 || (uintptr_t)white_rgb % 16 || (uintptr_t)cam_rays_t % 8 ||
+      (uintptr_t)proj_bt_t % 8) {
+    set_error("h_idx, v_idx and white_rgb must be 16-byte aligned, the tables 8-byte"); return kErrBadArg;
+  }
+  int sms = 0, rc;
+  if ((rc = device_gate(&sms))) return rc;
+  return launch_emit_rows(h_idx, v_idx, white_rgb, *calib, cam_rays_t, cam_rows, proj_bt_t, B, H, W, workspace, clouds[0],
+                          (cudaStream_t)stream, clouds + 1, n_clouds - 1, 1);
+}
+
 int sl_emit_cloud_at(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
                      const SlCalib* calib, int precision, const float* cam_rays, const float* proj_rays,
                      int B, int H, int W, const void* workspace, float* cloud, int64_t max_points, void* stream) {

@@ -959,6 +959,8 @@ struct EmitRowsArgs {
   const uint32_t* col_bits;
   const long long* col_base;
   uint4* out;
+  uint4* out_extra[kMaxWorld - 1];   // MULTI: further destinations of the same records (peer-mapped clouds)
+  int n_extra;
   const float2* cam_t;      // [W][cam_rows]
   const float2* proj_t;     // [proj_w][proj_h]: (|T x p|, T.p)
   int H, W, bands, tiles_x, cam_rows, row0;
@@ -998,6 +1000,8 @@ __device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
 #endif
 #define SL_PRAGMA_(x) _Pragma(#x)
 #define SL_UNROLL_N(n) SL_PRAGMA_(unroll n)
+// MULTI: `out` and out_extra[] may be peer mappings (multi-GPU gather, sl_peer.cu): plain stores, every record to all of them
+template <bool MULTI>
 __global__ void __launch_bounds__(kRowsWarps * 32, SL_ROWS_MIN_CTAS) emit_rows_kernel(const EmitRowsArgs a) {
   extern __shared__ __align__(16) uint8_t rows_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1125,9 +1129,16 @@ __global__ void __launch_bounds__(kRowsWarps * 32, SL_ROWS_MIN_CTAS) emit_rows_k
       const uint32_t colword = __ballot_sync(0xffffffffu, valid);       // = the column's bits: lanes are its rows
       const uint2 bb = lds_u2(b_s + (uint32_t)c * 8u);
       const long long base = (long long)(((unsigned long long)bb.y << 32) | bb.x);
-      if (valid)
-        stg_u4_hint(a.out + base + __popc(colword & below),
-                    make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), colour), stream);
+      if (valid) {
+        const uint4 rec = make_uint4(__float_as_uint(X), __float_as_uint(Y), __float_as_uint(Z), colour);
+        const long long at = base + __popc(colword & below);
+        if (MULTI) {
+          a.out[at] = rec;
+          for (int e = 0; e < a.n_extra; ++e) a.out_extra[e][at] = rec;
+        } else {
+          stg_u4_hint(a.out + at, rec, stream);
+        }
+      }
     }
   }
 }
@@ -1495,7 +1506,8 @@ int launch_transpose_f2(const float* src, int rows, int cols, float* dst, cudaSt
 }
 
 int launch_emit_rows(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib, const float* cam_t,
-                     int cam_rows, const float* proj_t, int B, int H, int W, const void* ws, float* cloud, cudaStream_t st) {
+                     int cam_rows, const float* proj_t, int B, int H, int W, const void* ws, float* cloud, cudaStream_t st,
+                     float* const* extra, int n_extra, int remote) {
   if (W % 32) { set_error("the row-mapped emission needs W to be a multiple of 32 (got %d)", W); return kErrBadArg; }
   if (calib.cam_row0 < 0 || calib.cam_row0 + H > cam_rows) { set_error("camera table has %d rows, the band needs %d", cam_rows, calib.cam_row0 + H); return kErrBadArg; }
   const CloudWorkspace c = carve_workspace(const_cast<void*>(ws), B, H, W);
@@ -1503,6 +1515,9 @@ int launch_emit_rows(const int16_t* h, const int16_t* v, const uint8_t* white, c
   EmitRowsArgs a;
   a.h = h; a.v = v; a.white = white; a.band_pre = c.band_cnt; a.col_bits = c.col_bits; a.col_base = c.col_base;
   a.out = reinterpret_cast<uint4*>(cloud);
+  if (n_extra < 0 || n_extra > kMaxWorld - 1) { set_error("at most %d clouds per emission", kMaxWorld); return kErrBadArg; }
+  for (int k = 0; k < kMaxWorld - 1; ++k) a.out_extra[k] = k < n_extra ? reinterpret_cast<uint4*>(extra[k]) : nullptr;
+  a.n_extra = n_extra;
   a.cam_t = reinterpret_cast<const float2*>(cam_t); a.proj_t = reinterpret_cast<const float2*>(proj_t);
   a.H = H; a.W = W; a.bands = c.bands; a.tiles_x = W / 32; a.cam_rows = cam_rows; a.row0 = cal.row0;
   a.pw1 = (uint32_t)(cal.proj_w - 1); a.ph1 = (uint32_t)(cal.proj_h - 1); a.ph = (uint32_t)cal.proj_h;
@@ -1510,7 +1525,8 @@ int launch_emit_rows(const int16_t* h, const int16_t* v, const uint8_t* white, c
   a.total_tiles = (long long)B * a.bands * a.tiles_x;
   if (a.total_tiles >= (1LL << 31)) { set_error("batch too large for one emit launch"); return kErrBadArg; }
   const int grid = (int)((a.total_tiles + kRowsWarps - 1) / kRowsWarps);
-  SL_CUDA(launch_stage2(emit_rows_kernel, grid, kRowsWarps * 32, (size_t)kRowsSmem, st, a));
+  if (remote || n_extra > 0) emit_rows_kernel<true><<<grid, kRowsWarps * 32, kRowsSmem, st>>>(a);
+  else SL_CUDA(launch_stage2(emit_rows_kernel<false>, grid, kRowsWarps * 32, (size_t)kRowsSmem, st, a));
   count_launch();
   SL_CUDA(cudaGetLastError());
   return kOk;

@@ -67,7 +67,8 @@ int launch_emit_cloud(const int16_t* h, const int16_t* v, const uint8_t* white, 
 int launch_transpose_f2(const float* src, int rows, int cols, float* dst, cudaStream_t st);   // dst[c][r] = src[r][c], float2 entries
 // K2r: the emission with lane = row (transposed lens tables, see sl_cloud.cu); fp32 table mode, local cloud, W % 32 == 0
 int launch_emit_rows(const int16_t* h, const int16_t* v, const uint8_t* white, const SlCalib& calib, const float* cam_t,
-                     int cam_rows, const float* proj_t, int B, int H, int W, const void* ws, float* cloud, cudaStream_t st);
+                     int cam_rows, const float* proj_t, int B, int H, int W, const void* ws, float* cloud, cudaStream_t st,
+                     float* const* extra = nullptr, int n_extra = 0, int remote = 0);
 int launch_triangulate_points(const float* cam_pts, const float* proj_pts, long long N,
                               const SlCalib& calib, int precision, double* out, cudaStream_t st);
 size_t filter_workspace_bytes(long long N);

@@ -85,6 +85,7 @@ SIGNATURES = {
                                 _vp]),
     "sl_transpose_table": (_i, [_vp, _i, _i, _vp, _vp]),
     "sl_emit_cloud_rows": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sl_emit_cloud_rows_multi": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sl_emit_cloud_at": (_i, [_vp, _vp, _vp, C.POINTER(SlCalib), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "sl_exchange_push": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _i, _vp]),
     "sl_exchange_arrive": (_i, [_vp, C.c_uint32, _i, _vp]),

@@ -16,6 +16,7 @@ device-side placement.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -218,6 +219,8 @@ class CloudExchange:
         # only; row bands interleave per column and always use "emit"): emit locally, then sl_exchange_push copies
         # the rank's block with push_ctas CTAs -- the better choice when the next batch's compute can overlap it.
         self.transport, self.push_ctas = transport, int(push_ctas)
+        # the emission through the peer mappings: row-mapped kernel where it applies (SLB200_PEER_EMIT=tiles: always tiled)
+        self.peer_rows = os.environ.get("SLB200_PEER_EMIT", "tiles") == "rows"
         self._stage = None
         self.max_points = int(max_points)
         self.max_scans, self.max_width = int(max_scans), int(max_width)
@@ -284,6 +287,13 @@ class CloudExchange:
     def emit(self, buffers, white_rgb, calib_struct, precision, tables, b: int, h: int, w: int):
         from ._lib import check, lib
         from .api import _PREC, _ptr, _stream
+        if (self.peer_rows and tables is not None and precision == "fp32" and w % 32 == 0 and tables.proj_bt is not None
+                and (white_rgb is None or white_rgb.data_ptr() % 16 == 0)):
+            cam_tt, proj_tt = tables.transposed()
+            check(lib().sl_emit_cloud_rows_multi(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb),
+                                                 C.byref(calib_struct), _ptr(cam_tt), int(cam_tt.shape[1]), _ptr(proj_tt),
+                                                 b, h, w, _ptr(buffers.ws), self._clouds_c, len(self._cloud_ptr_list), _stream()))
+            return
         cam_t = _ptr(tables.cam) if tables is not None else None
         proj_t = _ptr(tables.projector_table(precision)) if tables is not None else None
         check(lib().sl_emit_cloud_multi(_ptr(buffers.h_idx), _ptr(buffers.v_idx), _ptr(white_rgb), C.byref(calib_struct),

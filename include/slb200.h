@@ -374,6 +374,12 @@ int sl_emit_cloud_rows(const int16_t* h_idx, const int16_t* v_idx, const uint8_t
                        const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
                        const void* workspace, float* cloud, void* stream);
 
+/* sl_emit_cloud_rows writing every record to n_clouds buffers (local or peer-mapped), as sl_emit_cloud_multi does for the
+ * tiled emission: clouds[0] = the gathering rank's cloud for a gather, all ranks' clouds for an all-gather. */
+int sl_emit_cloud_rows_multi(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb, const SlCalib* calib,
+                             const float* cam_rays_t, int cam_rows, const float* proj_bt_t, int B, int H, int W,
+                             const void* workspace, float* const* clouds, int n_clouds, void* stream);
+
 /* sl_emit_cloud into LOCAL memory for a workspace whose offsets sl_exchange_offsets_* has rebased: cloud is laid out
  * like the gathered cloud (capacity max_points records). */
 int sl_emit_cloud_at(const int16_t* h_idx, const int16_t* v_idx, const uint8_t* white_rgb,
