@@ -15,6 +15,13 @@ for cam in ((160, 96), (131, 67)):
             b = slb200.scan_to_cloud(fr, wh, calib, tables=t, precision=prec)
     # a batch: the offsets kernel's cross-strip / cross-scan published totals
     slb200.scan_to_cloud(torch.stack([fr, fr, fr]).contiguous(), torch.stack([wh, wh, wh]).contiguous(), calib, tables=tab)
+    # both emissions explicitly (the row-mapped one needs W % 32 == 0), the boxed compaction, a row band
+    if cam[0] % 32 == 0:
+        for em in ("tiles", "rows"):
+            slb200.scan_to_cloud(torch.stack([fr, fr]).contiguous(), torch.stack([wh, wh]).contiguous(), calib, tables=tab, emit=em)
+            slb200.scan_to_cloud(fr, None, calib, tables=tab, emit=em, box=0.4)
+            slb200.scan_to_cloud(fr[:, 32:], wh[32:].contiguous(), calib, tables=tab, emit=em, row0=32)
+    slb200.scan_to_cloud(fr, wh, calib, box=0.4)
     slb200.decode_stats(fr)
     b = slb200.scan_to_cloud(fr, wh, calib, tables=tab)
     hc, vc, hi, vi = slb200.decode_codes(fr)
