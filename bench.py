@@ -648,7 +648,7 @@ def run_single(args, torch, slb200, synth, dev, local):
         "config": config_n1(ring_n),
         "run": {"scans_per_step_per_gpu": ring_n, "step": f"one pass over the ring of {ring_n} resident scans",
                 "valid_fraction": vfrac, "lens": lens_name(primary_tables), "parallelism": "1 GPU",
-                "launch": f"CUDA graph per scan (decode, strip-prefix + column scan, emit: {kernels_per_scan} kernels); independent scans pipelined over {S} CUDA streams",
+                "launch": f"CUDA graph per scan (decode_tma_kernel, strip_prefix_kernel, emit_rows_kernel with the lens tables / emit_kernel with the in-kernel iteration: {kernels_per_scan} kernels); independent scans pipelined over {S} CUDA streams",
                 "decode_grid": f"one persistent CTA per SM, {sm_reserve} SMs left to the other streams' kernels"},
         "us_per_scan": ms_total / (K * ring_n) * 1e3,
         "scans_per_s": K * ring_n / (ms_total * 1e-3),
